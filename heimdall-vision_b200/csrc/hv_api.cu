@@ -1,0 +1,974 @@
+// hv_api.cu -- host side of the C ABI (include/heimdall_cuda.h): contexts, device scratch, pinned staging, streams,
+// batch orchestration, result marshalling.  Mirrors the reference's PyO3 layer (rust/heimdall-core/src/lib.rs:42-178)
+// at the granularity a Rust FFI crate would bind.  No CPU fallback anywhere: every result comes from the kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hv_common.cuh"
+
+using namespace hv;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&p), n * sizeof(T), cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf<uint8_t> in, gray, blur, mask;
+    DevBuf<uint16_t> gauss_tmp;
+    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount;
+    DevBuf<int32_t> labels;
+    DevBuf<hv_blob> blobs;
+    DevBuf<hv_defect> defects;
+    DevBuf<hv_frame_result> results;
+    PinBuf<hv_frame_result> h_results;
+    PinBuf<hv_defect> h_defects;
+    // state of the batch currently held by the slot
+    BatchView view{};
+    bool has_batch = false;
+    bool have_blur = false;
+    int c = 1;
+    const uint8_t *d_input = nullptr;  // device frames the batch was run on (for the gray debug copy, c == 1)
+    int64_t ticket = -1;
+    void release() {
+        in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release();
+        bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
+        fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
+        h_results.release(), h_defects.release();
+        if (done) cudaEventDestroy(done);
+        if (stream) cudaStreamDestroy(stream);
+        done = nullptr;
+        stream = nullptr;
+    }
+};
+
+}  // namespace
+
+struct hv_ctx {
+    int device = 0;
+    hv_config cfg{};
+    std::string err;
+    std::vector<Slot> slots;
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    hv_line_stats *d_stats = nullptr;
+    uint64_t launches = 0;
+    int64_t next_ticket = 1;
+    int next_slot = 1;
+    // profiling
+    cudaEvent_t prof_ev[HV_K_COUNT][2] = {};
+    bool prof_used[HV_K_COUNT] = {};
+    float prof_ms[HV_K_COUNT] = {};
+    // scratch for the single-frame utilities
+    DevBuf<uint8_t> u_a, u_b, u_c;
+    DevBuf<hv_center> u_centers;
+    DevBuf<hv_contour> u_contours;
+    DevBuf<uint32_t> u_count;
+};
+
+namespace {
+
+hv_status fail(hv_ctx *ctx, hv_status s, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return s;
+}
+
+hv_status fail_cuda(hv_ctx *ctx, cudaError_t e, const char *what) {
+    std::string m = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear the sticky-free error state
+    return fail(ctx, HV_ERR_CUDA, m);
+}
+
+#define HV_TRY_CUDA(ctx, expr)                                         \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return fail_cuda((ctx), _e, #expr);     \
+    } while (0)
+
+int clamp_threshold(double thr) {
+    // `threshold as i32` (detection.rs:186): truncating, saturating, NaN -> 0; then clamped to [-256, 256], beyond
+    // which the comparison `px < mean - c` is constant for u8 data anyway.
+    long long c;
+    if (!(thr == thr))
+        c = 0;
+    else if (thr >= 2147483647.0)
+        c = 2147483647LL;
+    else if (thr <= -2147483648.0)
+        c = -2147483648LL;
+    else
+        c = (long long)thr;
+    if (c > 256) c = 256;
+    if (c < -256) c = -256;
+    return (int)c;
+}
+
+int blob_cap_for(const hv_ctx *ctx, int h, int w) {
+    const long long max_possible = (long long)h * w / 2 + 1;
+    long long cap = ctx->cfg.max_blobs_per_frame > 0 ? ctx->cfg.max_blobs_per_frame : 131072;
+    return (int)std::min(cap, max_possible);
+}
+
+int defect_cap_for(const hv_ctx *ctx) { return ctx->cfg.max_defects_per_frame > 0 ? ctx->cfg.max_defects_per_frame : 256; }
+
+struct ProfScope {
+    hv_ctx *ctx;
+    int k;
+    cudaStream_t s;
+    ProfScope(hv_ctx *c, int kk, cudaStream_t ss) : ctx(c), k(kk), s(ss) {
+        if ((ctx->cfg.flags & HV_FLAG_PROFILE) && !ctx->prof_used[k]) cudaEventRecord(ctx->prof_ev[k][0], s);
+    }
+    ~ProfScope() {
+        if (ctx->cfg.flags & HV_FLAG_PROFILE) {
+            cudaEventRecord(ctx->prof_ev[k][1], s);
+            ctx->prof_used[k] = true;
+        }
+    }
+};
+
+// OpenCV's 8-bit fixed-point Gaussian kernel (getGaussianKernelBitExact + getGaussianKernelFixedPoint_ED, 8 fractional
+// bits): normalised double kernel, error-diffused rounding from the ends toward the centre, centre takes the rest.
+bool gaussian_kernel_q8(int n, double sigma, uint16_t *k16) {
+    if (n <= 0 || n > 31 || (n & 1) == 0) return false;
+    double kd[31];
+    const int n2 = (n - 1) / 2;
+    static const double f3[] = {0.25, 0.5, 0.25};
+    static const double f5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
+    static const double f7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+    static const double f9[] = {4.0 / 256, 13.0 / 256, 30.0 / 256, 51.0 / 256, 60.0 / 256,
+                                51.0 / 256, 30.0 / 256, 13.0 / 256, 4.0 / 256};
+    const double *fixed = nullptr;
+    if (sigma <= 0) fixed = n == 3 ? f3 : n == 5 ? f5 : n == 7 ? f7 : n == 9 ? f9 : nullptr;
+    if (sigma <= 0 && n == 1) {
+        kd[0] = 1.0;
+    } else if (fixed) {
+        for (int i = 0; i < n; i++) kd[i] = fixed[i];
+    } else {
+        const double sigmaX = sigma > 0 ? sigma : std::fma((double)n, 0.15, 0.35);
+        const double scale2X = -0.125 / (sigmaX * sigmaX);
+        double values[16];
+        double sum = 0.0;
+        for (int i = 0, x = 1 - n; i < n2; i++, x += 2) {
+            values[i] = std::exp((double)(x * x) * scale2X);
+            sum += values[i];
+        }
+        sum = sum * 2.0 + 1.0;
+        const double mul1 = 1.0 / sum;
+        for (int i = 0; i < n2; i++) kd[i] = kd[n - 1 - i] = values[i] * mul1;
+        kd[n2] = mul1;
+    }
+    double err = 0.0;
+    long long sum = 0;
+    for (int i = 0; i < n2; i++) {
+        const double adj = kd[i] * 256.0 + err;
+        const long long v0 = (long long)std::nearbyint(adj);
+        err = adj - (double)v0;
+        k16[i] = k16[n - 1 - i] = (uint16_t)v0;
+        sum += v0;
+    }
+    k16[n2] = (uint16_t)(256 - 2 * sum);
+    return true;
+}
+
+cudaStream_t sync_stream(hv_ctx *ctx) { return ctx->use_user_stream ? ctx->user_stream : ctx->slots[0].stream; }
+
+hv_status validate_shape(hv_ctx *ctx, int n, int h, int w, int c) {
+    if (n <= 0 || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "batch, height and width must be positive");
+    if (c != 1 && c != 3) return fail(ctx, HV_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: expected 3D array");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large (h*w must fit in i32)");
+    return HV_OK;
+}
+
+hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, size_t in_bytes, bool need_gray,
+                       bool need_blur, bool need_gauss, bool need_mask, bool need_labels) {
+    const size_t px = (size_t)n * h * w;
+    const int ww = (w + 31) / 32;
+    const size_t words = (size_t)n * h * ww;
+    if (need_in) HV_TRY_CUDA(ctx, s.in.reserve(in_bytes));
+    if (need_gray) HV_TRY_CUDA(ctx, s.gray.reserve(px));
+    if (need_blur) HV_TRY_CUDA(ctx, s.blur.reserve(px));
+    if (need_gauss) HV_TRY_CUDA(ctx, s.gauss_tmp.reserve(px));
+    if (need_mask) HV_TRY_CUDA(ctx, s.mask.reserve(px));
+    if (need_labels) HV_TRY_CUDA(ctx, s.labels.reserve(px));
+    HV_TRY_CUDA(ctx, s.bits.reserve(words));
+    HV_TRY_CUDA(ctx, s.bits_tmp.reserve(words));
+    HV_TRY_CUDA(ctx, s.rootbits.reserve(words));
+    HV_TRY_CUDA(ctx, s.rankbase.reserve(words));
+    HV_TRY_CUDA(ctx, s.ncomp.reserve(n));
+    HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
+    HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
+    HV_TRY_CUDA(ctx, s.defects.reserve((size_t)n * defect_cap_for(ctx)));
+    HV_TRY_CUDA(ctx, s.results.reserve(n));
+    HV_TRY_CUDA(ctx, s.h_results.reserve(n));
+    HV_TRY_CUDA(ctx, s.h_defects.reserve((size_t)n * defect_cap_for(ctx)));
+    return HV_OK;
+}
+
+// Enqueue the whole detect pipeline for frames already on the device.  No host synchronisation.
+hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_frames, int n, int h, int w, int c,
+                           size_t row_stride, size_t frame_stride, const hv_params &pr, uint8_t *d_mask,
+                           int32_t *d_labels, bool want_blur) {
+    if (row_stride == 0) row_stride = (size_t)w * c;
+    if (frame_stride == 0) frame_stride = row_stride * h;
+    if (row_stride < (size_t)w * c || frame_stride < row_stride * (size_t)h)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "strides smaller than the frame");
+    if (pr.blur_mode != HV_BLUR_BOX && pr.blur_mode != HV_BLUR_GAUSSIAN && pr.blur_mode != HV_BLUR_NONE)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "unknown blur_mode");
+    if (pr.morph_open_k < 0 || pr.morph_open_k > 31 || pr.morph_close_k < 0 || pr.morph_close_k > 31)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "morphology kernel size must be in [0, 31]");
+    const bool fused_box = pr.blur_mode == HV_BLUR_BOX && pr.blur_ksize / 2 == 2;
+    const bool box_other = pr.blur_mode == HV_BLUR_BOX && !fused_box && pr.blur_ksize / 2 > 0;
+    const bool gauss = pr.blur_mode == HV_BLUR_GAUSSIAN;
+    uint16_t gk[32];
+    if (gauss && !gaussian_kernel_q8(pr.blur_ksize, pr.gauss_sigma, gk))
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "Gaussian kernel size must be odd and in [1, 31]");
+    const bool separate_blur = box_other || gauss;
+    const bool morph = pr.morph_open_k > 0 || pr.morph_close_k > 0;
+
+    hv_status rs = reserve_slot(ctx, s, n, h, w, false, 0, c == 3, separate_blur || want_blur, gauss, d_mask == nullptr,
+                                d_labels == nullptr);
+    if (rs != HV_OK) return rs;
+
+    BatchView b{};
+    b.n = n, b.h = h, b.w = w, b.ww = (w + 31) / 32;
+    if (c == 3) {
+        ProfScope ps(ctx, HV_K_GRAY, st);
+        HV_TRY_CUDA(ctx, launch_gray3(d_frames, n, h, w, row_stride, frame_stride, s.gray.p, st));
+        ctx->launches++;
+        b.gray = s.gray.p;
+        b.gray_row_stride = w;
+        b.gray_frame_stride = (size_t)h * w;
+    } else {
+        b.gray = d_frames;
+        b.gray_row_stride = row_stride;
+        b.gray_frame_stride = frame_stride;
+    }
+    b.blur = s.blur.p;
+    b.mask = d_mask ? d_mask : s.mask.p;
+    b.bits = s.bits.p;
+    b.bits_tmp = s.bits_tmp.p;
+    b.labels = d_labels ? d_labels : s.labels.p;
+    b.rootbits = s.rootbits.p;
+    b.rankbase = s.rankbase.p;
+    b.ncomp = s.ncomp.p;
+    b.fgcount = s.fgcount.p;
+    b.blobs = s.blobs.p;
+    b.blob_cap = blob_cap_for(ctx, h, w);
+    b.defects = s.defects.p;
+    b.defect_cap = defect_cap_for(ctx);
+    b.results = s.results.p;
+    b.stats = ctx->d_stats;
+
+    PreprocessParams pp{};
+    pp.c_thresh = clamp_threshold(pr.threshold);
+    pp.inverse = 1;
+    pp.write_mask = morph ? 0 : 1;
+    pp.init_labels = morph ? 0 : 1;
+    BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
+    if (separate_blur) {
+        if (gauss) {
+            // tightly packed gray required by the simple Gaussian kernels
+            if (c == 1 && (b.gray_row_stride != (size_t)w || b.gray_frame_stride != (size_t)h * w))
+                return fail(ctx, HV_ERR_UNSUPPORTED, "Gaussian blur needs tightly packed frames");
+            ProfScope ps(ctx, HV_K_PREPROCESS, st);
+            HV_TRY_CUDA(ctx, launch_gaussian_blur(b.gray, n, h, w, gk, pr.blur_ksize, s.blur.p, s.gauss_tmp.p, st));
+            ctx->launches += 2;
+        } else {
+            if (c == 1 && (b.gray_row_stride != (size_t)w || b.gray_frame_stride != (size_t)h * w))
+                return fail(ctx, HV_ERR_UNSUPPORTED, "non-default box radius needs tightly packed frames");
+            for (int f = 0; f < n; f++) {
+                HV_TRY_CUDA(ctx, launch_box_blur_generic(b.gray + (size_t)f * h * w, h, w, 1, pr.blur_ksize / 2,
+                                                         s.blur.p + (size_t)f * h * w, st));
+                ctx->launches++;
+            }
+        }
+        kb.gray = s.blur.p;
+        kb.gray_row_stride = w;
+        kb.gray_frame_stride = (size_t)h * w;
+        pp.blur_radius = 0;
+        pp.write_blur = 0;
+    } else {
+        pp.blur_radius = fused_box ? 2 : 0;
+        pp.write_blur = want_blur ? 1 : 0;
+    }
+    {
+        ProfScope ps(ctx, HV_K_PREPROCESS, st);
+        HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
+        ctx->launches++;
+    }
+    if (morph) {
+        ProfScope ps(ctx, HV_K_MORPH, st);
+        int nl = 0;
+        HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
+        HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b, st));
+        ctx->launches += nl + 1;
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_MERGE, st);
+        HV_TRY_CUDA(ctx, launch_ccl_merge(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_FLATTEN, st);
+        HV_TRY_CUDA(ctx, launch_ccl_flatten(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_SCAN, st);
+        HV_TRY_CUDA(ctx, launch_ccl_scan(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_LABEL, st);
+        HV_TRY_CUDA(ctx, launch_ccl_label(b, st));
+    }
+    ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
+    {
+        ProfScope ps(ctx, HV_K_SCORE, st);
+        HV_TRY_CUDA(ctx, launch_score(b, sp, st));
+    }
+    ctx->launches += 5;
+    s.view = b;
+    s.has_batch = true;
+    s.have_blur = separate_blur || want_blur;
+    s.c = c;
+    s.d_input = d_frames;
+    return HV_OK;
+}
+
+hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
+    const BatchView &b = s.view;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_results.p, b.results, sizeof(hv_frame_result) * b.n, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_defects.p, b.defects, sizeof(hv_defect) * (size_t)b.n * b.defect_cap,
+                                     cudaMemcpyDeviceToHost, st));
+    return HV_OK;
+}
+
+// After the stream has been synchronised: compact the per-frame defect blocks into the caller's arrays.
+hv_status unpack_results(hv_ctx *ctx, Slot &s, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                         size_t *n_total) {
+    const BatchView &b = s.view;
+    size_t off = 0;
+    hv_status rc = HV_OK;
+    for (int f = 0; f < b.n; f++) {
+        hv_frame_result r = s.h_results.p[f];
+        const hv_defect *src = s.h_defects.p + (size_t)f * b.defect_cap;
+        uint32_t nd = r.n_defects;
+        if (r.status != HV_OK) rc = HV_ERR_CAPACITY;
+        if (off + nd > defects_cap) {
+            nd = (uint32_t)(defects_cap > off ? defects_cap - off : 0);
+            r.status = HV_ERR_CAPACITY;
+            rc = HV_ERR_CAPACITY;
+        }
+        r.defects_offset = (uint32_t)off;
+        if (defects && nd) std::memcpy(defects + off, src, sizeof(hv_defect) * nd);
+        r.n_defects = nd;
+        off += nd;
+        if (results) results[f] = r;
+    }
+    if (n_total) *n_total = off;
+    if (rc != HV_OK)
+        ctx->err = "capacity exceeded: more components or defects than max_blobs_per_frame / max_defects_per_frame / "
+                   "defects_cap (see per-frame status)";
+    return rc;
+}
+
+hv_status copy_debug(hv_ctx *ctx, Slot &s, cudaStream_t st, const hv_debug_outputs *dbg) {
+    if (!dbg) return HV_OK;
+    const BatchView &b = s.view;
+    const size_t px = (size_t)b.n * b.h * b.w;
+    if (dbg->gray)
+        HV_TRY_CUDA(ctx, cudaMemcpy2DAsync(dbg->gray, b.w, b.gray, b.gray_row_stride, b.w, (size_t)b.n * b.h,
+                                           cudaMemcpyDeviceToHost, st));
+    if (dbg->blur) {
+        if (!s.have_blur) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "blur intermediate was not kept for this batch");
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(dbg->blur, s.blur.p, px, cudaMemcpyDeviceToHost, st));
+    }
+    if (dbg->mask) HV_TRY_CUDA(ctx, cudaMemcpyAsync(dbg->mask, b.mask, px, cudaMemcpyDeviceToHost, st));
+    if (dbg->labels)
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(dbg->labels, b.labels, px * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (dbg->blobs) {
+        const size_t stride = dbg->blobs_stride ? dbg->blobs_stride : (size_t)b.blob_cap;
+        const size_t rows = std::min(stride, (size_t)b.blob_cap);
+        HV_TRY_CUDA(ctx, cudaMemcpy2DAsync(dbg->blobs, stride * sizeof(hv_blob), b.blobs, (size_t)b.blob_cap * sizeof(hv_blob),
+                                           rows * sizeof(hv_blob), b.n, cudaMemcpyDeviceToHost, st));
+    }
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
+hv_status upload_frames(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *frames, int n, int h, int w, int c,
+                        size_t row_stride, size_t frame_stride) {
+    const size_t row_bytes = (size_t)w * c;
+    if (row_stride == 0) row_stride = row_bytes;
+    if (frame_stride == 0) frame_stride = row_stride * h;
+    if (row_stride < row_bytes || frame_stride < row_stride * (size_t)h)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "strides smaller than the frame");
+    HV_TRY_CUDA(ctx, s.in.reserve((size_t)n * h * row_bytes));
+    if (row_stride == row_bytes && frame_stride == row_bytes * h) {
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, frames, (size_t)n * h * row_bytes, cudaMemcpyHostToDevice, st));
+    } else if (frame_stride == row_stride * h) {
+        HV_TRY_CUDA(ctx, cudaMemcpy2DAsync(s.in.p, row_bytes, frames, row_stride, row_bytes, (size_t)n * h,
+                                           cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < n; f++)
+            HV_TRY_CUDA(ctx, cudaMemcpy2DAsync(s.in.p + (size_t)f * h * row_bytes, row_bytes, frames + f * frame_stride,
+                                               row_stride, row_bytes, h, cudaMemcpyHostToDevice, st));
+    }
+    return HV_OK;
+}
+
+void prof_reset(hv_ctx *ctx) {
+    for (int k = 0; k < HV_K_COUNT; k++) ctx->prof_used[k] = false;
+}
+
+void prof_collect(hv_ctx *ctx) {
+    if (!(ctx->cfg.flags & HV_FLAG_PROFILE)) return;
+    for (int k = 0; k < HV_K_COUNT; k++) {
+        ctx->prof_ms[k] = 0.f;
+        if (ctx->prof_used[k]) cudaEventElapsedTime(&ctx->prof_ms[k], ctx->prof_ev[k][0], ctx->prof_ev[k][1]);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t hv_abi_version(void) { return HV_ABI_VERSION; }
+const char *hv_version(void) { return "heimdall-cuda 0.1.0 (sm_100a)"; }
+
+const char *hv_status_string(hv_status s) {
+    switch (s) {
+        case HV_OK: return "ok";
+        case HV_ERR_INVALID_DIMENSIONS: return "Invalid image dimensions: expected 3D array";
+        case HV_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case HV_ERR_CUDA: return "CUDA error";
+        case HV_ERR_CAPACITY: return "capacity exceeded";
+        case HV_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case HV_ERR_UNSUPPORTED: return "unsupported";
+        case HV_ERR_CHANNELS: return "stage requires a 1-channel image";
+        case HV_ERR_BAD_TICKET: return "unknown or already consumed ticket";
+        default: return "unknown status";
+    }
+}
+
+int32_t hv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void hv_params_default(hv_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->min_size = 10.0;       // lib.rs:106
+    p->max_size = 3000.0;     // lib.rs:107
+    p->threshold = 25.0;      // lib.rs:108
+    p->min_confidence = 0.3;  // detection.rs:298
+    p->gauss_sigma = 0.0;
+    p->blur_mode = HV_BLUR_BOX;
+    p->blur_ksize = 5;  // detection.rs:163 (radius 2)
+    p->morph_open_k = 0;
+    p->morph_close_k = 0;
+}
+
+void hv_config_default(hv_config *c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+}
+
+hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
+    if (!out) return HV_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                         "); this backend has no CPU fallback";
+        return HV_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "device index out of range";
+        return HV_ERR_INVALID_ARGUMENT;
+    }
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return HV_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+        return HV_ERR_NO_DEVICE;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return HV_ERR_CUDA;
+    }
+    hv_ctx *ctx = new (std::nothrow) hv_ctx();
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    ctx->device = device;
+    if (cfg) ctx->cfg = *cfg;
+    const int nslots = 1 + (ctx->cfg.num_slots > 0 ? ctx->cfg.num_slots : 3);  // slot 0 = synchronous entry points
+    ctx->slots.resize(nslots);
+    for (auto &s : ctx->slots) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+            g_create_error = "stream/event creation failed";
+            hv_destroy(ctx);
+            return HV_ERR_CUDA;
+        }
+    }
+    for (int k = 0; k < HV_K_COUNT; k++)
+        for (int j = 0; j < 2; j++) cudaEventCreate(&ctx->prof_ev[k][j]);
+    if (cudaMalloc(reinterpret_cast<void **>(&ctx->d_stats), sizeof(hv_line_stats)) != cudaSuccess ||
+        cudaMemset(ctx->d_stats, 0, sizeof(hv_line_stats)) != cudaSuccess) {
+        g_create_error = "stats allocation failed";
+        hv_destroy(ctx);
+        return HV_ERR_CUDA;
+    }
+    *out = ctx;
+    return HV_OK;
+}
+
+void hv_destroy(hv_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : ctx->slots) s.release();
+    for (int k = 0; k < HV_K_COUNT; k++)
+        for (int j = 0; j < 2; j++)
+            if (ctx->prof_ev[k][j]) cudaEventDestroy(ctx->prof_ev[k][j]);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    ctx->u_a.release(), ctx->u_b.release(), ctx->u_c.release();
+    ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release();
+    delete ctx;
+}
+
+const char *hv_last_error(const hv_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    ctx->user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->use_user_stream = cuda_stream != nullptr;
+    return HV_OK;
+}
+
+void *hv_host_alloc(hv_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->err = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void hv_host_free(hv_ctx *ctx, void *p) {
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+
+hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                            size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
+                            int32_t *d_labels) {
+    if (!ctx || !d_frames) return HV_ERR_INVALID_ARGUMENT;
+    hv_status rs = validate_shape(ctx, n, h, w, c);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    hv_params pr;
+    if (params)
+        pr = *params;
+    else
+        hv_params_default(&pr);
+    prof_reset(ctx);
+    return enqueue_pipeline(ctx, ctx->slots[0], sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr, d_mask,
+                            d_labels, (ctx->cfg.flags & 4u) != 0);
+}
+
+hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                           size_t *n_defects_total) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    Slot &s = ctx->slots[0];
+    if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = sync_stream(ctx);
+    hv_status rs = enqueue_readback(ctx, s, st);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    prof_collect(ctx);
+    return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
+}
+
+hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    Slot &s = ctx->slots[0];
+    if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    return copy_debug(ctx, s, sync_stream(ctx), debug);
+}
+
+hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                                 size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
+                                 int32_t *d_labels, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                                 size_t *n_defects_total) {
+    hv_status rs = hv_enqueue_device(ctx, d_frames, n, h, w, c, row_stride, frame_stride, params, d_mask, d_labels);
+    if (rs != HV_OK) return rs;
+    return hv_fetch_results(ctx, results, defects, defects_cap, n_defects_total);
+}
+
+hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                          size_t row_stride, size_t frame_stride, const hv_params *params, hv_frame_result *results,
+                          hv_defect *defects, size_t defects_cap, size_t *n_defects_total,
+                          const hv_debug_outputs *debug) {
+    if (!ctx || !frames) return HV_ERR_INVALID_ARGUMENT;
+    hv_status rs = validate_shape(ctx, n, h, w, c);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    hv_params pr;
+    if (params)
+        pr = *params;
+    else
+        hv_params_default(&pr);
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = sync_stream(ctx);
+    rs = upload_frames(ctx, s, st, frames, n, h, w, c, row_stride, frame_stride);
+    if (rs != HV_OK) return rs;
+    prof_reset(ctx);
+    const bool want_blur = (debug && debug->blur) || (ctx->cfg.flags & 4u);
+    rs = enqueue_pipeline(ctx, s, st, s.in.p, n, h, w, c, 0, 0, pr, nullptr, nullptr, want_blur);
+    if (rs != HV_OK) return rs;
+    rs = enqueue_readback(ctx, s, st);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    prof_collect(ctx);
+    hv_status rc = unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
+    hv_status rd = copy_debug(ctx, s, st, debug);
+    return rd != HV_OK ? rd : rc;
+}
+
+hv_status hv_submit(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, int32_t w, int32_t c, size_t row_stride,
+                    size_t frame_stride, const hv_params *params, int64_t *ticket) {
+    if (!ctx || !frames || !ticket) return HV_ERR_INVALID_ARGUMENT;
+    hv_status rs = validate_shape(ctx, n, h, w, c);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    hv_params pr;
+    if (params)
+        pr = *params;
+    else
+        hv_params_default(&pr);
+    // find a free asynchronous slot (slots 1..)
+    int pick = -1;
+    const int nslots = (int)ctx->slots.size();
+    for (int k = 0; k < nslots - 1; k++) {
+        const int idx = 1 + (ctx->next_slot - 1 + k) % (nslots - 1);
+        if (ctx->slots[idx].ticket < 0) {
+            pick = idx;
+            break;
+        }
+    }
+    if (pick < 0) return fail(ctx, HV_ERR_CAPACITY, "all slots are in flight: call hv_wait first");
+    ctx->next_slot = 1 + (pick % (nslots - 1));
+    Slot &s = ctx->slots[pick];
+    rs = upload_frames(ctx, s, s.stream, frames, n, h, w, c, row_stride, frame_stride);
+    if (rs != HV_OK) return rs;
+    rs = enqueue_pipeline(ctx, s, s.stream, s.in.p, n, h, w, c, 0, 0, pr, nullptr, nullptr, false);
+    if (rs != HV_OK) return rs;
+    rs = enqueue_readback(ctx, s, s.stream);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+    s.ticket = ctx->next_ticket++;
+    *ticket = s.ticket;
+    return HV_OK;
+}
+
+hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                  size_t *n_defects_total) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    for (size_t i = 1; i < ctx->slots.size(); i++) {
+        Slot &s = ctx->slots[i];
+        if (s.ticket == ticket && ticket > 0) {
+            HV_TRY_CUDA(ctx, cudaEventSynchronize(s.done));
+            s.ticket = -1;
+            return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
+        }
+    }
+    return fail(ctx, HV_ERR_BAD_TICKET, "unknown or already consumed ticket");
+}
+
+// ---- single-frame utilities ---------------------------------------------------------------------------------------
+hv_status hv_preprocess_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, int32_t grayscale,
+                              int32_t blur_size, uint8_t *out) {
+    if (!ctx || !img || !out || h <= 0 || w <= 0 || c <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (grayscale && c < 3)
+        return fail(ctx, HV_ERR_INVALID_DIMENSIONS,
+                    "Invalid image dimensions: grayscale conversion indexes channels 0..2 (processing.rs:51-53)");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    const size_t in_bytes = (size_t)h * w * c;
+    const int och = grayscale ? 1 : c;
+    const size_t out_bytes = (size_t)h * w * och;
+    HV_TRY_CUDA(ctx, ctx->u_a.reserve(in_bytes));
+    HV_TRY_CUDA(ctx, ctx->u_b.reserve(out_bytes));
+    HV_TRY_CUDA(ctx, ctx->u_c.reserve(out_bytes));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->u_a.p, img, in_bytes, cudaMemcpyHostToDevice, st));
+    const uint8_t *cur = ctx->u_a.p;
+    if (grayscale) {
+        HV_TRY_CUDA(ctx, launch_gray_first3(ctx->u_a.p, h, w, c, ctx->u_b.p, st));
+        ctx->launches++;
+        cur = ctx->u_b.p;
+    }
+    if (blur_size > 0) {
+        HV_TRY_CUDA(ctx, launch_box_blur_generic(cur, h, w, och, blur_size / 2, ctx->u_c.p, st));
+        ctx->launches++;
+        cur = ctx->u_c.p;
+    }
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(out, cur, out_bytes, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
+hv_status hv_apply_threshold(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, uint8_t threshold_value,
+                             int32_t adaptive, int32_t inverse, uint8_t *out) {
+    if (!ctx || !img || !out || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (c != 1) return fail(ctx, HV_ERR_CHANNELS, "Image processing error: Thresholding requires a grayscale image");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px, false, false, false, true, true);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, img, px, cudaMemcpyHostToDevice, st));
+    if (adaptive) {
+        BatchView b{};
+        b.n = 1, b.h = h, b.w = w, b.ww = (w + 31) / 32;
+        b.gray = s.in.p, b.gray_row_stride = w, b.gray_frame_stride = px;
+        b.mask = s.mask.p, b.labels = s.labels.p, b.bits = s.bits.p;
+        PreprocessParams pp{};
+        pp.c_thresh = 2;  // processing.rs:134
+        pp.blur_radius = 0;
+        pp.write_mask = 1;
+        pp.init_labels = 0;
+        pp.inverse = inverse ? 1 : 0;
+        HV_TRY_CUDA(ctx, launch_preprocess(b, pp, s.bits.p, st));
+    } else {
+        HV_TRY_CUDA(ctx, launch_threshold_generic(s.in.p, h, w, 0, threshold_value, inverse, s.mask.p, st));
+    }
+    ctx->launches++;
+    s.has_batch = false;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(out, s.mask.p, px, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
+static hv_status run_ccl_only(hv_ctx *ctx, Slot &s, cudaStream_t st, BatchView &b) {
+    HV_TRY_CUDA(ctx, launch_ccl_merge(b, st));
+    HV_TRY_CUDA(ctx, launch_ccl_flatten(b, st));
+    HV_TRY_CUDA(ctx, launch_ccl_scan(b, st));
+    HV_TRY_CUDA(ctx, launch_ccl_label(b, st));
+    ctx->launches += 4;
+    (void)s;
+    return HV_OK;
+}
+
+static void fill_view(hv_ctx *ctx, Slot &s, BatchView &b, int h, int w) {
+    b.n = 1, b.h = h, b.w = w, b.ww = (w + 31) / 32;
+    b.mask = s.mask.p, b.bits = s.bits.p, b.bits_tmp = s.bits_tmp.p, b.labels = s.labels.p;
+    b.rootbits = s.rootbits.p, b.rankbase = s.rankbase.p, b.ncomp = s.ncomp.p, b.fgcount = s.fgcount.p;
+    b.blobs = s.blobs.p, b.blob_cap = blob_cap_for(ctx, h, w);
+    b.defects = s.defects.p, b.defect_cap = defect_cap_for(ctx);
+    b.results = s.results.p, b.stats = ctx->d_stats;
+}
+
+hv_status hv_find_contours(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, double min_area,
+                           double max_area, hv_contour *contours, size_t cap, size_t *n_contours, int32_t *labels) {
+    if (!ctx || !img || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (c != 1)
+        return fail(ctx, HV_ERR_CHANNELS, "Detection error: Contour detection requires a grayscale or binary image");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px, false, false, false, true, true);
+    if (rs != HV_OK) return rs;
+    BatchView b{};
+    fill_view(ctx, s, b, h, w);
+    const int ccap = (int)std::min<size_t>(cap, (size_t)b.blob_cap);
+    HV_TRY_CUDA(ctx, ctx->u_contours.reserve(std::max(ccap, 1)));
+    HV_TRY_CUDA(ctx, ctx->u_count.reserve(1));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, img, px, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, launch_bits_from_gt127(s.in.p, 1, h, w, b.ww, b.bits, st));
+    HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b, st));
+    ctx->launches += 2;
+    rs = run_ccl_only(ctx, s, st, b);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, launch_collect_contours(b, min_area, max_area, ctx->u_contours.p, ctx->u_count.p, ccap, st));
+    ctx->launches++;
+    uint32_t cnt = 0, ncomp = 0;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->u_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(&ncomp, b.ncomp, sizeof(ncomp), cudaMemcpyDeviceToHost, st));
+    if (labels) HV_TRY_CUDA(ctx, cudaMemcpyAsync(labels, b.labels, px * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    s.has_batch = false;
+    const uint32_t ncopy = std::min<uint32_t>(cnt, (uint32_t)ccap);
+    if (contours && ncopy)
+        HV_TRY_CUDA(ctx, cudaMemcpy(contours, ctx->u_contours.p, sizeof(hv_contour) * ncopy, cudaMemcpyDeviceToHost));
+    if (n_contours) *n_contours = ncopy;
+    if (ncomp > (uint32_t)b.blob_cap || cnt > (uint32_t)ccap)
+        return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more contours than max_blobs_per_frame / cap");
+    return HV_OK;
+}
+
+hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, int32_t pipeline,
+                           uint8_t *out_hw3, hv_center *contours, size_t cap, size_t *n_contours) {
+    if (!ctx || !img || !out_hw3 || h <= 0 || w <= 0 || c <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (pipeline != HV_PIPELINE_BASIC && pipeline != HV_PIPELINE_CONTAMINATION)
+        return fail(ctx, HV_ERR_UNSUPPORTED, "Unsupported pipeline type");
+    if (c < 3)
+        return fail(ctx, HV_ERR_INVALID_DIMENSIONS,
+                    "Invalid image dimensions: the pipelines index channels 0..2 (processing.rs:195-197,259-261)");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px * c, true, true, false, true, true);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, ctx->u_a.reserve(px * 3));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, img, px * c, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, launch_gray_first3(s.in.p, h, w, c, s.gray.p, st));
+    ctx->launches++;
+    BatchView b{};
+    fill_view(ctx, s, b, h, w);
+    b.gray = s.gray.p, b.gray_row_stride = w, b.gray_frame_stride = px;
+    size_t n_out = 0;
+    hv_status rc = HV_OK;
+    if (pipeline == HV_PIPELINE_BASIC) {
+        HV_TRY_CUDA(ctx, launch_box_blur_generic(s.gray.p, h, w, 1, 2, s.blur.p, st));
+        HV_TRY_CUDA(ctx, launch_threshold_generic(s.blur.p, h, w, 0, 127, 0, s.mask.p, st));
+        HV_TRY_CUDA(ctx, launch_visualise(s.mask.p, h, w, nullptr, 0, ctx->u_a.p, st));
+        ctx->launches += 3;
+    } else {
+        PreprocessParams pp{};
+        pp.c_thresh = 15;  // processing.rs:293
+        pp.blur_radius = 2;
+        pp.write_mask = 1;
+        pp.init_labels = 1;
+        pp.inverse = 1;
+        HV_TRY_CUDA(ctx, launch_preprocess(b, pp, b.bits, st));
+        ctx->launches++;
+        rs = run_ccl_only(ctx, s, st, b);
+        if (rs != HV_OK) return rs;
+        const int ccap = b.blob_cap;
+        HV_TRY_CUDA(ctx, ctx->u_centers.reserve(ccap));
+        HV_TRY_CUDA(ctx, ctx->u_count.reserve(1));
+        HV_TRY_CUDA(ctx, launch_collect_centers(b, 3u, ctx->u_centers.p, ctx->u_count.p, ccap, st));  // processing.rs:355
+        ctx->launches++;
+        uint32_t cnt = 0, ncomp = 0;
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->u_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(&ncomp, b.ncomp, sizeof(ncomp), cudaMemcpyDeviceToHost, st));
+        HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ncomp > (uint32_t)b.blob_cap) rc = fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: raise max_blobs_per_frame");
+        const uint32_t ndraw = std::min<uint32_t>(cnt, (uint32_t)ccap);
+        HV_TRY_CUDA(ctx, launch_visualise(s.mask.p, h, w, ctx->u_centers.p, (int)ndraw, ctx->u_a.p, st));
+        ctx->launches += ndraw ? 2 : 1;
+        n_out = std::min<size_t>(ndraw, cap);
+        if (ndraw > cap) rc = fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: contours array too small");
+        if (contours && n_out)
+            HV_TRY_CUDA(ctx, cudaMemcpyAsync(contours, ctx->u_centers.p, sizeof(hv_center) * n_out, cudaMemcpyDeviceToHost, st));
+    }
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(out_hw3, ctx->u_a.p, px * 3, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    s.has_batch = false;
+    if (n_contours) *n_contours = n_out;
+    return rc;
+}
+
+// ---- line statistics ----------------------------------------------------------------------------------------------
+hv_status hv_stats_get(hv_ctx *ctx, hv_line_stats *out) {
+    if (!ctx || !out) return HV_ERR_INVALID_ARGUMENT;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
+    HV_TRY_CUDA(ctx, cudaMemcpy(out, ctx->d_stats, sizeof(*out), cudaMemcpyDeviceToHost));
+    return HV_OK;
+}
+
+hv_status hv_stats_reset(hv_ctx *ctx) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
+    HV_TRY_CUDA(ctx, cudaMemset(ctx->d_stats, 0, sizeof(hv_line_stats)));
+    return HV_OK;
+}
+
+uint64_t *hv_stats_device_ptr(hv_ctx *ctx) { return ctx ? reinterpret_cast<uint64_t *>(ctx->d_stats) : nullptr; }
+
+uint64_t hv_launch_count(const hv_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+hv_status hv_profile_get(hv_ctx *ctx, float ms[HV_K_COUNT]) {
+    if (!ctx || !ms) return HV_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < HV_K_COUNT; k++) ms[k] = ctx->prof_ms[k];
+    return HV_OK;
+}
+
+const char *hv_kernel_name(int32_t k) {
+    static const char *names[HV_K_COUNT] = {"gray3",       "preprocess_mask", "morph",     "ccl_merge",
+                                            "ccl_flatten", "ccl_scan",        "ccl_label", "score"};
+    return (k >= 0 && k < HV_K_COUNT) ? names[k] : "?";
+}
+
+}  // extern "C"

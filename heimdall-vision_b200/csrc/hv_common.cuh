@@ -1,0 +1,85 @@
+// hv_common.cuh -- shared device/host declarations for the sm_100a backend (internal; the public ABI is
+// include/heimdall_cuda.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/heimdall_cuda.h"
+
+namespace hv {
+
+constexpr int kAdaptHalf = 5;  // 11x11 adaptive window (detection.rs:185)
+
+// Geometry of one batch resident on the device. All arrays are tightly packed, frame-major.
+struct BatchView {
+    int n, h, w;
+    int ww;                    // bitmask words per row = ceil(w / 32)
+    const uint8_t *gray;       // n*h*w  (the input itself when c == 1 and tightly packed)
+    size_t gray_row_stride;    // bytes
+    size_t gray_frame_stride;  // bytes
+    uint8_t *blur;             // n*h*w, optional (debug / non-fused blur modes)
+    uint8_t *mask;             // n*h*w  final mask {0,255}
+    uint32_t *bits;            // n*h*ww bit-packed final mask, bit x&31 of word x>>5
+    uint32_t *bits_tmp;        // scratch for morphology
+    int32_t *labels;           // n*h*w  union-find parents (+1) during CCL, canonical labels afterwards
+    uint32_t *rootbits;        // n*h*ww
+    uint32_t *rankbase;        // n*h*ww root counts -> exclusive prefix
+    uint32_t *ncomp;           // n
+    uint32_t *fgcount;         // n
+    hv_blob *blobs;            // n*blob_cap
+    int blob_cap;
+    hv_defect *defects;        // n*defect_cap
+    int defect_cap;
+    hv_frame_result *results;  // n
+    hv_line_stats *stats;      // 1
+};
+
+struct PreprocessParams {
+    int c_thresh;      // clamp(threshold as i32, -256, 256)
+    int blur_radius;   // 0 = input is already blurred / no blur, 2 = fused 5x5 box
+    int write_blur;    // also materialise the blurred image (debug)
+    int write_mask;    // write the u8 mask (0 when morphology follows and rewrites it)
+    int init_labels;   // write label zeros + word-run-start parents (0 when morphology follows)
+    int inverse;       // 1: 255 if px < mean - c (detection path); 0: 255 if px > mean - c
+};
+
+struct ScoreParams {
+    double min_size, max_size, min_confidence;
+};
+
+#define HV_CUDA_TRY(expr)                         \
+    do {                                          \
+        cudaError_t _e = (expr);                  \
+        if (_e != cudaSuccess) return _e;         \
+    } while (0)
+
+// ---- launch wrappers (one per kernel; each returns the launch status) -----------------------------------
+cudaError_t launch_gray3(const uint8_t *d_img, int n, int h, int w, size_t row_stride, size_t frame_stride,
+                         uint8_t *d_gray, cudaStream_t s);
+cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s);
+cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
+cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
+cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
+cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);
+cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s);
+cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s);
+cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s);
+
+// generic single-frame stage kernels (python-facing utilities, not the hot path)
+cudaError_t launch_box_blur_generic(const uint8_t *src, int h, int w, int nch, int radius, uint8_t *dst,
+                                    cudaStream_t s);
+cudaError_t launch_threshold_generic(const uint8_t *src, int h, int w, int adaptive, int c_or_thr, int inverse,
+                                     uint8_t *dst, cudaStream_t s);
+cudaError_t launch_gaussian_blur(const uint8_t *src, int n, int h, int w, const uint16_t *k_q8_host, int ksize,
+                                 uint8_t *dst, uint16_t *tmp_rows, cudaStream_t s);
+cudaError_t launch_bits_from_gt127(const uint8_t *src, int n, int h, int w, int ww, uint32_t *bits, cudaStream_t s);
+cudaError_t launch_visualise(const uint8_t *mask, int h, int w, const hv_center *d_centers, int n_centers,
+                             uint8_t *out_hw3, cudaStream_t s);
+cudaError_t launch_gray_first3(const uint8_t *d_img, int h, int w, int c, uint8_t *d_gray, cudaStream_t s);
+cudaError_t launch_collect_centers(const BatchView &b, uint32_t min_area, hv_center *d_centers, uint32_t *d_count,
+                                   int cap, cudaStream_t s);
+cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
+                                    uint32_t *d_count, int cap, cudaStream_t s);
+
+}  // namespace hv

@@ -1,0 +1,282 @@
+// k_ccl.cu -- K2..K5: 4-connected component labelling + per-blob statistics on the bit-packed mask.
+//
+// Reference semantics (rust/heimdall-core/src/detection.rs:215-245, same loops at :58-88 and processing.rs:322-353):
+// a raster scan starts a DFS flood fill (4 neighbours) at every unvisited foreground pixel, so component k is the
+// k-th component by the raster index of its first pixel.  The statistics the reference derives from each component's
+// pixel list (detection.rs:247-255, 286-291) are area, sum of rows, sum of columns and the bounding box.
+//
+// Device formulation (no pixel lists, no DFS):
+//   node      = "word-run": a maximal horizontal run of set bits inside one 32-pixel bitmask word.  Its id is the
+//               linear pixel index p = y*w + x of its first pixel; its parent lives in labels[p] as parent+1
+//               (K1 / bits_to_mask_labels initialise labels[p] = p+1 for every node and 0 elsewhere).
+//   K2 merge  : union nodes that touch horizontally across a word boundary or overlap vertically; the union always
+//               hooks the larger root under the smaller one (atomicMin), so every tree's root is the component's
+//               minimum linear index = its raster-first pixel.
+//   K3 flatten: every node points directly at its root; root nodes are flagged in rootbits, counted per word.
+//   K4 scan   : exclusive prefix sum of the per-word root counts in raster order -> rank of every root; the
+//               canonical label of a component is rank(root)+1, which is exactly the reference's discovery order.
+//   K5 label  : every foreground pixel gets its canonical label (in place: a word's label slots are only ever read
+//               and written by the thread that owns the word), blob statistics are accumulated with one set of
+//               atomics per word-run.
+// Only non-zero bitmask words do any work, so the cost follows the foreground, not the frame size.
+#include "hv_common.cuh"
+
+namespace hv {
+
+namespace {
+
+__device__ __forceinline__ int ld_parent(const int32_t *L, int a) {
+    // parents are modified concurrently by atomics in L2: bypass L1
+    return __ldcg(L + a) - 1;
+}
+
+__device__ __forceinline__ int uf_find(const int32_t *L, int a) {
+    int p = ld_parent(L, a);
+    while (p != a) {
+        a = p;
+        p = ld_parent(L, a);
+    }
+    return a;
+}
+
+// Lock-free union by minimum index.  Invariant: parent(a) <= a, so chains strictly decrease and terminate.
+__device__ __forceinline__ void uf_union(int32_t *L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        // a > b: try to hook root a under b
+        const int old = atomicMin(L + a, b + 1) - 1;
+        if (old == a) return;  // a was still a root: done
+        a = old;               // somebody else hooked a under `old` first; keep merging old's tree with b
+    }
+}
+
+// first bit of the run of set bits of m that contains bit `bit`
+__device__ __forceinline__ int run_start(uint32_t m, int bit) {
+    const uint32_t zeros_below = ~m & ((1u << bit) - 1u);
+    return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+
+__global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
+    const size_t words_per_frame = (size_t)b.h * b.ww;
+    const size_t total = words_per_frame * b.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = b.bits[i];
+        if (!m) continue;
+        const size_t f = i / words_per_frame;
+        const int wi = (int)(i - f * words_per_frame);
+        const int y = wi / b.ww, wx = wi - y * b.ww;
+        int32_t *L = b.labels + f * (size_t)b.h * b.w;
+        const int row = y * b.w + wx * 32;
+        if ((m & 1u) && wx > 0) {
+            const uint32_t left = b.bits[i - 1];
+            if (left >> 31) uf_union(L, row, row - 32 + run_start(left, 31));
+        }
+        if (y > 0) {
+            const uint32_t up = b.bits[i - b.ww];
+            const uint32_t o = m & up;
+            uint32_t starts = o & ~(o << 1);
+            while (starts) {
+                const int bit = __ffs(starts) - 1;
+                starts &= starts - 1;
+                uf_union(L, row + run_start(m, bit), row - b.w + run_start(up, bit));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
+    const size_t words_per_frame = (size_t)b.h * b.ww;
+    const size_t total = words_per_frame * b.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = b.bits[i];
+        uint32_t roots = 0;
+        if (m) {
+            const size_t f = i / words_per_frame;
+            const int wi = (int)(i - f * words_per_frame);
+            const int y = wi / b.ww, wx = wi - y * b.ww;
+            int32_t *L = b.labels + f * (size_t)b.h * b.w;
+            const int row = y * b.w + wx * 32;
+            uint32_t starts = m & ~(m << 1);
+            while (starts) {
+                const int bit = __ffs(starts) - 1;
+                starts &= starts - 1;
+                const int s = row + bit;
+                const int r = uf_find(L, s);
+                if (r == s)
+                    roots |= 1u << bit;
+                else
+                    L[s] = r + 1;
+            }
+        }
+        b.rootbits[i] = roots;
+        b.rankbase[i] = __popc(roots);
+    }
+}
+
+// One CTA per frame: exclusive scan of the per-word root counts (raster order), component count, blob-table reset.
+__global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const int f = blockIdx.x;
+    const int nwords = b.h * b.ww;
+    uint32_t *cnt = b.rankbase + (size_t)f * nwords;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (nwords + 1023) / 1024;
+    const int beg = min(tid * per, nwords), end = min(beg + per, nwords);
+    uint32_t sum = 0;
+    for (int i = beg; i < end; i++) sum += cnt[i];
+    // block exclusive scan of `sum`
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[wid] + incl - sum;
+    for (int i = beg; i < end; i++) {
+        const uint32_t c = cnt[i];
+        cnt[i] = run;
+        run += c;
+    }
+    const uint32_t ncomp = s_total;
+    if (tid == 0) {
+        b.ncomp[f] = ncomp;
+        b.fgcount[f] = 0;
+    }
+    hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;
+    const uint32_t nb = min(ncomp, (uint32_t)b.blob_cap);
+    for (uint32_t k = tid; k < nb; k += 1024) {
+        hv_blob z;
+        z.area = 0;
+        z.ymin = 0xffffffffu;
+        z.ymax = 0;
+        z.xmin = 0xffffffffu;
+        z.xmax = 0;
+        z.reserved = 0;
+        z.sum_y = 0;
+        z.sum_x = 0;
+        blobs[k] = z;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_label(BatchView b) {
+    const size_t words_per_frame = (size_t)b.h * b.ww;
+    const size_t total = words_per_frame * b.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = b.bits[i];
+        if (!m) continue;
+        const size_t f = i / words_per_frame;
+        const int wi = (int)(i - f * words_per_frame);
+        const int y = wi / b.ww, wx = wi - y * b.ww;
+        int32_t *L = b.labels + f * (size_t)b.h * b.w;
+        const uint32_t *rootbits = b.rootbits + f * words_per_frame;
+        const uint32_t *rankbase = b.rankbase + f * words_per_frame;
+        hv_blob *blobs = b.blobs + f * (size_t)b.blob_cap;
+        const int row = y * b.w + wx * 32;
+        atomicAdd(b.fgcount + f, (uint32_t)__popc(m));
+        uint32_t rest = m;
+        while (rest) {
+            const int bit = __ffs(rest) - 1;
+            // run [bit, bit+len)
+            const uint32_t shifted = ~(rest >> bit);
+            const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
+            rest = (bit + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << bit));
+            const int s = row + bit;
+            const int r = L[s] - 1;  // flattened: the root itself
+            const int ry = r / b.w, rx = r - ry * b.w;
+            const int rw = ry * b.ww + (rx >> 5);
+            const uint32_t rank = rankbase[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u));
+            const int label = (int)rank + 1;
+            for (int k = 0; k < len; k++) L[s + k] = label;
+            if (rank < (uint32_t)b.blob_cap) {
+                hv_blob *q = blobs + rank;
+                const uint32_t xs = wx * 32 + bit, xe = xs + len - 1;
+                atomicAdd(&q->area, (uint32_t)len);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_y), (unsigned long long)y * len);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_x),
+                          ((unsigned long long)(xs + xe) * len) >> 1);
+                atomicMin(&q->ymin, (uint32_t)y);
+                atomicMax(&q->ymax, (uint32_t)y);
+                atomicMin(&q->xmin, xs);
+                atomicMax(&q->xmax, xe);
+            }
+        }
+    }
+}
+
+// mask bytes + label-plane initialisation from a bit-packed mask (used after morphology, and by find_contours).
+__global__ void __launch_bounds__(256) k_bits_to_mask_labels(BatchView b) {
+    const size_t words_per_frame = (size_t)b.h * b.ww;
+    const size_t total = words_per_frame * b.n;
+    const int lane = threadIdx.x & 31;
+    // one warp per word: lane = pixel, so the 32 mask bytes / 32 labels of a word go out as one coalesced store
+    const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i = warp0; i < total; i += nwarps) {
+        const uint32_t m = b.bits[i];
+        const size_t f = i / words_per_frame;
+        const int wi = (int)(i - f * words_per_frame);
+        const int y = wi / b.ww, wx = wi - y * b.ww;
+        const int x = wx * 32 + lane;
+        if (x >= b.w) continue;
+        const size_t px = (f * b.h + y) * (size_t)b.w + x;
+        const bool fg = (m >> lane) & 1u;
+        const bool start = fg && (lane == 0 || !((m >> (lane - 1)) & 1u));
+        b.mask[px] = fg ? 255 : 0;
+        b.labels[px] = start ? (y * b.w + x + 1) : 0;
+    }
+}
+
+int grid_for(size_t work_items, int per_block) {
+    size_t g = (work_items + per_block - 1) / per_block;
+    const size_t cap = 148 * 32;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s) {
+    k_ccl_merge<<<grid_for((size_t)b.n * b.h * b.ww, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s) {
+    k_ccl_flatten<<<grid_for((size_t)b.n * b.h * b.ww, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s) {
+    k_ccl_scan<<<b.n, 1024, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s) {
+    k_ccl_label<<<grid_for((size_t)b.n * b.h * b.ww, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s) {
+    k_bits_to_mask_labels<<<grid_for((size_t)b.n * b.h * b.ww * 32, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+
+}  // namespace hv

@@ -1,0 +1,249 @@
+// k_score.cu -- K6: per-blob filters, contrast probe, confidence and the reject decision.
+//
+// Restates rust/heimdall-core/src/detection.rs:247-311:
+//   keep iff min_size <= area <= max_size (f64 compare, both ends inclusive)
+//   centre = (floor(sum_y/n), floor(sum_x/n))
+//   5x5 window clamped to the image around the centre: pixels with mask == 255 (ANY component) are foreground,
+//   the rest background; means of GRAY (not the blurred image); an empty side counts as 127.0
+//   shape = 1 - area/rect ; intensity = min(|bg-fg|/30, 1) ; confidence = intensity*0.7 + shape*0.3 ; keep iff >= 0.3
+// All f64 operations use the round-to-nearest intrinsics so nvcc cannot contract a*b+c into an FMA (rustc never does;
+// SURVEY.md KAT2 = 0.7999999999999999 depends on it).
+// Defects are emitted in label order (= the reference's discovery order) with an order-preserving block scan.
+// reject := n_defects > 0 (heimdall/inspection/base_inspector.py:40-42).
+#include "hv_common.cuh"
+
+namespace hv {
+
+namespace {
+
+struct Scored {
+    bool keep;
+    hv_defect d;
+};
+
+__device__ __forceinline__ Scored score_blob(const BatchView &b, const ScoreParams &p, int f, uint32_t k,
+                                             const hv_blob &q) {
+    Scored out;
+    out.keep = false;
+    const double area = (double)q.area;
+    if (!(area >= p.min_size && area <= p.max_size) || q.area == 0) return out;
+    const int H = b.h, W = b.w;
+    const uint64_t cy = q.sum_y / q.area, cx = q.sum_x / q.area;
+    const int icy = (int)cy, icx = (int)cx;
+    const int y_lo = max(icy - 2, 0), y_hi = min(icy + 2, H - 1);
+    const int x_lo = max(icx - 2, 0), x_hi = min(icx + 2, W - 1);
+    const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
+    const uint8_t *mask = b.mask + (size_t)f * H * W;
+    uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
+    for (int y = y_lo; y <= y_hi; y++)
+        for (int x = x_lo; x <= x_hi; x++) {
+            const uint32_t g = gray[(size_t)y * b.gray_row_stride + x];
+            if (mask[(size_t)y * W + x] == 255) {
+                fg_sum += g;
+                fg_cnt++;
+            } else {
+                bg_sum += g;
+                bg_cnt++;
+            }
+        }
+    const double fg_mean = fg_cnt ? __ddiv_rn((double)fg_sum, (double)fg_cnt) : 127.0;
+    const double bg_mean = bg_cnt ? __ddiv_rn((double)bg_sum, (double)bg_cnt) : 127.0;
+    const double idiff = fabs(__dsub_rn(bg_mean, fg_mean));
+    const uint64_t rect = (uint64_t)(q.ymax - q.ymin + 1) * (uint64_t)(q.xmax - q.xmin + 1);
+    const double shape = rect > 0 ? __dsub_rn(1.0, __ddiv_rn(area, (double)rect)) : 0.5;
+    double iscore = __ddiv_rn(idiff, 30.0);
+    if (!(iscore <= 1.0)) iscore = 1.0;
+    const double conf = __dadd_rn(__dmul_rn(iscore, 0.7), __dmul_rn(shape, 0.3));
+    if (conf >= p.min_confidence) {
+        out.keep = true;
+        out.d.y = icy;
+        out.d.x = icx;
+        out.d.size = area;
+        out.d.confidence = conf;
+        out.d.ymin = (int32_t)q.ymin;
+        out.d.xmin = (int32_t)q.xmin;
+        out.d.ymax = (int32_t)q.ymax;
+        out.d.xmax = (int32_t)q.xmax;
+        out.d.label = k + 1;
+        out.d.frame = (uint32_t)f;
+    }
+    return out;
+}
+
+__device__ __forceinline__ int area_bin(uint32_t area) {
+    const int bin = 31 - __clz(area | 1u);
+    return bin < HV_STATS_AREA_BINS ? bin : HV_STATS_AREA_BINS - 1;
+}
+
+// One CTA per frame.
+__global__ void __launch_bounds__(256) k_score(BatchView b, ScoreParams p) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    __shared__ unsigned long long s_area;
+    __shared__ uint32_t s_hist[HV_STATS_AREA_BINS];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t ncomp = b.ncomp[f];
+    const uint32_t nb = min(ncomp, (uint32_t)b.blob_cap);
+    const hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;
+    hv_defect *out = b.defects + (size_t)f * b.defect_cap;
+    if (tid == 0) {
+        s_base = 0;
+        s_area = 0;
+    }
+    if (tid < HV_STATS_AREA_BINS) s_hist[tid] = 0;
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < nb; k0 += 256) {
+        const uint32_t k = k0 + tid;
+        Scored sc;
+        sc.keep = false;
+        if (k < nb) sc = score_blob(b, p, f, k, blobs[k]);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, sc.keep);
+        if (lane == 0) s_warp[wid] = __popc(ballot);
+        __syncthreads();
+        uint32_t pos = s_base + __popc(ballot & ((1u << lane) - 1u));
+        uint32_t chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wid) pos += s_warp[w];
+            chunk_total += s_warp[w];
+        }
+        if (sc.keep) {
+            if (pos < (uint32_t)b.defect_cap) out[pos] = sc.d;
+            atomicAdd(&s_area, (unsigned long long)sc.d.size);
+            atomicAdd(&s_hist[area_bin((uint32_t)sc.d.size)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) s_base += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t nd = s_base;
+        const bool overflow = ncomp > (uint32_t)b.blob_cap || nd > (uint32_t)b.defect_cap;
+        hv_frame_result r;
+        r.n_components = ncomp;
+        r.n_defects = min(nd, (uint32_t)b.defect_cap);
+        r.defects_offset = 0;
+        r.rejected = nd > 0 ? 1u : 0u;
+        r.fg_pixels = b.fgcount[f];
+        r.status = overflow ? HV_ERR_CAPACITY : HV_OK;
+        b.results[f] = r;
+        unsigned long long *st = reinterpret_cast<unsigned long long *>(b.stats);
+        atomicAdd(st + 0, 1ull);                         // frames_inspected
+        atomicAdd(st + 1, (unsigned long long)r.rejected);  // frames_rejected
+        atomicAdd(st + 2, (unsigned long long)nd);          // total_defects
+        atomicAdd(st + 3, (unsigned long long)ncomp);       // total_components
+        atomicAdd(st + 4, s_area);                          // total_defect_area
+        atomicAdd(st + 5, (unsigned long long)r.fg_pixels); // total_fg_pixels
+        if (overflow) atomicAdd(st + 6 + HV_STATS_AREA_BINS, 1ull);
+    }
+    if (tid < HV_STATS_AREA_BINS && s_hist[tid])
+        atomicAdd(reinterpret_cast<unsigned long long *>(b.stats) + 6 + tid, (unsigned long long)s_hist[tid]);
+}
+
+// (cy, cx) of every blob with area >= min_area, label order (processing.rs:355-366).
+__global__ void __launch_bounds__(256) k_collect_centers(BatchView b, uint32_t min_area, hv_center *out,
+                                                         uint32_t *count, int cap) {
+    // single CTA, frame 0; ordered compaction as in k_score
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nb = min(b.ncomp[0], (uint32_t)b.blob_cap);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < nb; k0 += 256) {
+        const uint32_t k = k0 + tid;
+        bool keep = false;
+        hv_blob q;
+        if (k < nb) {
+            q = b.blobs[k];
+            keep = q.area >= min_area;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(ballot);
+        __syncthreads();
+        uint32_t pos = s_base + __popc(ballot & ((1u << lane) - 1u));
+        uint32_t chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wid) pos += s_warp[w];
+            chunk_total += s_warp[w];
+        }
+        if (keep && pos < (uint32_t)cap) {
+            hv_center c;
+            c.y = (int32_t)(q.sum_y / q.area);
+            c.x = (int32_t)(q.sum_x / q.area);
+            c.confidence = 0.75;
+            out[pos] = c;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_base;
+}
+
+// find_contours records (detection.rs:90-113): min_area <= area <= max_area, label order.
+__global__ void __launch_bounds__(256) k_collect_contours(BatchView b, double min_area, double max_area,
+                                                          hv_contour *out, uint32_t *count, int cap) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nb = min(b.ncomp[0], (uint32_t)b.blob_cap);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t k0 = 0; k0 < nb; k0 += 256) {
+        const uint32_t k = k0 + tid;
+        bool keep = false;
+        hv_blob q;
+        if (k < nb) {
+            q = b.blobs[k];
+            const double area = (double)q.area;
+            keep = q.area > 0 && area >= min_area && area <= max_area;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(ballot);
+        __syncthreads();
+        uint32_t pos = s_base + __popc(ballot & ((1u << lane) - 1u));
+        uint32_t chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wid) pos += s_warp[w];
+            chunk_total += s_warp[w];
+        }
+        if (keep && pos < (uint32_t)cap) {
+            hv_contour c;
+            c.y = (int32_t)(q.sum_y / q.area);
+            c.x = (int32_t)(q.sum_x / q.area);
+            c.area = (double)q.area;
+            c.pixel_count = q.area;
+            c.label = k + 1;
+            c.reserved = 0;
+            out[pos] = c;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) *count = s_base;
+}
+
+}  // namespace
+
+cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s) {
+    k_score<<<b.n, 256, 0, s>>>(b, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_collect_centers(const BatchView &b, uint32_t min_area, hv_center *d_centers, uint32_t *d_count,
+                                   int cap, cudaStream_t s) {
+    k_collect_centers<<<1, 256, 0, s>>>(b, min_area, d_centers, d_count, cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
+                                    uint32_t *d_count, int cap, cudaStream_t s) {
+    k_collect_contours<<<1, 256, 0, s>>>(b, min_area, max_area, d_out, d_count, cap);
+    return cudaGetLastError();
+}
+
+}  // namespace hv

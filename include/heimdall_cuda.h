@@ -1,0 +1,270 @@
+/*
+ * heimdall_cuda.h -- C ABI of the B200 (sm_100a) backend for heimdall-vision's contamination-inspection hot path.
+ *
+ * This is the drop-in boundary: exactly what a Rust `heimdall-cuda` crate (build.rs + extern "C" block, see
+ * rust/heimdall-cuda/ and INTEGRATION.md) or any other FFI (ctypes, cgo, JNI) binds.  Plain pointers and sizes,
+ * fixed-width integers, POD structs; no C++ or torch types.  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Threading: an hv_ctx is bound to one CUDA device and is NOT thread-safe; use one context per (thread, device).
+ * The library keeps no global mutable state.  There is no CPU fallback: without a usable CUDA device hv_create fails.
+ *
+ * Results are bit-exact with the reference's Rust CPU path (masks, labels in raster-first-pixel order, blob
+ * statistics, defect list order, confidences as IEEE f64, reject decision).
+ */
+#ifndef HEIMDALL_CUDA_H
+#define HEIMDALL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HV_API __declspec(dllexport)
+#else
+#define HV_API __attribute__((visibility("default")))
+#endif
+
+#define HV_ABI_VERSION 1
+
+typedef struct hv_ctx hv_ctx;
+typedef int32_t hv_status;
+
+/* Status codes. The message texts returned by hv_last_error() reproduce the reference's error enums:
+ * DetectionError (rust/heimdall-core/src/detection.rs:20-27), ProcessingError (processing.rs:11-21). */
+enum {
+    HV_OK = 0,
+    HV_ERR_INVALID_DIMENSIONS = -1, /* "Invalid image dimensions: expected 3D array" (detection.rs:159) */
+    HV_ERR_INVALID_ARGUMENT = -2,
+    HV_ERR_CUDA = -3,               /* CUDA runtime failure; text in hv_last_error() */
+    HV_ERR_CAPACITY = -4,           /* more blobs/defects than the configured capacity; never truncates silently */
+    HV_ERR_NO_DEVICE = -5,          /* no CUDA device / wrong architecture: there is no CPU fallback */
+    HV_ERR_UNSUPPORTED = -6,        /* "Unsupported pipeline type: ..." (lib.rs:80-84) and similar */
+    HV_ERR_CHANNELS = -7,           /* stage needs a 1-channel image (processing.rs:119-121, detection.rs:50-52) */
+    HV_ERR_BAD_TICKET = -8
+};
+
+/* Context sizing. Zero means "default / grow on demand". */
+typedef struct {
+    int32_t max_batch;              /* frames per hv_detect_* call the scratch is pre-sized for */
+    int32_t max_height, max_width;
+    int32_t max_blobs_per_frame;    /* stats-table rows per frame; 0 -> h*w/2+1 (the 4-connectivity maximum) */
+    int32_t max_defects_per_frame;  /* device-side defect slots per frame; 0 -> 256 */
+    int32_t num_slots;              /* in-flight batches for hv_submit/hv_wait; 0 -> 3 */
+    int32_t flags;                  /* HV_FLAG_* */
+    int32_t reserved;
+} hv_config;
+
+#define HV_FLAG_NO_GRAPH 1u   /* launch kernels directly instead of replaying a captured CUDA graph */
+#define HV_FLAG_PROFILE 2u    /* record a CUDA event pair around every kernel (hv_profile_get) */
+#define HV_FLAG_KEEP_BLUR 4u  /* materialise the blurred intermediate for hv_fetch_debug (disables the flat-tile skip) */
+
+/* Blur selection for the preprocess stage. */
+enum {
+    HV_BLUR_BOX = 0,      /* detection.rs:162-182: (2r+1)^2 box mean, floor division, interior only; r = blur_ksize/2 */
+    HV_BLUR_GAUSSIAN = 1, /* cv2.GaussianBlur(k,k,sigma) semantics (heimdall/detectors/contamination_detector.py:66) */
+    HV_BLUR_NONE = 2
+};
+
+/* Per-call parameters. hv_params_default() fills the reference defaults
+ * (rust/heimdall-core/src/lib.rs:106-108: 10.0 / 3000.0 / 25.0; detection.rs:163 radius 2, :185 window 11). */
+typedef struct {
+    double min_size;       /* inclusive lower area bound (detection.rs:250) */
+    double max_size;       /* inclusive upper area bound */
+    double threshold;      /* `c = threshold as i32` (detection.rs:186) */
+    double min_confidence; /* 0.3 (detection.rs:298) */
+    double gauss_sigma;    /* HV_BLUR_GAUSSIAN only; <=0 -> OpenCV's automatic sigma */
+    int32_t blur_mode;     /* HV_BLUR_* */
+    int32_t blur_ksize;    /* 5 */
+    int32_t morph_open_k;  /* 0 = off (the Rust path has no morphology); k>0: rect kxk MORPH_OPEN on the mask
+                              (contamination_detector.py:81-84) */
+    int32_t morph_close_k; /* 0 = off; k>0: rect kxk MORPH_CLOSE after the open (contamination_detector.py:87) */
+    int32_t reserved[4];
+} hv_params;
+
+/* One defect. Mirrors `Defect` (detection.rs:12-18): position = (row, col), size = area as f64.  The extra integer
+ * fields are what the reference computes on the way (bbox for the shape score, 1-based component label). */
+typedef struct {
+    int32_t y, x;
+    double size;
+    double confidence;
+    int32_t ymin, xmin, ymax, xmax;
+    uint32_t label;
+    uint32_t frame; /* index of the frame inside the batch */
+} hv_defect;
+
+/* Per-frame summary. `rejected` is the reject decision: n_defects > 0 (heimdall/inspection/base_inspector.py:40-42). */
+typedef struct {
+    uint32_t n_components; /* all 4-connected components of the mask, before any filter */
+    uint32_t n_defects;
+    uint32_t defects_offset; /* first defect of this frame in the caller's defects array */
+    uint32_t rejected;
+    uint32_t fg_pixels; /* mask pixels == 255 */
+    int32_t status;     /* HV_OK or HV_ERR_CAPACITY for this frame */
+} hv_frame_result;
+
+/* Per-blob integer statistics, canonical (raster-first-pixel) order; row k describes label k+1. */
+typedef struct {
+    uint32_t area;
+    uint32_t ymin, ymax, xmin, xmax;
+    uint32_t reserved;
+    uint64_t sum_y, sum_x;
+} hv_blob;
+
+/* Optional host-side copies of the intermediates for parity checks (any pointer may be NULL).
+ * gray/blur/mask: n*h*w u8; labels: n*h*w i32 (0 = background, k = k-th component in raster-first-pixel order);
+ * blobs: n * blobs_stride rows. */
+typedef struct {
+    uint8_t *gray;
+    uint8_t *blur;
+    uint8_t *mask;
+    int32_t *labels;
+    hv_blob *blobs;
+    size_t blobs_stride;
+} hv_debug_outputs;
+
+/* Line-level statistics accumulated on the device across calls (dashboard.py:38-46,483-500;
+ * heimdall/core/system.py:168-175).  All fields u64 so that the whole struct can be all-reduced with one
+ * ncclAllReduce(ncclUint64, ncclSum) over hv_stats_device_ptr(). */
+#define HV_STATS_AREA_BINS 16
+typedef struct {
+    uint64_t frames_inspected;
+    uint64_t frames_rejected;
+    uint64_t total_defects;
+    uint64_t total_components;
+    uint64_t total_defect_area;
+    uint64_t total_fg_pixels;
+    uint64_t area_hist[HV_STATS_AREA_BINS]; /* bin = floor(log2(area)), clamped */
+    uint64_t capacity_errors;
+    uint64_t reserved[9];
+} hv_line_stats; /* 32 x u64 = 256 bytes */
+
+/* Kernel indices for hv_profile_get(). */
+enum {
+    HV_K_GRAY = 0,       /* A1 gray (C==3 only) */
+    HV_K_PREPROCESS = 1, /* A2+A3 fused blur + adaptive threshold + mask/bitmask/label-zero store */
+    HV_K_MORPH = 2,      /* A8 open/close on the bit-packed mask (when enabled) */
+    HV_K_CCL_MERGE = 3,  /* A4 union-find merge of word-runs */
+    HV_K_CCL_FLATTEN = 4,
+    HV_K_CCL_SCAN = 5,
+    HV_K_CCL_LABEL = 6,  /* A4 canonical relabel + A5 blob statistics */
+    HV_K_SCORE = 7,      /* A5b + A6 */
+    HV_K_COUNT = 8
+};
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+HV_API int32_t hv_abi_version(void);
+HV_API const char *hv_version(void);
+HV_API const char *hv_status_string(hv_status s);
+HV_API int32_t hv_device_count(void);
+HV_API void hv_params_default(hv_params *p);
+HV_API void hv_config_default(hv_config *c);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+HV_API hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out);
+HV_API void hv_destroy(hv_ctx *ctx);
+/* Text of the last failure on this context ("" if none). With ctx == NULL: last hv_create failure of this thread. */
+HV_API const char *hv_last_error(const hv_ctx *ctx);
+/* Use the caller's CUDA stream (a cudaStream_t) for the synchronous device-resident entry points; NULL restores
+ * the context's own stream. */
+HV_API hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream);
+
+/* Pinned host staging buffers (cudaHostAlloc). Frames handed to hv_detect_batch / hv_submit from such a buffer are
+ * copied to the device without an intermediate host copy. */
+HV_API void *hv_host_alloc(hv_ctx *ctx, size_t bytes);
+HV_API void hv_host_free(hv_ctx *ctx, void *p);
+
+/* ---- the hot path --------------------------------------------------------------------------------------
+ * Replaces heimdall_core.detect_contamination (rust/heimdall-core/src/lib.rs:95-143) ->
+ * detection::detect_contamination (detection.rs:127-317), for a batch of n frames.
+ *
+ * frames: HOST memory, n frames of h x w x c u8 (c = 1 or 3), element (f,y,x,ch) at
+ *         frames[f*frame_stride + y*row_stride + x*c + ch]; strides in bytes, 0 = tightly packed.
+ * results: n entries. defects: up to defects_cap entries, frame-major, discovery order inside a frame.
+ * Returns HV_OK, or HV_ERR_CAPACITY if any frame overflowed (per-frame status says which; the other frames are valid).
+ */
+HV_API hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                                 size_t row_stride, size_t frame_stride, const hv_params *params,
+                                 hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                                 size_t *n_defects_total, const hv_debug_outputs *debug);
+
+/* Same, frames already resident in DEVICE memory (c = 1 or 3, tightly packed rows unless strides given).
+ * d_mask (n*h*w u8) and d_labels (n*h*w i32) are optional caller-owned DEVICE outputs; when NULL the context's
+ * scratch is used.  results/defects are HOST memory. */
+HV_API hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w,
+                                        int32_t c, size_t row_stride, size_t frame_stride, const hv_params *params,
+                                        uint8_t *d_mask, int32_t *d_labels, hv_frame_result *results,
+                                        hv_defect *defects, size_t defects_cap, size_t *n_defects_total);
+
+/* Device-resident, asynchronous: enqueue only (no host synchronisation, no result read-back); results stay in the
+ * context until hv_fetch_results().  This is the form CUDA-graph replay and kernel timing use. */
+HV_API hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                                   size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
+                                   int32_t *d_labels);
+HV_API hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                                  size_t *n_defects_total);
+/* Copy intermediates of the last enqueued batch to the host (parity checks). */
+HV_API hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug);
+
+/* Pipelined host-fed form (camera streams): hv_submit copies/points at the host frames, enqueues H2D + kernels +
+ * D2H on one of the context's slots and returns a ticket; hv_wait blocks for that ticket and fills the outputs.
+ * Up to num_slots tickets may be in flight; the frames buffer must stay valid until hv_wait returns. */
+HV_API hv_status hv_submit(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, int32_t w, int32_t c,
+                           size_t row_stride, size_t frame_stride, const hv_params *params, int64_t *ticket);
+HV_API hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects,
+                         size_t defects_cap, size_t *n_defects_total);
+
+/* ---- stage entry points (single frame, host memory) ----------------------------------------------------
+ * heimdall_core.processing.preprocess_image (processing.rs:30-101): out has (grayscale ? 1 : c) channels;
+ * blur_size <= 0 -> no blur.  grayscale != 0 requires c >= 3 (the reference indexes channels 1 and 2). */
+HV_API hv_status hv_preprocess_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                     int32_t grayscale, int32_t blur_size, uint8_t *out);
+/* heimdall_core.processing.apply_threshold (processing.rs:104-185): c must be 1. */
+HV_API hv_status hv_apply_threshold(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                    uint8_t threshold_value, int32_t adaptive, int32_t inverse, uint8_t *out);
+
+/* heimdall_core.detection.find_contours (detection.rs:36-124): foreground is `> 127`; blobs with
+ * min_area <= area <= max_area in discovery order. labels (optional, h*w i32) receives the full label map. */
+typedef struct {
+    int32_t y, x;
+    double area;
+    uint64_t pixel_count;
+    uint32_t label;
+    uint32_t reserved;
+} hv_contour;
+HV_API hv_status hv_find_contours(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, double min_area,
+                                  double max_area, hv_contour *contours, size_t cap, size_t *n_contours,
+                                  int32_t *labels);
+
+/* heimdall_core.process_image (lib.rs:42-92). pipeline: 0 = "basic" (processing.rs:188-249),
+ * 1 = "contamination" (processing.rs:252-404). out_hw3: h*w*3 u8 visualisation. contours (cy, cx, 0.75) only for
+ * pipeline 1. */
+enum { HV_PIPELINE_BASIC = 0, HV_PIPELINE_CONTAMINATION = 1 };
+typedef struct {
+    int32_t y, x;
+    double confidence;
+} hv_center;
+HV_API hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                  int32_t pipeline, uint8_t *out_hw3, hv_center *contours, size_t cap,
+                                  size_t *n_contours);
+
+/* ---- line statistics ------------------------------------------------------------------------------------ */
+HV_API hv_status hv_stats_get(hv_ctx *ctx, hv_line_stats *out);
+HV_API hv_status hv_stats_reset(hv_ctx *ctx);
+/* Device pointer to the 32 x u64 stats vector, for the host's NCCL communicator (the only collective of this path). */
+HV_API uint64_t *hv_stats_device_ptr(hv_ctx *ctx);
+
+/* ---- measurement ---------------------------------------------------------------------------------------- */
+/* Kernels launched by this context so far. */
+HV_API uint64_t hv_launch_count(const hv_ctx *ctx);
+/* With HV_FLAG_PROFILE: milliseconds of each kernel of the last synchronous batch (0 when not launched). */
+HV_API hv_status hv_profile_get(hv_ctx *ctx, float ms[HV_K_COUNT]);
+HV_API const char *hv_kernel_name(int32_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEIMDALL_CUDA_H */

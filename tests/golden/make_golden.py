@@ -1,0 +1,139 @@
+#!/usr/bin/env python3
+"""Regenerates the committed golden fixtures under tests/golden/.  Run in the dev container only (it needs
+opencv-python and, for the reference-derived vectors, /root/reference); the tests read the committed files and never
+touch /root/reference.
+
+Sources of truth:
+  cv2_gaussian.npz / cv2_morph.npz / cv2_ccl.npz : outputs of opencv-python (the reference's real third-party
+      dependency for its Python path; version printed into meta.json) on seeded inputs.
+  reference_python.json : outputs of the UNMODIFIED reference Python code imported from /root/reference
+      (heimdall/rust_bridge.py RustBridge.detect_contamination -> heimdall/detectors/contamination_detector.py) on
+      seeded synthetic frames; pins the fallback path.
+  fixture_frames.npz + rust_path.json : the reference's own fixture images contaminated_{1,2,3}.jpg decoded with this
+      cv2 build, and the Rust-path results of the oracle on them (regression vectors; the reference ships no expected
+      outputs for them -- parity of the Rust path itself is pinned by the hand-derived KATs in tests/test_oracle.py).
+  bottle_expectations.json : oracle results on the synthetic bottle frames used by the GPU parity tests and bench.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import importlib.util  # noqa: E402
+
+import cv2  # noqa: E402
+
+# load synth.py by path: the package directory must NOT be on sys.path here, or the reference bridge below would pick
+# up our drop-in `heimdall_core` instead of its own Python fallback
+_spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "heimdall-vision_b200", "synth.py"))
+synth = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(synth)
+from oracle import oracle as O  # noqa: E402
+
+GAUSS_CASES = [(3, 0), (5, 0), (7, 0), (9, 0), (11, 0), (13, 0), (15, 0), (7, 1.0), (13, 2.0), (15, 3.0), (5, 1.1),
+               (9, 1.5), (15, 2.5), (3, 0.8)]
+MORPH_KS = [2, 3, 4, 5, 7, 9, 11, 13, 15]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    rng = np.random.default_rng(20261018)
+    meta = {"opencv": cv2.__version__, "numpy": np.__version__}
+
+    # ---- Gaussian ------------------------------------------------------------------------------------------
+    src = rng.integers(0, 256, (61, 83), dtype=np.uint8)
+    src2 = synth.bottle_frame(96, 128, 7, contaminants=2)
+    g = {"src": src, "src2": src2}
+    for k, s in GAUSS_CASES:
+        g[f"a_k{k}_s{s}"] = cv2.GaussianBlur(src, (k, k), s)
+        g[f"b_k{k}_s{s}"] = cv2.GaussianBlur(src2, (k, k), s)
+    np.savez_compressed(os.path.join(HERE, "cv2_gaussian.npz"), **g)
+
+    # ---- morphology ------------------------------------------------------------------------------------------
+    m1 = (rng.random((70, 101)) < 0.55).astype(np.uint8) * 255
+    m2 = np.zeros((64, 96), np.uint8)
+    cv2.circle(m2, (40, 30), 17, 255, -1)
+    cv2.rectangle(m2, (60, 5), (90, 50), 255, 2)
+    m2[rng.random(m2.shape) < 0.03] ^= 255
+    mm = {"m1": m1, "m2": m2}
+    ops = {"erode": cv2.MORPH_ERODE, "dilate": cv2.MORPH_DILATE, "open": cv2.MORPH_OPEN, "close": cv2.MORPH_CLOSE}
+    for k in MORPH_KS:
+        ker = cv2.getStructuringElement(cv2.MORPH_RECT, (k, k))
+        for name, op in ops.items():
+            mm[f"m1_{name}_{k}"] = cv2.morphologyEx(m1, op, ker)
+            mm[f"m2_{name}_{k}"] = cv2.morphologyEx(m2, op, ker)
+    np.savez_compressed(os.path.join(HERE, "cv2_morph.npz"), **mm)
+
+    # ---- CCL -------------------------------------------------------------------------------------------------
+    cc = {}
+    for i, (shape, p) in enumerate([((40, 70), 0.3), ((64, 64), 0.5), ((33, 97), 0.62), ((50, 50), 0.05)]):
+        m = (rng.random(shape) < p).astype(np.uint8) * 255
+        n, lab, st, _ = cv2.connectedComponentsWithStats(m, connectivity=4, ltype=cv2.CV_32S)
+        cc[f"mask{i}"] = m
+        cc[f"labels{i}"] = lab.astype(np.int32)
+        cc[f"stats{i}"] = st[1:].astype(np.int32)  # x, y, w, h, area per component
+    np.savez_compressed(os.path.join(HERE, "cv2_ccl.npz"), **cc)
+
+    # ---- reference fixtures + Rust-path regression vectors ---------------------------------------------------------
+    frames = {}
+    rust_path = {}
+    for i in (1, 2, 3):
+        p = f"/root/reference/contaminated_{i}.jpg"
+        if not os.path.exists(p):
+            continue
+        img = cv2.imread(p, cv2.IMREAD_COLOR)  # BGR; the bridge hands this array to heimdall_core unchanged
+        frames[f"contaminated_{i}"] = img
+        r = O.detect_contamination(img)
+        rust_path[f"contaminated_{i}"] = {
+            "sha256": sha(img), "shape": list(img.shape), "fg_pixels": int((r.mask == 255).sum()),
+            "ncomp": r.ncomp, "mask_sha256": sha(r.mask), "labels_sha256": sha(r.labels),
+            "defects": [[d["position"][0], d["position"][1], d["size"], d["confidence"]] for d in r.defects]}
+    if frames:
+        np.savez_compressed(os.path.join(HERE, "fixture_frames.npz"), **frames)
+        json.dump(rust_path, open(os.path.join(HERE, "rust_path.json"), "w"), indent=1)
+
+    # ---- unmodified reference Python fallback ---------------------------------------------------------------------
+    if os.path.isdir("/root/reference/heimdall"):
+        sys.path.insert(0, "/root/reference")
+        import logging
+        logging.disable(logging.CRITICAL)
+        from heimdall.rust_bridge import RustBridge, RUST_AVAILABLE
+        assert not RUST_AVAILABLE  # nothing named heimdall_core may be importable while generating these
+        ref = {}
+        for idx in (0, 3, 5):
+            fr = synth.bottle_frame(240, 320, idx, contaminants=2)
+            out = RustBridge.detect_contamination(np.dstack([fr, fr, fr]), 10.0, 3000.0, 25.0)
+            ref[str(idx)] = [{"position": list(map(int, d["position"])), "size": float(d["size"]),
+                              "confidence": float(d["confidence"])} for d in out["defects"]]
+        json.dump({"frames": "synth.bottle_frame(240,320,idx,contaminants=2) replicated to 3 channels",
+                   "results": ref}, open(os.path.join(HERE, "reference_python.json"), "w"), indent=1)
+        logging.disable(logging.NOTSET)
+
+    # ---- synthetic bottle expectations (oracle) --------------------------------------------------------------------
+    exp = {}
+    for (h, w, idx, kw) in [(1024, 1280, 0, {}), (1024, 1280, 1, {"contaminants": 2}), (1024, 1280, 2, {}),
+                            (1024, 1280, 3, {"contaminants": 3}), (480, 640, 4, {"contaminants": 1}),
+                            (2048, 2448, 5, {"contaminants": 3})]:
+        fr = synth.bottle_frame(h, w, idx, **kw)
+        r = O.detect_contamination(fr)
+        exp[f"{h}x{w}_{idx}"] = {"kw": kw, "sha256": sha(fr), "fg_pixels": int((r.mask == 255).sum()),
+                                 "ncomp": r.ncomp, "mask_sha256": sha(r.mask), "labels_sha256": sha(r.labels),
+                                 "defects": [[d["position"][0], d["position"][1], d["size"], d["confidence"]]
+                                             for d in r.defects]}
+    json.dump(exp, open(os.path.join(HERE, "bottle_expectations.json"), "w"), indent=1)
+    json.dump(meta, open(os.path.join(HERE, "meta.json"), "w"), indent=1)
+    for f in sorted(os.listdir(HERE)):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
