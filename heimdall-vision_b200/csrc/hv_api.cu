@@ -103,10 +103,14 @@ struct hv_ctx {
     uint64_t launches = 0;
     int64_t next_ticket = 1;
     int next_slot = 1;
-    // profiling
-    cudaEvent_t prof_ev[HV_K_COUNT][2] = {};
-    bool prof_used[HV_K_COUNT] = {};
-    float prof_ms[HV_K_COUNT] = {};
+    // profiling: event pairs recorded around kernels whose bit is set in prof_mask
+    struct ProfRec {
+        int k;
+        cudaEvent_t a, b;
+    };
+    uint32_t prof_mask = 0;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
     // scratch for the single-frame utilities
     DevBuf<uint8_t> u_a, u_b, u_c;
     DevBuf<hv_center> u_centers;
@@ -158,17 +162,33 @@ int blob_cap_for(const hv_ctx *ctx, int h, int w) {
 
 int defect_cap_for(const hv_ctx *ctx) { return ctx->cfg.max_defects_per_frame > 0 ? ctx->cfg.max_defects_per_frame : 256; }
 
+cudaEvent_t prof_event(hv_ctx *ctx) {
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
 struct ProfScope {
     hv_ctx *ctx;
     int k;
     cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(hv_ctx *c, int kk, cudaStream_t ss) : ctx(c), k(kk), s(ss) {
-        if ((ctx->cfg.flags & HV_FLAG_PROFILE) && !ctx->prof_used[k]) cudaEventRecord(ctx->prof_ev[k][0], s);
+        if (ctx->prof_mask & (1u << k)) {
+            a = prof_event(ctx);
+            b = prof_event(ctx);
+            if (a) cudaEventRecord(a, s);
+        }
     }
     ~ProfScope() {
-        if (ctx->cfg.flags & HV_FLAG_PROFILE) {
-            cudaEventRecord(ctx->prof_ev[k][1], s);
-            ctx->prof_used[k] = true;
+        if (a && b) {
+            cudaEventRecord(b, s);
+            ctx->prof_recs.push_back({k, a, b});
         }
     }
 };
@@ -462,17 +482,6 @@ hv_status upload_frames(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *fr
     return HV_OK;
 }
 
-void prof_reset(hv_ctx *ctx) {
-    for (int k = 0; k < HV_K_COUNT; k++) ctx->prof_used[k] = false;
-}
-
-void prof_collect(hv_ctx *ctx) {
-    if (!(ctx->cfg.flags & HV_FLAG_PROFILE)) return;
-    for (int k = 0; k < HV_K_COUNT; k++) {
-        ctx->prof_ms[k] = 0.f;
-        if (ctx->prof_used[k]) cudaEventElapsedTime(&ctx->prof_ms[k], ctx->prof_ev[k][0], ctx->prof_ev[k][1]);
-    }
-}
 
 }  // namespace
 
@@ -569,8 +578,7 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
             return HV_ERR_CUDA;
         }
     }
-    for (int k = 0; k < HV_K_COUNT; k++)
-        for (int j = 0; j < 2; j++) cudaEventCreate(&ctx->prof_ev[k][j]);
+    if (ctx->cfg.flags & HV_FLAG_PROFILE) ctx->prof_mask = 0xffffffffu;
     if (cudaMalloc(reinterpret_cast<void **>(&ctx->d_stats), sizeof(hv_line_stats)) != cudaSuccess ||
         cudaMemset(ctx->d_stats, 0, sizeof(hv_line_stats)) != cudaSuccess) {
         g_create_error = "stats allocation failed";
@@ -586,9 +594,11 @@ void hv_destroy(hv_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots) s.release();
-    for (int k = 0; k < HV_K_COUNT; k++)
-        for (int j = 0; j < 2; j++)
-            if (ctx->prof_ev[k][j]) cudaEventDestroy(ctx->prof_ev[k][j]);
+    for (auto &r : ctx->prof_recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     ctx->u_a.release(), ctx->u_b.release(), ctx->u_c.release();
     ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release();
@@ -597,10 +607,10 @@ void hv_destroy(hv_ctx *ctx) {
 
 const char *hv_last_error(const hv_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream) {
+hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream, int32_t enable) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
-    ctx->user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-    ctx->use_user_stream = cuda_stream != nullptr;
+    ctx->user_stream = enable ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
+    ctx->use_user_stream = enable != 0;
     return HV_OK;
 }
 
@@ -633,7 +643,6 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
         pr = *params;
     else
         hv_params_default(&pr);
-    prof_reset(ctx);
     return enqueue_pipeline(ctx, ctx->slots[0], sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr, d_mask,
                             d_labels, (ctx->cfg.flags & 4u) != 0);
 }
@@ -648,7 +657,6 @@ hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *def
     hv_status rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-    prof_collect(ctx);
     return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
 }
 
@@ -686,14 +694,12 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
     cudaStream_t st = sync_stream(ctx);
     rs = upload_frames(ctx, s, st, frames, n, h, w, c, row_stride, frame_stride);
     if (rs != HV_OK) return rs;
-    prof_reset(ctx);
     const bool want_blur = (debug && debug->blur) || (ctx->cfg.flags & 4u);
     rs = enqueue_pipeline(ctx, s, st, s.in.p, n, h, w, c, 0, 0, pr, nullptr, nullptr, want_blur);
     if (rs != HV_OK) return rs;
     rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-    prof_collect(ctx);
     hv_status rc = unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
     hv_status rd = copy_debug(ctx, s, st, debug);
     return rd != HV_OK ? rd : rc;
@@ -959,9 +965,29 @@ uint64_t *hv_stats_device_ptr(hv_ctx *ctx) { return ctx ? reinterpret_cast<uint6
 
 uint64_t hv_launch_count(const hv_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-hv_status hv_profile_get(hv_ctx *ctx, float ms[HV_K_COUNT]) {
-    if (!ctx || !ms) return HV_ERR_INVALID_ARGUMENT;
-    for (int k = 0; k < HV_K_COUNT; k++) ms[k] = ctx->prof_ms[k];
+hv_status hv_profile_enable(hv_ctx *ctx, uint32_t kernel_mask) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    ctx->prof_mask = kernel_mask;
+    return HV_OK;
+}
+
+hv_status hv_profile_get(hv_ctx *ctx, float total_ms[HV_K_COUNT], uint32_t counts[HV_K_COUNT]) {
+    if (!ctx || !total_ms) return HV_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < HV_K_COUNT; k++) {
+        total_ms[k] = 0.f;
+        if (counts) counts[k] = 0;
+    }
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            total_ms[r.k] += ms;
+            if (counts) counts[r.k]++;
+        }
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    cudaGetLastError();
+    ctx->prof_recs.clear();
     return HV_OK;
 }
 

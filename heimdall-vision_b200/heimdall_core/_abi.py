@@ -31,6 +31,8 @@ HV_BLUR_BOX, HV_BLUR_GAUSSIAN, HV_BLUR_NONE = 0, 1, 2
 HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION = 0, 1
 HV_STATS_AREA_BINS = 16
 HV_K_COUNT = 8
+(HV_K_GRAY, HV_K_PREPROCESS, HV_K_MORPH, HV_K_CCL_MERGE, HV_K_CCL_FLATTEN, HV_K_CCL_SCAN, HV_K_CCL_LABEL,
+ HV_K_SCORE) = range(8)
 
 
 class hv_config(C.Structure):
@@ -100,7 +102,7 @@ PROTOTYPES = {
     "hv_create": (_i32, [_i32, _P(hv_config), _P(_vp)]),
     "hv_destroy": (None, [_vp]),
     "hv_last_error": (C.c_char_p, [_vp]),
-    "hv_set_stream": (_i32, [_vp, _vp]),
+    "hv_set_stream": (_i32, [_vp, _vp, _i32]),
     "hv_host_alloc": (_vp, [_vp, _sz]),
     "hv_host_free": (None, [_vp, _vp]),
     "hv_detect_batch": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _P(hv_frame_result),
@@ -120,7 +122,8 @@ PROTOTYPES = {
     "hv_stats_reset": (_i32, [_vp]),
     "hv_stats_device_ptr": (_vp, [_vp]),
     "hv_launch_count": (C.c_uint64, [_vp]),
-    "hv_profile_get": (_i32, [_vp, _P(C.c_float)]),
+    "hv_profile_enable": (_i32, [_vp, C.c_uint32]),
+    "hv_profile_get": (_i32, [_vp, _P(C.c_float), _P(C.c_uint32)]),
     "hv_kernel_name": (C.c_char_p, [_i32]),
 }
 

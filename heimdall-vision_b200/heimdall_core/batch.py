@@ -194,8 +194,9 @@ class Detector:
         _lib.hv_host_free(self._ctx, ptr)
 
     # ---- device-resident -----------------------------------------------------------------------------------------
-    def set_stream(self, cuda_stream: int) -> None:
-        st = _lib.hv_set_stream(self._ctx, cuda_stream)
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """Run on the caller's stream (0 = legacy default stream, e.g. torch's current stream); None = own stream."""
+        st = _lib.hv_set_stream(self._ctx, cuda_stream or None, 0 if cuda_stream is None else 1)
         if st != A.HV_OK:
             _raise(st, self._ctx)
 
@@ -309,10 +310,18 @@ class Detector:
     def launch_count(self) -> int:
         return int(_lib.hv_launch_count(self._ctx))
 
-    def profile(self) -> Dict[str, float]:
+    def profile_enable(self, kernels: Optional[Sequence[int]] = None) -> None:
+        """Time the given HV_K_* kernels with CUDA events on the launching stream (None = all, [] = off)."""
+        mask = 0xFFFFFFFF if kernels is None else sum(1 << k for k in kernels)
+        _lib.hv_profile_enable(self._ctx, mask)
+
+    def profile(self) -> Dict[str, dict]:
+        """Summed milliseconds and launch counts per kernel since the last call (waits for the events)."""
         ms = (C.c_float * A.HV_K_COUNT)()
-        _lib.hv_profile_get(self._ctx, ms)
-        return {_lib.hv_kernel_name(k).decode(): float(ms[k]) for k in range(A.HV_K_COUNT)}
+        cnt = (C.c_uint32 * A.HV_K_COUNT)()
+        _lib.hv_profile_get(self._ctx, ms, cnt)
+        return {_lib.hv_kernel_name(k).decode(): {"ms": float(ms[k]), "launches": int(cnt[k])}
+                for k in range(A.HV_K_COUNT)}
 
 
 _default: Dict[int, Detector] = {}

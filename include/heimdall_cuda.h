@@ -168,9 +168,10 @@ HV_API hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out);
 HV_API void hv_destroy(hv_ctx *ctx);
 /* Text of the last failure on this context ("" if none). With ctx == NULL: last hv_create failure of this thread. */
 HV_API const char *hv_last_error(const hv_ctx *ctx);
-/* Use the caller's CUDA stream (a cudaStream_t) for the synchronous device-resident entry points; NULL restores
- * the context's own stream. */
-HV_API hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream);
+/* enable != 0: run the synchronous / device-resident entry points on the caller's CUDA stream (a cudaStream_t; NULL
+ * is the legacy default stream, which is what torch.cuda.current_stream().cuda_stream returns by default).
+ * enable == 0: back to the context's own non-blocking stream. */
+HV_API hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream, int32_t enable);
 
 /* Pinned host staging buffers (cudaHostAlloc). Frames handed to hv_detect_batch / hv_submit from such a buffer are
  * copied to the device without an intermediate host copy. */
@@ -260,8 +261,11 @@ HV_API uint64_t *hv_stats_device_ptr(hv_ctx *ctx);
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 /* Kernels launched by this context so far. */
 HV_API uint64_t hv_launch_count(const hv_ctx *ctx);
-/* With HV_FLAG_PROFILE: milliseconds of each kernel of the last synchronous batch (0 when not launched). */
-HV_API hv_status hv_profile_get(hv_ctx *ctx, float ms[HV_K_COUNT]);
+/* Per-kernel device timing with CUDA events recorded on the launching stream.  kernel_mask: bit k enables kernel
+ * HV_K_* = k (0 disables; HV_FLAG_PROFILE at creation enables all).  hv_profile_get waits for the recorded events,
+ * returns the summed milliseconds and the number of timed launches per kernel since the previous call, and clears. */
+HV_API hv_status hv_profile_enable(hv_ctx *ctx, uint32_t kernel_mask);
+HV_API hv_status hv_profile_get(hv_ctx *ctx, float total_ms[HV_K_COUNT], uint32_t counts[HV_K_COUNT]);
 HV_API const char *hv_kernel_name(int32_t k);
 
 #ifdef __cplusplus

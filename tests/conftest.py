@@ -26,7 +26,7 @@ def oracle():
 def detector():
     """One CUDA context for the whole GPU session; fails loudly (no skip) if the extension or the GPU is missing."""
     import heimdall_core
-    det = heimdall_core.Detector(0, keep_blur=True)
+    det = heimdall_core.Detector(0, max_defects_per_frame=8192)
     yield det
     det.close()
 
