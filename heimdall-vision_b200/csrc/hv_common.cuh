@@ -42,6 +42,7 @@ struct PreprocessParams {
     int write_mask;    // write the u8 mask (0 when morphology follows and rewrites it)
     int init_labels;   // write label zeros + word-run-start parents (0 when morphology follows)
     int inverse;       // 1: 255 if px < mean - c (detection path); 0: 255 if px > mean - c
+    int force_generic; // testing: never take the packed fast path
 };
 
 struct ScoreParams {

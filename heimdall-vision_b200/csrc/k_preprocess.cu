@@ -33,26 +33,167 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // exact floor(s / 25) for s <= 6375
 __device__ __forceinline__ uint32_t div25(uint32_t s) { return (s * 5243u) >> 17; }
 
+// Shared-memory plan of one tile (TW x TH outputs, 256 threads).  Column index i of s_g / s_bl is image column
+// x0 - 8 + i; row r of s_g is image row y0 - HALO + r; row r of s_v / s_bl / s_h11 is image row y0 - 5 + r.
+//   s_g   [GH][GW]  u8   gray tile + halo                                  (dead after the blur phase)
+//   s_f   [TH][TW]  u8   mask bytes of the tile            -- aliases s_g
+//   s_v   [BH][VP]  u16  vertical 5-sums, column i stored at i + 2         (fast path only, dead after the blur phase)
+//   s_h11 [BH][TW]  u16  horizontal 11-sums of the blur    -- aliases s_v
+//   s_bl  [BH][GW]  u8   blurred tile + 5-px ring
 template <int TW, int TH, int RB>
 struct Tile {
     static constexpr int HALO = RB + kAdaptHalf;  // rows of gray needed above/below
     static constexpr int HX = 8;                  // column halo, padded to a multiple of 4 for aligned loads
     static constexpr int GW = TW + 2 * HX;
     static constexpr int GH = TH + 2 * HALO;
-    static constexpr int BW = TW + 2 * kAdaptHalf;  // blur columns needed
-    static constexpr int BWP = BW + 2;              // padded pitch
     static constexpr int BH = TH + 2 * kAdaptHalf;
+    static constexpr int VP = GW + 4;  // pitch of s_v in u16
+    static constexpr int G_BYTES = GH * GW;
+    static constexpr int U1_BYTES = (BH * VP * 2 > BH * TW * 2) ? BH * VP * 2 : BH * TW * 2;
+    static constexpr int BL_BYTES = BH * GW;
+    static_assert(TH * TW <= G_BYTES, "s_f must fit inside s_g");
+    static_assert((G_BYTES % 16) == 0 && (U1_BYTES % 16) == 0, "alignment");
 };
+
+// ---- fast path, interior tiles only (every blur pixel is an interior pixel, every window has 121 pixels) ---------
+// Packed u16x2 arithmetic: sums of u8 never overflow a 16-bit lane (5x5: 6375, 11x11 of blur: 30855), so plain 32-bit
+// adds/subs act on both lanes at once; VIMNMX.U16x2 gives the lane-wise compare for the threshold test.
+template <int TW, int TH>
+__device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
+    using T = Tile<TW, TH, 2>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem);
+    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(smem);
+    uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(smem + T::G_BYTES);
+    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(smem + T::G_BYTES);
+    uint8_t(*s_bl)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem + T::G_BYTES + T::U1_BYTES);
+    static_assert(TW == 128 && TH == 32, "thread mappings below are written for 128x32 tiles");
+
+    // A. vertical 5-sums: thread = (column quad q, row segment of 7) -> 36 x 6 = 216 threads
+    if (tid < 36 * 6) {
+        const int q = tid % 36, seg = tid / 36;
+        const int r0 = seg * 7;
+        uint32_t lo[5], hi[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k][4 * q]);
+            lo[k] = prmt(v, 0, 0x4140);
+            hi[k] = prmt(v, 0, 0x4342);
+        }
+        uint32_t alo = lo[0] + lo[1] + lo[2] + lo[3], ahi = hi[0] + hi[1] + hi[2] + hi[3];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k + 4][4 * q]);
+            const uint32_t nlo = prmt(v, 0, 0x4140), nhi = prmt(v, 0, 0x4342);
+            alo += nlo;
+            ahi += nhi;
+            *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q + 4]) = make_uint2(alo, ahi);  // column i at i + 4 ... see B
+            alo -= lo[k % 5];
+            ahi -= hi[k % 5];
+            lo[(k + 4) % 5] = nlo;
+            hi[(k + 4) % 5] = nhi;
+        }
+    }
+    __syncthreads();
+    // B. horizontal 5-sums + /25 -> s_bl.  thread = (row, group of 36 columns) -> 42 x 4 = 168 threads.
+    //    s_v stores column i at index i + 4, so the window i-2..i+2 of output i is s_v[i+2 .. i+6]; a group needs
+    //    s_v[36g + 2 .. 36g + 42), loaded as 11 aligned 8-byte words starting at 36g.
+    if (tid < 42 * 4) {
+        const int g = tid & 3, r = tid >> 2;
+        const uint16_t *vrow = &s_v[r][36 * g];
+        uint32_t pk[22];
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(vrow + 4 * k);
+            pk[2 * k] = t.x;
+            pk[2 * k + 1] = t.y;
+        }
+        // element e (0..43) = s_v[36g + e]; outputs i = 36g + j (j = 0..35) use elements j+2 .. j+6
+        auto el = [&](int e) -> uint32_t { return (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xffffu); };
+        uint32_t s = el(2) + el(3) + el(4) + el(5);
+        uint32_t *brow = reinterpret_cast<uint32_t *>(&s_bl[r][36 * g]);
+#pragma unroll
+        for (int j4 = 0; j4 < 9; j4++) {
+            uint32_t q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = 4 * j4 + u;
+                s += el(j + 6);
+                q[u] = __umulhi(s, 5243u << 15);  // floor(s / 25)
+                s -= el(j + 2);
+            }
+            brow[j4] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+        }
+    }
+    __syncthreads();
+    // C. horizontal 11-sums of the blur.  thread = (row, group of 32 output columns) -> 42 x 4 = 168 threads.
+    //    output column c uses s_bl[c + 3 .. c + 13]; a group needs bytes 32g + 3 .. 32g + 44 = words 8g .. 8g + 11.
+    if (tid < 42 * 4) {
+        const int g = tid & 3, r = tid >> 2;
+        const uint32_t *brow = reinterpret_cast<const uint32_t *>(&s_bl[r][32 * g]);
+        uint32_t wd[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) wd[k] = brow[k];
+        auto by = [&](int e) -> uint32_t { return (wd[e >> 2] >> (8 * (e & 3))) & 0xffu; };
+        uint32_t s = 0;
+#pragma unroll
+        for (int e = 3; e < 13; e++) s += by(e);
+        uint32_t *hrow = reinterpret_cast<uint32_t *>(&s_h11[r][32 * g]);
+#pragma unroll
+        for (int c2 = 0; c2 < 16; c2++) {
+            s += by(2 * c2 + 13);
+            const uint32_t a = s;
+            s -= by(2 * c2 + 3);
+            s += by(2 * c2 + 14);
+            hrow[c2] = a | (s << 16);
+            s -= by(2 * c2 + 4);
+        }
+    }
+    __syncthreads();
+    // D. vertical 11-sums + threshold test.  thread = (column quad, segment of 8 rows) -> 32 x 4 = 128 threads.
+    //    fg  <=>  (px + c + 1) * 121 <= S  <=>  S + 1 > px * 121 + (c + 1) * 121      (all lanes < 65536 for 0 <= c <= 255)
+    if (tid < 32 * 4) {
+        const int q = tid & 31, seg = tid >> 5;
+        const int r0 = seg * 8;
+        const uint32_t K2 = (uint32_t)((cth + 1) * 121) * 0x00010001u;
+        uint32_t rl[11], rh[11];
+        uint32_t alo = 0x00010001u, ahi = 0x00010001u;  // the "+ 1"
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(&s_h11[r0 + k][4 * q]);
+            rl[k] = t.x;
+            rh[k] = t.y;
+            alo += t.x;
+            ahi += t.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(&s_h11[r0 + k + 10][4 * q]);
+            alo += t.x;
+            ahi += t.y;
+            const uint32_t px4 = *reinterpret_cast<const uint32_t *>(&s_bl[r0 + k + 5][4 * q + 8]);
+            const uint32_t xlo = prmt(px4, 0, 0x4140) * 121u + K2, xhi = prmt(px4, 0, 0x4342) * 121u + K2;
+            const uint32_t dlo = __vminu2(__vmaxu2(alo, xlo) - xlo, 0x00010001u);
+            const uint32_t dhi = __vminu2(__vmaxu2(ahi, xhi) - xhi, 0x00010001u);
+            *reinterpret_cast<uint32_t *>(&s_f[r0 + k][4 * q]) = prmt(dlo, dhi, 0x6420) * 255u;
+            alo -= rl[k % 11];
+            ahi -= rh[k % 11];
+            rl[(k + 10) % 11] = t.x;
+            rh[(k + 10) % 11] = t.y;
+        }
+    }
+    __syncthreads();
+}
 
 template <int TW, int TH, int RB>
 __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParams p, uint32_t *bits_out) {
     using T = Tile<TW, TH, RB>;
     static_assert(TW % 32 == 0, "tile width must cover whole bitmask words");
-    __shared__ __align__(16) uint8_t s_g[T::GH][T::GW];
-    __shared__ __align__(16) uint8_t s_bl[T::BH][T::BWP];
-    __shared__ __align__(16) uint16_t s_h11[T::BH][TW];
-    __shared__ __align__(16) uint8_t s_f[TH][TW];
+    __shared__ __align__(16) uint8_t smem[T::G_BYTES + T::U1_BYTES + T::BL_BYTES];
     __shared__ uint32_t s_red[2][8];
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem);
+    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(smem);  // aliases s_g (dead by then)
+    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(smem + T::G_BYTES);
+    uint8_t(*s_bl)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem + T::G_BYTES + T::U1_BYTES);
 
     const int tid = threadIdx.x;
     const int f = blockIdx.z;
@@ -111,60 +252,67 @@ __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParam
     const int vmin = min(mn & 0xffffu, mn >> 16), vmax = max(mx & 0xffffu, mx >> 16);
     const int cth = p.c_thresh;
     const bool flat = p.inverse && !p.write_blur && cth >= 0 && (vmax - vmin) <= cth;
+    // interior tile: the blur ring (tile +- 5) lies >= RB pixels inside the image, so no border rule applies anywhere
+    const bool interior = x0 >= T::HALO && y0 >= T::HALO && x0 + TW + T::HALO <= W && y0 + TH + T::HALO <= H;
 
     if (!flat) {
-        // ---- 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior) ---
-        for (int idx = tid; idx < T::BH * T::BW; idx += 256) {
-            const int r = idx / T::BW, c = idx - r * T::BW;
-            const int gy = y0 - kAdaptHalf + r, gx = x0 - kAdaptHalf + c;
-            const int ry = r + RB, rx = c + (T::HX - kAdaptHalf);
-            uint32_t v = 0;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                if (RB > 0 && gy >= RB && gy < H - RB && gx >= RB && gx < W - RB) {
-                    uint32_t s = 0;
+        if (RB == 2 && TW == 128 && TH == 32 && interior && p.inverse && !p.write_blur && cth >= 0 && cth <= 255 &&
+            !p.force_generic) {
+            fast_tile_rb2<128, 32>(smem, tid, cth);
+        } else {
+            // ---- generic path: any border, any c, either comparison direction --------------------------------------
+            // 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior)
+            for (int idx = tid; idx < T::BH * (TW + 2 * kAdaptHalf); idx += 256) {
+                const int r = idx / (TW + 2 * kAdaptHalf), i = idx - r * (TW + 2 * kAdaptHalf) + (T::HX - kAdaptHalf);
+                const int gy = y0 - kAdaptHalf + r, gx = x0 - T::HX + i;
+                const int ry = r + RB;
+                uint32_t v = 0;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    if (RB > 0 && gy >= RB && gy < H - RB && gx >= RB && gx < W - RB) {
+                        uint32_t s = 0;
 #pragma unroll
-                    for (int dy = -RB; dy <= RB; dy++)
+                        for (int dy = -RB; dy <= RB; dy++)
 #pragma unroll
-                        for (int dx = -RB; dx <= RB; dx++) s += s_g[ry + dy][rx + dx];
-                    v = (RB == 2) ? div25(s) : s / ((2 * RB + 1) * (2 * RB + 1));
-                } else {
-                    v = s_g[ry][rx];
+                            for (int dx = -RB; dx <= RB; dx++) s += s_g[ry + dy][i + dx];
+                        v = (RB == 2) ? div25(s) : s / ((2 * RB + 1) * (2 * RB + 1));
+                    } else {
+                        v = s_g[ry][i];
+                    }
+                    if (p.write_blur && r >= kAdaptHalf && r < kAdaptHalf + TH && i >= T::HX && i < T::HX + TW)
+                        b.blur[((size_t)f * H + gy) * W + gx] = (uint8_t)v;
                 }
-                if (p.write_blur && r >= kAdaptHalf && r < kAdaptHalf + TH && c >= kAdaptHalf &&
-                    c < kAdaptHalf + TW)
-                    b.blur[((size_t)f * H + gy) * W + gx] = (uint8_t)v;
+                s_bl[r][i] = (uint8_t)v;
             }
-            s_bl[r][c] = (uint8_t)v;
-        }
-        __syncthreads();
-        // ---- 3. horizontal 11-sums ------------------------------------------------------------------------------
-        for (int idx = tid; idx < T::BH * TW; idx += 256) {
-            const int r = idx / TW, c = idx - r * TW;
-            uint32_t s = 0;
+            __syncthreads();
+            // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
+            for (int idx = tid; idx < T::BH * TW; idx += 256) {
+                const int r = idx / TW, c = idx - r * TW;
+                uint32_t s = 0;
 #pragma unroll
-            for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][c + k];
-            s_h11[r][c] = (uint16_t)s;
-        }
-        __syncthreads();
-        // ---- 4. vertical 11-sums + threshold test -------------------------------------------------------------
-        for (int idx = tid; idx < TH * TW; idx += 256) {
-            const int r = idx / TW, c = idx - r * TW;
-            const int gy = y0 + r, gx = x0 + c;
-            uint8_t fg = 0;
-            if (gy < H && gx < W) {
-                int s = 0;
-#pragma unroll
-                for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_h11[r + k][c];
-                const int rows = min(gy + kAdaptHalf, H - 1) - max(gy - kAdaptHalf, 0) + 1;
-                const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
-                const int cnt = rows * cols;
-                const int px = s_bl[r + kAdaptHalf][c + kAdaptHalf];
-                const bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
-                fg = t ? 255 : 0;
+                for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][c + (T::HX - kAdaptHalf) + k];
+                s_h11[r][c] = (uint16_t)s;
             }
-            s_f[r][c] = fg;
+            __syncthreads();
+            // 4. vertical 11-sums + threshold test (window truncated at the image border: cnt = rows * cols)
+            for (int idx = tid; idx < TH * TW; idx += 256) {
+                const int r = idx / TW, c = idx - r * TW;
+                const int gy = y0 + r, gx = x0 + c;
+                uint8_t fg = 0;
+                if (gy < H && gx < W) {
+                    int s = 0;
+#pragma unroll
+                    for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_h11[r + k][c];
+                    const int rows = min(gy + kAdaptHalf, H - 1) - max(gy - kAdaptHalf, 0) + 1;
+                    const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
+                    const int cnt = rows * cols;
+                    const int px = s_bl[r + kAdaptHalf][c + T::HX];
+                    const bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
+                    fg = t ? 255 : 0;
+                }
+                s_f[r][c] = fg;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- 5. outputs: u8 mask, bit-packed mask, label plane ------------------------------------------------------

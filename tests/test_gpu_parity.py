@@ -241,7 +241,8 @@ def test_capacity_error_is_loud(detector):
             det.detect_batch(img, p)
         res = det.detect_batch(img, p, raise_on_capacity=False)
         assert res.status == hc._abi.HV_ERR_CAPACITY and res.frames["status"][0] == hc._abi.HV_ERR_CAPACITY
-        assert res.frames["n_components"][0] > 100      # the true count is still reported
+        assert res.frames["n_components"][0] > 8        # the true component count is still reported
+        assert res.frames["n_defects"][0] == 8          # ... and the defect slots that exist are filled
         # a frame that fits is unaffected
         ok = det.detect_batch(np.full((64, 64, 1), 200, np.uint8))
         assert ok.status == 0 and ok.frames["n_components"][0] == 0
