@@ -62,9 +62,12 @@ struct PinBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf<uint8_t> in, gray, blur, mask;
+    DevBuf<uint8_t> in, gray, blur, mask, rowflags;
     DevBuf<uint16_t> gauss_tmp;
-    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount;
+    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags;
+    PinBuf<uint32_t> h_flags;
+    bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
+    ScoreParams score{};
     DevBuf<int32_t> labels;
     DevBuf<hv_blob> blobs;
     DevBuf<hv_defect> defects;
@@ -79,9 +82,10 @@ struct Slot {
     const uint8_t *d_input = nullptr;  // device frames the batch was run on (for the gray debug copy, c == 1)
     int64_t ticket = -1;
     void release() {
-        in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release();
+        in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release(), rowflags.release();
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
+        frame_flags.release(), h_flags.release();
         h_results.release(), h_defects.release();
         if (done) cudaEventDestroy(done);
         if (stream) cudaStreamDestroy(stream);
@@ -100,9 +104,14 @@ struct hv_ctx {
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
     hv_line_stats *d_stats = nullptr;
+    unsigned long long *d_phase_ns = nullptr;
     uint64_t launches = 0;
     int64_t next_ticket = 1;
     int next_slot = 1;
+    // CCL path selection: sparse masks go through the fused per-frame kernel; if a batch needed the global-memory
+    // fallback the next batches use the global path directly and the fused kernel is re-tried every 8th batch
+    bool dense_hint = false;
+    uint32_t dense_batches = 0;
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -257,17 +266,46 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     if (need_gauss) HV_TRY_CUDA(ctx, s.gauss_tmp.reserve(px));
     if (need_mask) HV_TRY_CUDA(ctx, s.mask.reserve(px));
     if (need_labels) HV_TRY_CUDA(ctx, s.labels.reserve(px));
+    HV_TRY_CUDA(ctx, s.rowflags.reserve((size_t)n * (((size_t)h * ((w + 127) / 128) + 15) & ~(size_t)15)));
     HV_TRY_CUDA(ctx, s.bits.reserve(words));
     HV_TRY_CUDA(ctx, s.bits_tmp.reserve(words));
     HV_TRY_CUDA(ctx, s.rootbits.reserve(words));
     HV_TRY_CUDA(ctx, s.rankbase.reserve(words));
     HV_TRY_CUDA(ctx, s.ncomp.reserve(n));
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
+    HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
+    HV_TRY_CUDA(ctx, s.h_flags.reserve(n));
     HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
     HV_TRY_CUDA(ctx, s.defects.reserve((size_t)n * defect_cap_for(ctx)));
     HV_TRY_CUDA(ctx, s.results.reserve(n));
     HV_TRY_CUDA(ctx, s.h_results.reserve(n));
     HV_TRY_CUDA(ctx, s.h_defects.reserve((size_t)n * defect_cap_for(ctx)));
+    return HV_OK;
+}
+
+// The global-memory CCL path (K2..K6): robust for any density; b.frame_select restricts it to flagged frames.
+hv_status enqueue_global_ccl(hv_ctx *ctx, const BatchView &b, const ScoreParams &sp, cudaStream_t st) {
+    {
+        ProfScope ps(ctx, HV_K_CCL_MERGE, st);
+        HV_TRY_CUDA(ctx, launch_ccl_merge(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_FLATTEN, st);
+        HV_TRY_CUDA(ctx, launch_ccl_flatten(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_SCAN, st);
+        HV_TRY_CUDA(ctx, launch_ccl_scan(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_CCL_LABEL, st);
+        HV_TRY_CUDA(ctx, launch_ccl_label(b, st));
+    }
+    {
+        ProfScope ps(ctx, HV_K_SCORE, st);
+        HV_TRY_CUDA(ctx, launch_score(b, sp, st));
+    }
+    ctx->launches += 5;
     return HV_OK;
 }
 
@@ -314,6 +352,9 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.mask = d_mask ? d_mask : s.mask.p;
     b.bits = s.bits.p;
     b.bits_tmp = s.bits_tmp.p;
+    b.rowflags = s.rowflags.p;
+    b.tiles_x = (w + 127) / 128;
+    b.rf_stride = ((size_t)h * b.tiles_x + 15) & ~(size_t)15;
     b.labels = d_labels ? d_labels : s.labels.p;
     b.rootbits = s.rootbits.p;
     b.rankbase = s.rankbase.p;
@@ -325,10 +366,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p;
     b.stats = ctx->d_stats;
+    b.frame_flags = s.frame_flags.p;
+    b.frame_select = nullptr;
+    b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
 
     PreprocessParams pp{};
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
+    pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
     pp.write_mask = morph ? 0 : 1;
     pp.init_labels = morph ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
@@ -368,30 +413,25 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         int nl = 0;
         HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
         HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b, st));
-        ctx->launches += nl + 1;
-    }
-    {
-        ProfScope ps(ctx, HV_K_CCL_MERGE, st);
-        HV_TRY_CUDA(ctx, launch_ccl_merge(b, st));
-    }
-    {
-        ProfScope ps(ctx, HV_K_CCL_FLATTEN, st);
-        HV_TRY_CUDA(ctx, launch_ccl_flatten(b, st));
-    }
-    {
-        ProfScope ps(ctx, HV_K_CCL_SCAN, st);
-        HV_TRY_CUDA(ctx, launch_ccl_scan(b, st));
-    }
-    {
-        ProfScope ps(ctx, HV_K_CCL_LABEL, st);
-        HV_TRY_CUDA(ctx, launch_ccl_label(b, st));
+        HV_TRY_CUDA(ctx, launch_rowflags_from_bits(b, st));
+        ctx->launches += nl + 2;
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
-    {
-        ProfScope ps(ctx, HV_K_SCORE, st);
-        HV_TRY_CUDA(ctx, launch_score(b, sp, st));
+    bool fused = !(ctx->cfg.flags & HV_FLAG_GLOBAL_CCL) && ccl_frame_supported(b);
+    if (fused && ctx->dense_hint) {
+        ctx->dense_batches++;
+        if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
     }
-    ctx->launches += 5;
+    if (fused) {
+        ProfScope ps(ctx, HV_K_CCL_FRAME, st);
+        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, st));
+        ctx->launches += 1;
+    } else {
+        hv_status rg = enqueue_global_ccl(ctx, b, sp, st);
+        if (rg != HV_OK) return rg;
+    }
+    s.used_fused = fused;
+    s.score = sp;
     s.view = b;
     s.has_batch = true;
     s.have_blur = separate_blur || want_blur;
@@ -405,6 +445,31 @@ hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_results.p, b.results, sizeof(hv_frame_result) * b.n, cudaMemcpyDeviceToHost, st));
     HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_defects.p, b.defects, sizeof(hv_defect) * (size_t)b.n * b.defect_cap,
                                      cudaMemcpyDeviceToHost, st));
+    if (s.used_fused)
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_flags.p, b.frame_flags, sizeof(uint32_t) * b.n, cudaMemcpyDeviceToHost, st));
+    return HV_OK;
+}
+
+// After the read-back has completed: if the fused kernel flagged frames it could not hold in shared memory, run the
+// global-memory path on exactly those frames (same stream), read back again and wait.
+hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
+    if (!s.used_fused) return HV_OK;
+    bool any = false;
+    for (int f = 0; f < s.view.n; f++) any |= s.h_flags.p[f] != 0;
+    if (!any) {
+        ctx->dense_hint = false;
+        return HV_OK;
+    }
+    BatchView b = s.view;
+    b.frame_select = b.frame_flags;
+    hv_status rs = enqueue_global_ccl(ctx, b, s.score, st);
+    if (rs != HV_OK) return rs;
+    s.used_fused = false;
+    rs = enqueue_readback(ctx, s, st);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->dense_hint = true;
+    ctx->dense_batches = 0;
     return HV_OK;
 }
 
@@ -579,9 +644,20 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
         }
     }
     if (ctx->cfg.flags & HV_FLAG_PROFILE) ctx->prof_mask = 0xffffffffu;
+    if (configure_ccl_frame() != cudaSuccess) {
+        g_create_error = "cannot configure shared memory for the per-frame CCL kernel";
+        hv_destroy(ctx);
+        return HV_ERR_CUDA;
+    }
     if (cudaMalloc(reinterpret_cast<void **>(&ctx->d_stats), sizeof(hv_line_stats)) != cudaSuccess ||
         cudaMemset(ctx->d_stats, 0, sizeof(hv_line_stats)) != cudaSuccess) {
         g_create_error = "stats allocation failed";
+        hv_destroy(ctx);
+        return HV_ERR_CUDA;
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&ctx->d_phase_ns), 256 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_phase_ns, 0, 256 * sizeof(unsigned long long)) != cudaSuccess) {
+        g_create_error = "debug buffer allocation failed";
         hv_destroy(ctx);
         return HV_ERR_CUDA;
     }
@@ -600,6 +676,7 @@ void hv_destroy(hv_ctx *ctx) {
     }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->d_phase_ns) cudaFree(ctx->d_phase_ns);
     ctx->u_a.release(), ctx->u_b.release(), ctx->u_c.release();
     ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release();
     delete ctx;
@@ -657,6 +734,8 @@ hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *def
     hv_status rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    rs = resolve_fallback(ctx, s, st);
+    if (rs != HV_OK) return rs;
     return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
 }
 
@@ -665,6 +744,14 @@ hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug) {
     Slot &s = ctx->slots[0];
     if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (s.used_fused) {  // make sure flagged frames have been completed by the global path before copying
+        cudaStream_t st = sync_stream(ctx);
+        hv_status rs = enqueue_readback(ctx, s, st);
+        if (rs != HV_OK) return rs;
+        HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+        rs = resolve_fallback(ctx, s, st);
+        if (rs != HV_OK) return rs;
+    }
     return copy_debug(ctx, s, sync_stream(ctx), debug);
 }
 
@@ -700,6 +787,8 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
     rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    rs = resolve_fallback(ctx, s, st);
+    if (rs != HV_OK) return rs;
     hv_status rc = unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
     hv_status rd = copy_debug(ctx, s, st, debug);
     return rd != HV_OK ? rd : rc;
@@ -749,6 +838,8 @@ hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defe
         if (s.ticket == ticket && ticket > 0) {
             HV_TRY_CUDA(ctx, cudaEventSynchronize(s.done));
             s.ticket = -1;
+            hv_status rf = resolve_fallback(ctx, s, s.stream);
+            if (rf != HV_OK) return rf;
             return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
         }
     }
@@ -837,6 +928,7 @@ static void fill_view(hv_ctx *ctx, Slot &s, BatchView &b, int h, int w) {
     b.blobs = s.blobs.p, b.blob_cap = blob_cap_for(ctx, h, w);
     b.defects = s.defects.p, b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p, b.stats = ctx->d_stats;
+    b.frame_flags = s.frame_flags.p, b.frame_select = nullptr;
 }
 
 hv_status hv_find_contours(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, double min_area,
@@ -991,9 +1083,17 @@ hv_status hv_profile_get(hv_ctx *ctx, float total_ms[HV_K_COUNT], uint32_t count
     return HV_OK;
 }
 
+hv_status hv_debug_phase_times(hv_ctx *ctx, uint64_t out_ns[256]) {
+    if (!ctx || !out_ns) return HV_ERR_INVALID_ARGUMENT;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
+    HV_TRY_CUDA(ctx, cudaMemcpy(out_ns, ctx->d_phase_ns, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return HV_OK;
+}
+
 const char *hv_kernel_name(int32_t k) {
-    static const char *names[HV_K_COUNT] = {"gray3",       "preprocess_mask", "morph",     "ccl_merge",
-                                            "ccl_flatten", "ccl_scan",        "ccl_label", "score"};
+    static const char *names[HV_K_COUNT] = {"gray3",       "preprocess_mask", "morph",     "ccl_merge", "ccl_flatten",
+                                            "ccl_scan",    "ccl_label",       "score",     "ccl_frame_fused"};
     return (k >= 0 && k < HV_K_COUNT) ? names[k] : "?";
 }
 

@@ -22,6 +22,9 @@ struct BatchView {
     uint8_t *mask;             // n*h*w  final mask {0,255}
     uint32_t *bits;            // n*h*ww bit-packed final mask, bit x&31 of word x>>5
     uint32_t *bits_tmp;        // scratch for morphology
+    uint8_t *rowflags;         // n * rf_stride: per (row, 128-px tile) nibble, bit k = word 4*tile+k of that row is non-zero
+    int tiles_x;               // ceil(w / 128)
+    size_t rf_stride;          // bytes per frame in rowflags (h * tiles_x rounded up to 16)
     int32_t *labels;           // n*h*w  union-find parents (+1) during CCL, canonical labels afterwards
     uint32_t *rootbits;        // n*h*ww
     uint32_t *rankbase;        // n*h*ww root counts -> exclusive prefix
@@ -33,6 +36,9 @@ struct BatchView {
     int defect_cap;
     hv_frame_result *results;  // n
     hv_line_stats *stats;      // 1
+    uint32_t *frame_flags;     // n: written by the fused per-frame kernel, 1 = frame needs the global-memory CCL path
+    unsigned long long *phase_ns;  // 16 or NULL: per-phase timestamps of frame 0 in the fused kernel (debug)
+    const uint32_t *frame_select;  // n or NULL: when set, the global-path kernels only touch frames with a non-zero entry
 };
 
 struct PreprocessParams {
@@ -60,12 +66,16 @@ cudaError_t launch_gray3(const uint8_t *d_img, int n, int h, int w, size_t row_s
                          uint8_t *d_gray, cudaStream_t s);
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s);
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
+cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
 cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s);
 cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s);
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, cudaStream_t s);
+bool ccl_frame_supported(const BatchView &b);
+cudaError_t configure_ccl_frame();
 
 // generic single-frame stage kernels (python-facing utilities, not the hot path)
 cudaError_t launch_box_blur_generic(const uint8_t *src, int h, int w, int nch, int radius, uint8_t *dst,

@@ -39,11 +39,26 @@ __device__ __forceinline__ int uf_find(const int32_t *L, int a) {
     return a;
 }
 
+// find with intermediate pointer jumping: every node visited on the way is re-pointed at its grandparent
+// (atomicMin keeps the parent of a node monotonically decreasing, so concurrent unions are never undone).
+__device__ __forceinline__ int uf_find_compress(int32_t *L, int a) {
+    int p = ld_parent(L, a);
+    if (p == a) return a;
+    int prev = a;
+    while (true) {
+        const int next = ld_parent(L, p);
+        if (next == p) return p;
+        atomicMin(L + prev, next + 1);
+        prev = p;
+        p = next;
+    }
+}
+
 // Lock-free union by minimum index.  Invariant: parent(a) <= a, so chains strictly decrease and terminate.
 __device__ __forceinline__ void uf_union(int32_t *L, int a, int b) {
     while (true) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find_compress(L, a);
+        b = uf_find_compress(L, b);
         if (a == b) return;
         if (a < b) {
             const int t = a;
@@ -70,6 +85,7 @@ __global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
         const uint32_t m = b.bits[i];
         if (!m) continue;
         const size_t f = i / words_per_frame;
+        if (b.frame_select && !b.frame_select[f]) continue;
         const int wi = (int)(i - f * words_per_frame);
         const int y = wi / b.ww, wx = wi - y * b.ww;
         int32_t *L = b.labels + f * (size_t)b.h * b.w;
@@ -97,6 +113,7 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t m = b.bits[i];
         uint32_t roots = 0;
+        if (b.frame_select && !b.frame_select[i / words_per_frame]) continue;
         if (m) {
             const size_t f = i / words_per_frame;
             const int wi = (int)(i - f * words_per_frame);
@@ -121,28 +138,31 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
 }
 
 // One CTA per frame: exclusive scan of the per-word root counts (raster order), component count, blob-table reset.
+// Each of the 32 warps owns a contiguous chunk of the frame's words and walks it 32 words (128 B, coalesced) at a
+// time.  Only words that contain a root ever have their prefix read back (K5 looks up rankbase[word of the root]), so
+// groups of 32 words without any root are skipped after one load + ballot.
 __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const int f = blockIdx.x;
+    if (b.frame_select && !b.frame_select[f]) return;
     const int nwords = b.h * b.ww;
     uint32_t *cnt = b.rankbase + (size_t)f * nwords;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (nwords + 1023) / 1024;
-    const int beg = min(tid * per, nwords), end = min(beg + per, nwords);
+    const int groups = (nwords + 31) / 32;              // 32-word groups in the frame
+    const int gper = (groups + 31) / 32;                // groups per warp
+    const int g0 = min(wid * gper, groups), g1 = min(g0 + gper, groups);
     uint32_t sum = 0;
-    for (int i = beg; i < end; i++) sum += cnt[i];
-    // block exclusive scan of `sum`
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    for (int g = g0; g < g1; g++) {
+        const int i = g * 32 + lane;
+        sum += i < nwords ? cnt[i] : 0u;
     }
-    if (lane == 31) s_warp[wid] = incl;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_warp[wid] = sum;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = s_warp[lane];
+        const uint32_t w = s_warp[lane];
         uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -153,11 +173,21 @@ __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
         if (lane == 31) s_total = wi;
     }
     __syncthreads();
-    uint32_t run = s_warp[wid] + incl - sum;
-    for (int i = beg; i < end; i++) {
-        const uint32_t c = cnt[i];
-        cnt[i] = run;
-        run += c;
+    uint32_t run = s_warp[wid];
+    if (sum) {  // warp-uniform: chunks without roots need no prefixes at all
+        for (int g = g0; g < g1; g++) {
+            const int i = g * 32 + lane;
+            const uint32_t c = i < nwords ? cnt[i] : 0u;
+            if (!__any_sync(0xffffffffu, c != 0)) continue;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (c) cnt[i] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     const uint32_t ncomp = s_total;
     if (tid == 0) {
@@ -180,46 +210,72 @@ __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
     }
 }
 
+// K5.  A warp owns a patch of 4 words x 8 rows (128 x 8 pixels) so that runs of the same blob in neighbouring rows
+// and words meet in one warp: lanes whose current run carries the same label are grouped with __match_any_sync, their
+// partial statistics are combined with redux.sync, and one lane per group issues the atomics.
 __global__ void __launch_bounds__(256) k_ccl_label(BatchView b) {
+    const int lane = threadIdx.x & 31;
+    const int pw = (b.ww + 3) >> 2, ph = (b.h + 7) >> 3;  // patches per row / per column
+    const size_t patches_per_frame = (size_t)pw * ph;
+    const size_t total = patches_per_frame * b.n;
     const size_t words_per_frame = (size_t)b.h * b.ww;
-    const size_t total = words_per_frame * b.n;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t m = b.bits[i];
-        if (!m) continue;
-        const size_t f = i / words_per_frame;
-        const int wi = (int)(i - f * words_per_frame);
-        const int y = wi / b.ww, wx = wi - y * b.ww;
+    const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t pi = warp0; pi < total; pi += nwarps) {
+        const size_t f = pi / patches_per_frame;
+        if (b.frame_select && !b.frame_select[f]) continue;
+        const int pj = (int)(pi - f * patches_per_frame);
+        const int py = pj / pw, px = pj - py * pw;
+        const int y = py * 8 + (lane >> 2), wx = px * 4 + (lane & 3);
+        const bool inside = y < b.h && wx < b.ww;
+        const uint32_t m = inside ? b.bits[f * words_per_frame + (size_t)y * b.ww + wx] : 0u;
+        const uint32_t any = __ballot_sync(0xffffffffu, m != 0);
+        if (!any) continue;
         int32_t *L = b.labels + f * (size_t)b.h * b.w;
         const uint32_t *rootbits = b.rootbits + f * words_per_frame;
         const uint32_t *rankbase = b.rankbase + f * words_per_frame;
         hv_blob *blobs = b.blobs + f * (size_t)b.blob_cap;
         const int row = y * b.w + wx * 32;
-        atomicAdd(b.fgcount + f, (uint32_t)__popc(m));
+        uint32_t fgsum = __popc(m);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) fgsum += __shfl_xor_sync(0xffffffffu, fgsum, o);
+        if (lane == 0) atomicAdd(b.fgcount + f, fgsum);
         uint32_t rest = m;
-        while (rest) {
-            const int bit = __ffs(rest) - 1;
-            // run [bit, bit+len)
-            const uint32_t shifted = ~(rest >> bit);
-            const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
-            rest = (bit + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << bit));
-            const int s = row + bit;
-            const int r = L[s] - 1;  // flattened: the root itself
-            const int ry = r / b.w, rx = r - ry * b.w;
-            const int rw = ry * b.ww + (rx >> 5);
-            const uint32_t rank = rankbase[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u));
-            const int label = (int)rank + 1;
-            for (int k = 0; k < len; k++) L[s + k] = label;
-            if (rank < (uint32_t)b.blob_cap) {
-                hv_blob *q = blobs + rank;
+        while (true) {
+            const uint32_t act = __ballot_sync(0xffffffffu, rest != 0);
+            if (!act) break;
+            if (rest) {
+                const int bit = __ffs(rest) - 1;
+                const uint32_t shifted = ~(rest >> bit);
+                const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;  // run [bit, bit+len)
+                rest = (bit + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << bit));
+                const int s = row + bit;
+                const int r = L[s] - 1;  // flattened by K3: the root itself
+                const int ry = r / b.w, rx = r - ry * b.w;
+                const int rw = ry * b.ww + (rx >> 5);
+                const uint32_t rank = rankbase[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u));
+                const int label = (int)rank + 1;
+                for (int k = 0; k < len; k++) L[s + k] = label;
                 const uint32_t xs = wx * 32 + bit, xe = xs + len - 1;
-                atomicAdd(&q->area, (uint32_t)len);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_y), (unsigned long long)y * len);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_x),
-                          ((unsigned long long)(xs + xe) * len) >> 1);
-                atomicMin(&q->ymin, (uint32_t)y);
-                atomicMax(&q->ymax, (uint32_t)y);
-                atomicMin(&q->xmin, xs);
-                atomicMax(&q->xmax, xe);
+                const uint32_t grp = __match_any_sync(act, rank);
+                const uint32_t area = __reduce_add_sync(grp, (uint32_t)len);
+                const uint32_t sy = __reduce_add_sync(grp, (uint32_t)y * (uint32_t)len);       // <= 8 rows x 128 px x y
+                const uint32_t sx = __reduce_add_sync(grp, ((xs + xe) * (uint32_t)len) >> 1);  // fits 32 bits
+                const uint32_t ymax = __reduce_max_sync(grp, (uint32_t)y);
+                const uint32_t xmin = __reduce_min_sync(grp, xs);
+                const uint32_t xmax = __reduce_max_sync(grp, xe);
+                if (rank < (uint32_t)b.blob_cap) {
+                    hv_blob *q = blobs + rank;
+                    if (r == s) q->ymin = (uint32_t)y;  // the root run is the raster-first pixel: its row is ymin
+                    if (lane == __ffs(grp) - 1) {
+                        atomicAdd(&q->area, area);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_y), (unsigned long long)sy);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&q->sum_x), (unsigned long long)sx);
+                        atomicMax(&q->ymax, ymax);
+                        atomicMin(&q->xmin, xmin);
+                        atomicMax(&q->xmax, xmax);
+                    }
+                }
             }
         }
     }
@@ -248,6 +304,23 @@ __global__ void __launch_bounds__(256) k_bits_to_mask_labels(BatchView b) {
     }
 }
 
+// occupancy nibbles from a bit-packed mask (needed when morphology rewrote the bits K1 had summarised)
+__global__ void __launch_bounds__(256) k_rowflags_from_bits(BatchView b) {
+    const size_t per_frame = (size_t)b.h * b.tiles_x;
+    const size_t total = per_frame * b.n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = i / per_frame;
+        const int j = (int)(i - f * per_frame);
+        const int y = j / b.tiles_x, tx = j - y * b.tiles_x;
+        const uint32_t *row = b.bits + (f * b.h + y) * (size_t)b.ww;
+        uint32_t nib = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (4 * tx + k < b.ww && row[4 * tx + k]) nib |= 1u << k;
+        b.rowflags[f * b.rf_stride + j] = (uint8_t)nib;
+    }
+}
+
 int grid_for(size_t work_items, int per_block) {
     size_t g = (work_items + per_block - 1) / per_block;
     const size_t cap = 148 * 32;
@@ -271,7 +344,12 @@ cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s) {
-    k_ccl_label<<<grid_for((size_t)b.n * b.h * b.ww, 256), 256, 0, s>>>(b);
+    const size_t patches = (size_t)b.n * ((b.ww + 3) / 4) * ((b.h + 7) / 8);
+    k_ccl_label<<<grid_for(patches * 32, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s) {
+    k_rowflags_from_bits<<<grid_for((size_t)b.n * b.h * b.tiles_x, 256), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s) {

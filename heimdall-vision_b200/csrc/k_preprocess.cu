@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t div25(uint32_t s) { return (s * 5243u) >> 17
 // x0 - 8 + i; row r of s_g is image row y0 - HALO + r; row r of s_v / s_bl / s_h11 is image row y0 - 5 + r.
 //   s_g   [GH][GW]  u8   gray tile + halo                                  (dead after the blur phase)
 //   s_f   [TH][TW]  u8   mask bytes of the tile            -- aliases s_g
-//   s_v   [BH][VP]  u16  vertical 5-sums, column i stored at i + 2         (fast path only, dead after the blur phase)
+//   s_v   [BH][VP]  u16  vertical 5-sums, column i stored at i + 4         (fast path only, dead after the blur phase)
 //   s_h11 [BH][TW]  u16  horizontal 11-sums of the blur    -- aliases s_v
 //   s_bl  [BH][GW]  u8   blurred tile + 5-px ring
 template <int TW, int TH, int RB>
@@ -47,7 +47,7 @@ struct Tile {
     static constexpr int GW = TW + 2 * HX;
     static constexpr int GH = TH + 2 * HALO;
     static constexpr int BH = TH + 2 * kAdaptHalf;
-    static constexpr int VP = GW + 4;  // pitch of s_v in u16
+    static constexpr int VP = GW + 8;  // pitch of s_v in u16 (column i is stored at i + 4; 4 spare on each side)
     static constexpr int G_BYTES = GH * GW;
     static constexpr int U1_BYTES = (BH * VP * 2 > BH * TW * 2) ? BH * VP * 2 : BH * TW * 2;
     static constexpr int BL_BYTES = BH * GW;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
             const uint32_t nlo = prmt(v, 0, 0x4140), nhi = prmt(v, 0, 0x4342);
             alo += nlo;
             ahi += nhi;
-            *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q + 4]) = make_uint2(alo, ahi);  // column i at i + 4 ... see B
+            *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q + 4]) = make_uint2(alo, ahi);  // column i at index i + 4
             alo -= lo[k % 5];
             ahi -= hi[k % 5];
             lo[(k + 4) % 5] = nlo;
@@ -185,11 +185,10 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
 }
 
 template <int TW, int TH, int RB>
-__global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParams p, uint32_t *bits_out) {
+__global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessParams p, uint32_t *bits_out) {
     using T = Tile<TW, TH, RB>;
     static_assert(TW % 32 == 0, "tile width must cover whole bitmask words");
     __shared__ __align__(16) uint8_t smem[T::G_BYTES + T::U1_BYTES + T::BL_BYTES];
-    __shared__ uint32_t s_red[2][8];
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem);
     uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(smem);  // aliases s_g (dead by then)
     uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(smem + T::G_BYTES);
@@ -202,56 +201,77 @@ __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParam
     const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
     const size_t gpitch = b.gray_row_stride;
     const bool aligned_in = ((reinterpret_cast<uintptr_t>(gray) | gpitch) & 3) == 0;
+    const bool vec = (W & 3) == 0;
+    uint8_t *mask = b.mask + (size_t)f * H * W;
+    int32_t *labels = b.labels + (size_t)f * H * W;
 
-    // ---- 1. stage the gray tile + halo in shared memory, tracking min/max of the in-image pixels -------------
-    uint32_t mn = 0x00ff00ffu, mx = 0u;  // packed u16x2 running min / max
-    for (int idx = tid; idx < T::GH * (T::GW / 4); idx += 256) {
-        const int r = idx / (T::GW / 4), cw = idx - r * (T::GW / 4);
-        const int gy = y0 - T::HALO + r, gx = x0 - T::HX + 4 * cw;
-        uint32_t v = 0;
-        if (gy >= 0 && gy < H) {
-            const uint8_t *row = gray + (size_t)gy * gpitch;
-            if (aligned_in && gx >= 0 && gx + 3 < W) {
-                v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-                const uint32_t lo = prmt(v, 0, 0x4140), hi = prmt(v, 0, 0x4342);
-                mn = __vminu2(__vminu2(mn, lo), hi);
-                mx = __vmaxu2(__vmaxu2(mx, lo), hi);
-            } else {
+    // ---- 1. stage the gray tile + halo in shared memory and test it for flatness on the way ------------------------
+    // Flatness (conservative, exact in effect): if every in-image pixel of the tile + halo satisfies
+    // |g - ref| <= floor(c/2) for one reference pixel, the range is <= c and the mask of the tile is empty (see the
+    // header).  VABSDIFF4 gives the four byte distances; (d & 0x7f) + (127 - T) sets bit 7 of a byte iff d > T, and
+    // d itself has bit 7 set iff d >= 128, so OR-accumulating both and testing 0x80808080 decides the whole tile.
+    const int cth = p.c_thresh;
+    const bool try_flat = p.inverse && !p.write_blur && !p.force_generic && cth >= 0;
+    uint32_t ref4 = 0;
+    if (try_flat) ref4 = 0x01010101u * __ldg(gray + (size_t)min(y0 + TH / 2, H - 1) * gpitch + min(x0 + TW / 2, W - 1));
+    const uint32_t kq = 0x01010101u * (uint32_t)(127 - min(cth >> 1, 127));
+    uint32_t acc = 0;
+    auto flat_test = [&](uint32_t v) {
+        const uint32_t d = __vabsdiffu4(v, ref4);
+        acc |= d | ((d & 0x7f7f7f7fu) + kq);
+    };
+    const bool full_in = x0 >= T::HX && x0 + TW + T::HX <= W && y0 >= T::HALO && y0 + TH + T::HALO <= H &&
+                         ((reinterpret_cast<uintptr_t>(gray) | gpitch) & 7) == 0;
+    if (full_in) {
+        // all loads of the thread are issued before the first use: one DRAM latency per tile instead of one per word
+        const uint8_t *base = gray + (size_t)(y0 - T::HALO) * gpitch + (x0 - T::HX);
+        constexpr int NW = T::GH * (T::GW / 8);
+        constexpr int PER = (NW + 255) / 256;
+        uint2 v[PER];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x = gx + k;
-                    if (x >= 0 && x < W) {
-                        const uint32_t q = __ldg(row + x);
-                        v |= q << (8 * k);
-                        mn = __vminu2(mn, q | (q << 16));
-                        mx = __vmaxu2(mx, q | (q << 16));
+        for (int k = 0; k < PER; k++) {
+            const int idx = tid + 256 * k;
+            const int r = idx / (T::GW / 8), cw = idx - r * (T::GW / 8);
+            v[k] = make_uint2(ref4, ref4);
+            if (idx < NW) v[k] = __ldg(reinterpret_cast<const uint2 *>(base + (size_t)r * gpitch + 8 * cw));
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int idx = tid + 256 * k;
+            const int r = idx / (T::GW / 8), cw = idx - r * (T::GW / 8);
+            flat_test(v[k].x);
+            flat_test(v[k].y);
+            if (idx < NW) *reinterpret_cast<uint2 *>(&s_g[r][8 * cw]) = v[k];
+        }
+    } else {
+        for (int idx = tid; idx < T::GH * (T::GW / 4); idx += 256) {
+            const int r = idx / (T::GW / 4), cw = idx - r * (T::GW / 4);
+            const int gy = y0 - T::HALO + r, gx = x0 - T::HX + 4 * cw;
+            uint32_t v = 0;
+            if (gy >= 0 && gy < H) {
+                const uint8_t *row = gray + (size_t)gy * gpitch;
+                if (aligned_in && gx >= 0 && gx + 3 < W) {
+                    v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+                    flat_test(v);
+                } else {
+                    uint32_t vt = ref4;  // out-of-image bytes must not fail the test
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int x = gx + k;
+                        if (x >= 0 && x < W) {
+                            const uint32_t q = __ldg(row + x);
+                            v |= q << (8 * k);
+                            vt = (vt & ~(0xffu << (8 * k))) | (q << (8 * k));
+                        }
                     }
+                    flat_test(vt);
                 }
             }
+            *reinterpret_cast<uint32_t *>(&s_g[r][4 * cw]) = v;
         }
-        *reinterpret_cast<uint32_t *>(&s_g[r][4 * cw]) = v;
     }
-    // block-wide min / max
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        mn = __vminu2(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = __vmaxu2(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if ((tid & 31) == 0) {
-        s_red[0][tid >> 5] = mn;
-        s_red[1][tid >> 5] = mx;
-    }
-    __syncthreads();
-    mn = s_red[0][0];
-    mx = s_red[1][0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) {
-        mn = __vminu2(mn, s_red[0][k]);
-        mx = __vmaxu2(mx, s_red[1][k]);
-    }
-    const int vmin = min(mn & 0xffffu, mn >> 16), vmax = max(mx & 0xffffu, mx >> 16);
-    const int cth = p.c_thresh;
-    const bool flat = p.inverse && !p.write_blur && cth >= 0 && (vmax - vmin) <= cth;
+    // barrier (s_g complete) + block-wide OR in one instruction
+    const bool flat = !__syncthreads_or((int)(acc & 0x80808080u)) && try_flat;
     // interior tile: the blur ring (tile +- 5) lies >= RB pixels inside the image, so no border rule applies anywhere
     const bool interior = x0 >= T::HALO && y0 >= T::HALO && x0 + TW + T::HALO <= W && y0 + TH + T::HALO <= H;
 
@@ -316,9 +336,28 @@ __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParam
     }
 
     // ---- 5. outputs: u8 mask, bit-packed mask, label plane ------------------------------------------------------
-    const bool vec = (W & 3) == 0;
-    uint8_t *mask = b.mask + (size_t)f * H * W;
-    int32_t *labels = b.labels + (size_t)f * H * W;
+    if (flat && x0 + TW <= W && y0 + TH <= H && (W & 15) == 0) {
+        // flat tile fully inside a 16-px aligned image: nothing but wide zero stores (one warp writes one 512-byte
+        // label row per instruction)
+        const int4 z = make_int4(0, 0, 0, 0);
+        if (p.init_labels) {
+#pragma unroll
+            for (int r = tid >> 5; r < TH; r += 8)
+                *reinterpret_cast<int4 *>(labels + (size_t)(y0 + r) * W + x0 + 4 * (tid & 31)) = z;
+        }
+        if (p.write_mask) {
+            for (int idx = tid; idx < TH * (TW / 16); idx += 256) {
+                const int r = idx / (TW / 16), c16 = idx - r * (TW / 16);
+                *reinterpret_cast<int4 *>(mask + (size_t)(y0 + r) * W + x0 + 16 * c16) = z;
+            }
+        }
+        if (tid < TH * (TW / 32)) {
+            const int r = tid / (TW / 32), wq = tid - r * (TW / 32);
+            bits_out[((size_t)f * H + y0 + r) * b.ww + (x0 >> 5) + wq] = 0u;
+        }
+        if (b.rowflags && tid < TH) b.rowflags[(size_t)f * b.rf_stride + (size_t)(y0 + tid) * b.tiles_x + blockIdx.x] = 0;
+        return;
+    }
     for (int idx = tid; idx < TH * (TW / 4); idx += 256) {
         const int r = idx / (TW / 4), c4 = (idx - r * (TW / 4)) * 4;
         const int gy = y0 + r, gx = x0 + c4;
@@ -347,12 +386,13 @@ __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParam
                 }
         }
     }
-    for (int idx = tid; idx < TH * (TW / 32); idx += 256) {
-        const int r = idx / (TW / 32), wq = idx - r * (TW / 32);
+    static_assert(TW == 128 && TH * (TW / 32) <= 256 && (TH * (TW / 32)) % 32 == 0, "bit-packing stage layout");
+    if (tid < TH * (TW / 32)) {  // whole warps: 8 rows x 4 words per warp
+        const int r = tid >> 2, wq = tid & 3;
         const int gy = y0 + r, gwx = (x0 >> 5) + wq;
-        if (gy >= H || gwx >= b.ww) continue;
+        const bool inside = gy < H && gwx < b.ww;
         uint32_t word = 0;
-        if (!flat) {
+        if (!flat && inside) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f[r][wq * 32]);
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -361,7 +401,12 @@ __global__ void __launch_bounds__(256) k_preprocess(BatchView b, PreprocessParam
                 word |= nib << (4 * k);
             }
         }
-        bits_out[((size_t)f * H + gy) * b.ww + gwx] = word;
+        if (inside) bits_out[((size_t)f * H + gy) * b.ww + gwx] = word;
+        // occupancy nibble of this (row, tile): which of its 4 words are non-zero
+        const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+        if (b.rowflags && wq == 0 && gy < H)
+            b.rowflags[(size_t)f * b.rf_stride + (size_t)gy * b.tiles_x + blockIdx.x] =
+                (uint8_t)((bal >> (tid & 31)) & 0xfu);
     }
 }
 

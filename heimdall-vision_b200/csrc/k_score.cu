@@ -11,69 +11,11 @@
 // Defects are emitted in label order (= the reference's discovery order) with an order-preserving block scan.
 // reject := n_defects > 0 (heimdall/inspection/base_inspector.py:40-42).
 #include "hv_common.cuh"
+#include "score_device.cuh"
 
 namespace hv {
 
 namespace {
-
-struct Scored {
-    bool keep;
-    hv_defect d;
-};
-
-__device__ __forceinline__ Scored score_blob(const BatchView &b, const ScoreParams &p, int f, uint32_t k,
-                                             const hv_blob &q) {
-    Scored out;
-    out.keep = false;
-    const double area = (double)q.area;
-    if (!(area >= p.min_size && area <= p.max_size) || q.area == 0) return out;
-    const int H = b.h, W = b.w;
-    const uint64_t cy = q.sum_y / q.area, cx = q.sum_x / q.area;
-    const int icy = (int)cy, icx = (int)cx;
-    const int y_lo = max(icy - 2, 0), y_hi = min(icy + 2, H - 1);
-    const int x_lo = max(icx - 2, 0), x_hi = min(icx + 2, W - 1);
-    const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
-    const uint8_t *mask = b.mask + (size_t)f * H * W;
-    uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
-    for (int y = y_lo; y <= y_hi; y++)
-        for (int x = x_lo; x <= x_hi; x++) {
-            const uint32_t g = gray[(size_t)y * b.gray_row_stride + x];
-            if (mask[(size_t)y * W + x] == 255) {
-                fg_sum += g;
-                fg_cnt++;
-            } else {
-                bg_sum += g;
-                bg_cnt++;
-            }
-        }
-    const double fg_mean = fg_cnt ? __ddiv_rn((double)fg_sum, (double)fg_cnt) : 127.0;
-    const double bg_mean = bg_cnt ? __ddiv_rn((double)bg_sum, (double)bg_cnt) : 127.0;
-    const double idiff = fabs(__dsub_rn(bg_mean, fg_mean));
-    const uint64_t rect = (uint64_t)(q.ymax - q.ymin + 1) * (uint64_t)(q.xmax - q.xmin + 1);
-    const double shape = rect > 0 ? __dsub_rn(1.0, __ddiv_rn(area, (double)rect)) : 0.5;
-    double iscore = __ddiv_rn(idiff, 30.0);
-    if (!(iscore <= 1.0)) iscore = 1.0;
-    const double conf = __dadd_rn(__dmul_rn(iscore, 0.7), __dmul_rn(shape, 0.3));
-    if (conf >= p.min_confidence) {
-        out.keep = true;
-        out.d.y = icy;
-        out.d.x = icx;
-        out.d.size = area;
-        out.d.confidence = conf;
-        out.d.ymin = (int32_t)q.ymin;
-        out.d.xmin = (int32_t)q.xmin;
-        out.d.ymax = (int32_t)q.ymax;
-        out.d.xmax = (int32_t)q.xmax;
-        out.d.label = k + 1;
-        out.d.frame = (uint32_t)f;
-    }
-    return out;
-}
-
-__device__ __forceinline__ int area_bin(uint32_t area) {
-    const int bin = 31 - __clz(area | 1u);
-    return bin < HV_STATS_AREA_BINS ? bin : HV_STATS_AREA_BINS - 1;
-}
 
 // One CTA per frame.
 __global__ void __launch_bounds__(256) k_score(BatchView b, ScoreParams p) {
@@ -82,6 +24,7 @@ __global__ void __launch_bounds__(256) k_score(BatchView b, ScoreParams p) {
     __shared__ unsigned long long s_area;
     __shared__ uint32_t s_hist[HV_STATS_AREA_BINS];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (b.frame_select && !b.frame_select[f]) return;
     const uint32_t ncomp = b.ncomp[f];
     const uint32_t nb = min(ncomp, (uint32_t)b.blob_cap);
     const hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;

@@ -1,0 +1,80 @@
+// score_device.cuh -- per-blob scoring shared by the global-path K6 (k_score.cu) and the fused per-frame kernel
+// (k_ccl_frame.cu).  Restates rust/heimdall-core/src/detection.rs:247-311; see k_score.cu for the commentary.
+#pragma once
+#include "hv_common.cuh"
+
+namespace hv {
+namespace {
+
+struct Scored {
+    bool keep;
+    hv_defect d;
+};
+
+__device__ __forceinline__ Scored score_blob(const BatchView &b, const ScoreParams &p, int f, uint32_t k,
+                                             const hv_blob &q) {
+    Scored out;
+    out.keep = false;
+    const double area = (double)q.area;
+    if (!(area >= p.min_size && area <= p.max_size) || q.area == 0) return out;
+    const int H = b.h, W = b.w;
+    const uint64_t cy = q.sum_y / q.area, cx = q.sum_x / q.area;
+    const int icy = (int)cy, icx = (int)cx;
+    const int y_lo = max(icy - 2, 0), y_hi = min(icy + 2, H - 1);
+    const int x_lo = max(icx - 2, 0), x_hi = min(icx + 2, W - 1);
+    const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
+    const uint8_t *mask = b.mask + (size_t)f * H * W;
+    uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
+    // 5x5 probe, fully unrolled with clamped coordinates so that all 50 loads are in flight together
+    uint32_t gv[25], mv[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+        const int y = min(max(icy - 2 + k / 5, 0), H - 1), x = min(max(icx - 2 + k % 5, 0), W - 1);
+        gv[k] = gray[(size_t)y * b.gray_row_stride + x];
+        mv[k] = mask[(size_t)y * W + x];
+    }
+#pragma unroll
+    for (int k = 0; k < 25; k++) {
+        const int y = icy - 2 + k / 5, x = icx - 2 + k % 5;
+        if (y >= y_lo && y <= y_hi && x >= x_lo && x <= x_hi) {
+            if (mv[k] == 255) {
+                fg_sum += gv[k];
+                fg_cnt++;
+            } else {
+                bg_sum += gv[k];
+                bg_cnt++;
+            }
+        }
+    }
+    const double fg_mean = fg_cnt ? __ddiv_rn((double)fg_sum, (double)fg_cnt) : 127.0;
+    const double bg_mean = bg_cnt ? __ddiv_rn((double)bg_sum, (double)bg_cnt) : 127.0;
+    const double idiff = fabs(__dsub_rn(bg_mean, fg_mean));
+    const uint64_t rect = (uint64_t)(q.ymax - q.ymin + 1) * (uint64_t)(q.xmax - q.xmin + 1);
+    const double shape = rect > 0 ? __dsub_rn(1.0, __ddiv_rn(area, (double)rect)) : 0.5;
+    double iscore = __ddiv_rn(idiff, 30.0);
+    if (!(iscore <= 1.0)) iscore = 1.0;
+    const double conf = __dadd_rn(__dmul_rn(iscore, 0.7), __dmul_rn(shape, 0.3));
+    if (conf >= p.min_confidence) {
+        out.keep = true;
+        out.d.y = icy;
+        out.d.x = icx;
+        out.d.size = area;
+        out.d.confidence = conf;
+        out.d.ymin = (int32_t)q.ymin;
+        out.d.xmin = (int32_t)q.xmin;
+        out.d.ymax = (int32_t)q.ymax;
+        out.d.xmax = (int32_t)q.xmax;
+        out.d.label = k + 1;
+        out.d.frame = (uint32_t)f;
+    }
+    return out;
+}
+
+__device__ __forceinline__ int area_bin(uint32_t area) {
+    const int bin = 31 - __clz(area | 1u);
+    return bin < HV_STATS_AREA_BINS ? bin : HV_STATS_AREA_BINS - 1;
+}
+
+
+}  // namespace
+}  // namespace hv

@@ -26,13 +26,16 @@ HV_ERR_BAD_TICKET = -8
 HV_FLAG_NO_GRAPH = 1
 HV_FLAG_PROFILE = 2
 HV_FLAG_KEEP_BLUR = 4
+HV_FLAG_FORCE_GENERIC = 8
+HV_FLAG_GLOBAL_CCL = 16
+HV_FLAG_PHASE_TIMING = 32
 
 HV_BLUR_BOX, HV_BLUR_GAUSSIAN, HV_BLUR_NONE = 0, 1, 2
 HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION = 0, 1
 HV_STATS_AREA_BINS = 16
-HV_K_COUNT = 8
+HV_K_COUNT = 9
 (HV_K_GRAY, HV_K_PREPROCESS, HV_K_MORPH, HV_K_CCL_MERGE, HV_K_CCL_FLATTEN, HV_K_CCL_SCAN, HV_K_CCL_LABEL,
- HV_K_SCORE) = range(8)
+ HV_K_SCORE, HV_K_CCL_FRAME) = range(9)
 
 
 class hv_config(C.Structure):
@@ -125,6 +128,7 @@ PROTOTYPES = {
     "hv_profile_enable": (_i32, [_vp, C.c_uint32]),
     "hv_profile_get": (_i32, [_vp, _P(C.c_float), _P(C.c_uint32)]),
     "hv_kernel_name": (C.c_char_p, [_i32]),
+    "hv_debug_phase_times": (_i32, [_vp, _P(C.c_uint64)]),
 }
 
 

@@ -82,13 +82,17 @@ class Detector:
     """One CUDA device, one hv_ctx.  Not thread-safe by itself; calls are serialised with a lock."""
 
     def __init__(self, device: int = 0, *, max_blobs_per_frame: int = 0, max_defects_per_frame: int = 0,
-                 num_slots: int = 0, profile: bool = False, keep_blur: bool = False):
+                 num_slots: int = 0, profile: bool = False, keep_blur: bool = False, force_generic: bool = False,
+                 global_ccl: bool = False, phase_timing: bool = False):
         cfg = A.hv_config()
         _lib.hv_config_default(C.byref(cfg))
         cfg.max_blobs_per_frame = max_blobs_per_frame
         cfg.max_defects_per_frame = max_defects_per_frame
         cfg.num_slots = num_slots
-        cfg.flags = (A.HV_FLAG_PROFILE if profile else 0) | (A.HV_FLAG_KEEP_BLUR if keep_blur else 0)
+        cfg.flags = ((A.HV_FLAG_PROFILE if profile else 0) | (A.HV_FLAG_KEEP_BLUR if keep_blur else 0) |
+                     (A.HV_FLAG_FORCE_GENERIC if force_generic else 0) |
+                     (A.HV_FLAG_GLOBAL_CCL if global_ccl else 0) |
+                     (A.HV_FLAG_PHASE_TIMING if phase_timing else 0))
         self._ctx = C.c_void_p()
         self._lock = threading.Lock()
         self.device = device
@@ -306,6 +310,11 @@ class Detector:
 
     def stats_device_ptr(self) -> int:
         return int(_lib.hv_stats_device_ptr(self._ctx) or 0)
+
+    def phase_times(self) -> List[int]:
+        out = (C.c_uint64 * 256)()
+        _lib.hv_debug_phase_times(self._ctx, out)
+        return [int(x) for x in out]
 
     def launch_count(self) -> int:
         return int(_lib.hv_launch_count(self._ctx))

@@ -60,6 +60,9 @@ typedef struct {
 
 #define HV_FLAG_NO_GRAPH 1u   /* launch kernels directly instead of replaying a captured CUDA graph */
 #define HV_FLAG_PROFILE 2u    /* record a CUDA event pair around every kernel (hv_profile_get) */
+#define HV_FLAG_FORCE_GENERIC 8u /* testing: K1 never takes the packed fast path nor the flat-tile skip */
+#define HV_FLAG_GLOBAL_CCL 16u   /* always use the global-memory CCL kernels (K2..K6), never the fused per-frame kernel */
+#define HV_FLAG_PHASE_TIMING 32u /* fused CCL kernel records per-phase timestamps of frame 0 (hv_debug_phase_times) */
 #define HV_FLAG_KEEP_BLUR 4u  /* materialise the blurred intermediate for hv_fetch_debug (disables the flat-tile skip) */
 
 /* Blur selection for the preprocess stage. */
@@ -152,7 +155,8 @@ enum {
     HV_K_CCL_SCAN = 5,
     HV_K_CCL_LABEL = 6,  /* A4 canonical relabel + A5 blob statistics */
     HV_K_SCORE = 7,      /* A5b + A6 */
-    HV_K_COUNT = 8
+    HV_K_CCL_FRAME = 8,  /* A4 + A5 + A5b + A6 fused, one CTA per frame, union-find in shared memory (sparse masks) */
+    HV_K_COUNT = 9
 };
 
 /* ---- library ------------------------------------------------------------------------------------------- */
@@ -267,6 +271,9 @@ HV_API uint64_t hv_launch_count(const hv_ctx *ctx);
 HV_API hv_status hv_profile_enable(hv_ctx *ctx, uint32_t kernel_mask);
 HV_API hv_status hv_profile_get(hv_ctx *ctx, float total_ms[HV_K_COUNT], uint32_t counts[HV_K_COUNT]);
 HV_API const char *hv_kernel_name(int32_t k);
+/* With HV_FLAG_PHASE_TIMING: globaltimer (ns) of every warp of frame 0's CTA at the phase boundaries of the fused
+ * per-frame kernel, out_ns[stamp * 16 + warp]; entries not recorded are 0. */
+HV_API hv_status hv_debug_phase_times(hv_ctx *ctx, uint64_t out_ns[256]);
 
 #ifdef __cplusplus
 }

@@ -22,11 +22,13 @@ def oracle():
     return O
 
 
-@pytest.fixture(scope="session")
-def detector():
-    """One CUDA context for the whole GPU session; fails loudly (no skip) if the extension or the GPU is missing."""
+@pytest.fixture(scope="session", params=["fused", "global"])
+def detector(request):
+    """One CUDA context per CCL path for the whole GPU session; fails loudly (no skip) if the extension or the GPU is
+    missing.  "fused" = default configuration (per-frame shared-memory CCL kernel with automatic fallback to the
+    global-memory kernels for dense frames), "global" = global-memory CCL kernels only."""
     import heimdall_core
-    det = heimdall_core.Detector(0, max_defects_per_frame=8192)
+    det = heimdall_core.Detector(0, max_defects_per_frame=8192, global_ccl=(request.param == "global"))
     yield det
     det.close()
 

@@ -110,6 +110,35 @@ def test_random_textured(oracle, detector, c):
     check_frame(oracle, detector, img, min_size=3.0, max_size=40.0, threshold=0.0)
 
 
+@pytest.mark.parametrize("thr", [0.0, 3.0, 25.0, 120.0, 255.0, 256.0, -1.0, -2.0])
+def test_fast_path_interior_tiles(oracle, detector, thr):
+    """Images large enough to contain interior 128x32 tiles (packed-u16x2 fast path) next to border tiles (generic
+    path), textured so that no tile is flat; both paths must agree with the oracle and with each other."""
+    import heimdall_core as hc
+    rng = np.random.default_rng(int(thr) + 1000)
+    img = rng.integers(0, 256, (200, 650, 1), dtype=np.uint8)
+    img[60:140, 200:500] = (img[60:140, 200:500] // 8 + 100)          # a calmer region: thresholds near 25 matter
+    img[90:110, 300:340] = 10
+    res, ref = check_frame(oracle, detector, img, min_size=1.0, max_size=1e9, threshold=thr)
+    gen = hc.Detector(0, force_generic=True, max_defects_per_frame=8192)
+    try:
+        r2 = gen.detect_batch(img, hc.make_params(1.0, 1e9, thr), debug=["mask", "labels"])
+    finally:
+        gen.close()
+    assert np.array_equal(r2.debug["mask"][0], ref.mask) and np.array_equal(r2.debug["labels"][0], ref.labels)
+
+
+def test_fast_path_extreme_values(oracle, detector):
+    """Saturated inputs: all-255 blocks next to all-0 blocks maximise every packed 16-bit lane (30855 + 1, 61831)."""
+    img = np.zeros((160, 520, 1), np.uint8)
+    img[:, ::37] = 255
+    img[40:120, 100:400] = 255
+    img[70:90, 200:300] = 0
+    for thr in (0.0, 25.0, 255.0):
+        check_frame(oracle, detector, img, min_size=1.0, max_size=1e9, threshold=thr)
+    check_frame(oracle, detector, np.full((160, 520, 1), 255, np.uint8), threshold=0.0)
+
+
 @pytest.mark.parametrize("thr", [-1.0, -40.0, -300.0, 0.0, 0.9, 1e12, -1e12, float("nan"), 254.0, 255.0, 256.0, 300.0])
 def test_threshold_edge_values(oracle, detector, thr):
     rng = np.random.default_rng(17)
@@ -417,7 +446,7 @@ def test_line_stats_and_launch_count(oracle):
         batch = synth.bottle_batch(5, 240, 320, start_index=400)
         l0 = det.launch_count()
         res = det.detect_batch(batch[..., None])
-        assert det.launch_count() - l0 >= 6
+        assert det.launch_count() - l0 >= 2      # K1 + fused per-frame CCL (global path: K1 + 5)
         s = det.stats()
         assert s["frames_inspected"] == 5 and s["frames_rejected"] == int(res.rejected.sum())
         assert s["total_defects"] == int(res.frames["n_defects"].sum())
@@ -426,7 +455,7 @@ def test_line_stats_and_launch_count(oracle):
         assert s["total_defect_area"] == int(res.defects["size"].sum())
         assert sum(s["area_hist"]) == s["total_defects"]
         prof = det.profile()
-        assert prof["preprocess_mask"]["ms"] > 0 and prof["ccl_label"]["launches"] == 1
+        assert prof["preprocess_mask"]["ms"] > 0 and prof["ccl_frame_fused"]["launches"] == 1
         det.stats_reset()
         assert det.stats()["frames_inspected"] == 0
     finally:
@@ -440,7 +469,7 @@ def test_full_size_properties_12mp_high_contamination(detector):
     order (canonical numbering), per-label pixel counts equal the blob table, 4-neighbours of equal mask share labels."""
     import heimdall_core as hc
     fr = synth.high_contamination_frame(3000, 4096, 0)
-    det = hc.Detector(0, max_blobs_per_frame=400000)
+    det = hc.Detector(0, max_blobs_per_frame=400000, max_defects_per_frame=200000)
     try:
         res = det.detect_batch(fr, hc.make_params(10.0, 3000.0, 25.0), debug=["mask", "labels", "blobs"])
     finally:
