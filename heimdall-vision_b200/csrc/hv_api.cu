@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -64,7 +65,7 @@ struct Slot {
     cudaEvent_t done = nullptr;
     DevBuf<uint8_t> in, gray, blur, mask, rowflags;
     DevBuf<uint16_t> gauss_tmp;
-    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags;
+    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags, sched;
     PinBuf<uint32_t> h_flags;
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
     ScoreParams score{};
@@ -85,7 +86,7 @@ struct Slot {
         in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release(), rowflags.release();
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
-        frame_flags.release(), h_flags.release();
+        frame_flags.release(), h_flags.release(), sched.release();
         h_results.release(), h_defects.release();
         if (done) cudaEventDestroy(done);
         if (stream) cudaStreamDestroy(stream);
@@ -98,6 +99,7 @@ struct Slot {
 
 struct hv_ctx {
     int device = 0;
+    int num_sms = 148;
     hv_config cfg{};
     std::string err;
     std::vector<Slot> slots;
@@ -274,6 +276,10 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     HV_TRY_CUDA(ctx, s.ncomp.reserve(n));
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
     HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
+    if (!s.sched.p) {  // K1's tile scheduler: {next tile, CTAs done}; the kernel rearms it itself
+        HV_TRY_CUDA(ctx, s.sched.reserve(2));
+        HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 2 * sizeof(uint32_t)));
+    }
     HV_TRY_CUDA(ctx, s.h_flags.reserve(n));
     HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
     HV_TRY_CUDA(ctx, s.defects.reserve((size_t)n * defect_cap_for(ctx)));
@@ -369,11 +375,13 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.frame_flags = s.frame_flags.p;
     b.frame_select = nullptr;
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
+    if (b.phase_ns) cudaMemsetAsync(ctx->d_phase_ns + 200, 0, 8 * sizeof(unsigned long long), st);
 
     PreprocessParams pp{};
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
+    pp.static_sched = getenv("HV_K1_DYNAMIC") ? 0 : 1;
     pp.write_mask = morph ? 0 : 1;
     pp.init_labels = morph ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
@@ -405,7 +413,10 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     }
     {
         ProfScope ps(ctx, HV_K_PREPROCESS, st);
-        HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
+        bool used_tma = false;
+        if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
+            HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, st, &used_tma));
+        if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
         ctx->launches++;
     }
     if (morph) {
@@ -632,6 +643,7 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
     hv_ctx *ctx = new (std::nothrow) hv_ctx();
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
     const int nslots = 1 + (ctx->cfg.num_slots > 0 ? ctx->cfg.num_slots : 3);  // slot 0 = synchronous entry points
     ctx->slots.resize(nslots);
@@ -644,7 +656,7 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
         }
     }
     if (ctx->cfg.flags & HV_FLAG_PROFILE) ctx->prof_mask = 0xffffffffu;
-    if (configure_ccl_frame() != cudaSuccess) {
+    if (configure_ccl_frame() != cudaSuccess || configure_preprocess_tma() != cudaSuccess) {
         g_create_error = "cannot configure shared memory for the per-frame CCL kernel";
         hv_destroy(ctx);
         return HV_ERR_CUDA;

@@ -49,6 +49,7 @@ struct PreprocessParams {
     int init_labels;   // write label zeros + word-run-start parents (0 when morphology follows)
     int inverse;       // 1: 255 if px < mean - c (detection path); 0: 255 if px > mean - c
     int force_generic; // testing: never take the packed fast path
+    int static_sched;  // TMA kernel: static round-robin tile schedule instead of the atomic tile counter
 };
 
 struct ScoreParams {
@@ -65,6 +66,8 @@ struct ScoreParams {
 cudaError_t launch_gray3(const uint8_t *d_img, int n, int h, int w, size_t row_stride, size_t frame_stride,
                          uint8_t *d_gray, cudaStream_t s);
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s);
+cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
+                                  int num_sms, cudaStream_t s, bool *used);
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
@@ -76,6 +79,7 @@ cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t 
 cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, cudaStream_t s);
 bool ccl_frame_supported(const BatchView &b);
 cudaError_t configure_ccl_frame();
+cudaError_t configure_preprocess_tma();
 
 // generic single-frame stage kernels (python-facing utilities, not the hot path)
 cudaError_t launch_box_blur_generic(const uint8_t *src, int h, int w, int nch, int radius, uint8_t *dst,

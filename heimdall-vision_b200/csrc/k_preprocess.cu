@@ -18,6 +18,9 @@
 // 15x15 neighbourhood N(p), so mean - blur <= max_N(gray) - min_N(gray).  If that range is <= c over a whole tile
 // plus halo, no pixel of the tile can satisfy blur < mean - c and the tile is written as zeros without computing
 // the sums.  On bottle frames most tiles are flat, which makes this kernel HBM-bound: 1 B/px read, 5.125 B/px written.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "hv_common.cuh"
 
 namespace hv {
@@ -39,18 +42,22 @@ __device__ __forceinline__ uint32_t div25(uint32_t s) { return (s * 5243u) >> 17
 //   s_f   [TH][TW]  u8   mask bytes of the tile            -- aliases s_g
 //   s_v   [BH][VP]  u16  vertical 5-sums, column i stored at i + 4         (fast path only, dead after the blur phase)
 //   s_h11 [BH][TW]  u16  horizontal 11-sums of the blur    -- aliases s_v
-//   s_bl  [BH][GW]  u8   blurred tile + 5-px ring
-template <int TW, int TH, int RB>
+//   s_bl  [BH][BW]  u8   blurred tile + 5-px ring (logical columns)
+template <int TW, int TH, int RB, int HXP = 8>
 struct Tile {
     static constexpr int HALO = RB + kAdaptHalf;  // rows of gray needed above/below
-    static constexpr int HX = 8;                  // column halo, padded to a multiple of 4 for aligned loads
-    static constexpr int GW = TW + 2 * HX;
+    static constexpr int HX = HXP;                // column halo of the staged gray tile: 8 (aligned 8-byte loads) or 16
+                                                  // (TMA: the box must start on a 16-byte boundary)
+    static constexpr int GW = TW + 2 * HX;        // pitch of s_g
+    static constexpr int GOFF = HX - 8;           // s_g column of logical column 0 (logical column i = image x0 - 8 + i)
+    static constexpr int BW = TW + 16;            // logical width = pitch of s_bl
     static constexpr int GH = TH + 2 * HALO;
     static constexpr int BH = TH + 2 * kAdaptHalf;
-    static constexpr int VP = GW + 8;  // pitch of s_v in u16 (column i is stored at i + 4; 4 spare on each side)
+    static constexpr int VP = BW + 8;  // pitch of s_v in u16 (column i is stored at i + 4; 4 spare on each side)
     static constexpr int G_BYTES = GH * GW;
     static constexpr int U1_BYTES = (BH * VP * 2 > BH * TW * 2) ? BH * VP * 2 : BH * TW * 2;
-    static constexpr int BL_BYTES = BH * GW;
+    static constexpr int BL_BYTES = BH * BW;
+    static_assert(HX >= 8 && (HX % 8) == 0, "column halo");
     static_assert(TH * TW <= G_BYTES, "s_f must fit inside s_g");
     static_assert((G_BYTES % 16) == 0 && (U1_BYTES % 16) == 0, "alignment");
 };
@@ -58,14 +65,15 @@ struct Tile {
 // ---- fast path, interior tiles only (every blur pixel is an interior pixel, every window has 121 pixels) ---------
 // Packed u16x2 arithmetic: sums of u8 never overflow a 16-bit lane (5x5: 6375, 11x11 of blur: 30855), so plain 32-bit
 // adds/subs act on both lanes at once; VIMNMX.U16x2 gives the lane-wise compare for the threshold test.
-template <int TW, int TH>
-__device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
-    using T = Tile<TW, TH, 2>;
-    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem);
-    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(smem);
-    uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(smem + T::G_BYTES);
-    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(smem + T::G_BYTES);
-    uint8_t(*s_bl)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem + T::G_BYTES + T::U1_BYTES);
+template <int TW, int TH, int HXP>
+__device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid,
+                                              int cth) {
+    using T = Tile<TW, TH, 2, HXP>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);  // may alias s_g: only written after s_g is dead
+    uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(u1_raw);
+    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(u1_raw);
+    uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
     static_assert(TW == 128 && TH == 32, "thread mappings below are written for 128x32 tiles");
 
     // A. vertical 5-sums: thread = (column quad q, row segment of 7) -> 36 x 6 = 216 threads
@@ -75,14 +83,14 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
         uint32_t lo[5], hi[5];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k][4 * q]);
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k][4 * q + T::GOFF]);
             lo[k] = prmt(v, 0, 0x4140);
             hi[k] = prmt(v, 0, 0x4342);
         }
         uint32_t alo = lo[0] + lo[1] + lo[2] + lo[3], ahi = hi[0] + hi[1] + hi[2] + hi[3];
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k + 4][4 * q]);
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k + 4][4 * q + T::GOFF]);
             const uint32_t nlo = prmt(v, 0, 0x4140), nhi = prmt(v, 0, 0x4342);
             alo += nlo;
             ahi += nhi;
@@ -184,15 +192,196 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *smem, int tid, int cth) {
     __syncthreads();
 }
 
+// Everything after the gray tile (+ halo, zero outside the image) sits in shared memory and the flat decision is known:
+// blur + threshold (fast or generic path) and the three outputs.  Block-uniform control flow; contains barriers.
+template <int TW, int TH, int RB, int HXP>
+__device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out,
+                                                       uint8_t *g_raw, uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw,
+                                                       int f, int tile_x, int x0, int y0, bool flat, int tid) {
+    using T = Tile<TW, TH, RB, HXP>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);
+    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(u1_raw);
+    uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
+    const int H = b.h, W = b.w;
+    const int cth = p.c_thresh;
+    const bool vec = (W & 3) == 0;
+    uint8_t *mask = b.mask + (size_t)f * H * W;
+    int32_t *labels = b.labels + (size_t)f * H * W;
+    // interior tile: the blur ring (tile +- 5) lies >= RB pixels inside the image, so no border rule applies anywhere
+    const bool interior = x0 >= T::HALO && y0 >= T::HALO && x0 + TW + T::HALO <= W && y0 + TH + T::HALO <= H;
+
+    if (!flat) {
+        if (RB == 2 && TW == 128 && TH == 32 && interior && p.inverse && !p.write_blur && cth >= 0 && cth <= 255 &&
+            !p.force_generic) {
+            fast_tile_rb2<128, 32, HXP>(g_raw, f_raw, u1_raw, bl_raw, tid, cth);
+        } else {
+            // ---- generic path: any border, any c, either comparison direction --------------------------------------
+            // 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior)
+            for (int idx = tid; idx < T::BH * (TW + 2 * kAdaptHalf); idx += 256) {
+                const int r = idx / (TW + 2 * kAdaptHalf), i = idx - r * (TW + 2 * kAdaptHalf) + (8 - kAdaptHalf);
+                const int gy = y0 - kAdaptHalf + r, gx = x0 - 8 + i;
+                const int ry = r + RB;
+                uint32_t v = 0;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    if (RB > 0 && gy >= RB && gy < H - RB && gx >= RB && gx < W - RB) {
+                        uint32_t s = 0;
+#pragma unroll
+                        for (int dy = -RB; dy <= RB; dy++)
+#pragma unroll
+                            for (int dx = -RB; dx <= RB; dx++) s += s_g[ry + dy][i + dx + T::GOFF];
+                        v = (RB == 2) ? div25(s) : s / ((2 * RB + 1) * (2 * RB + 1));
+                    } else {
+                        v = s_g[ry][i + T::GOFF];
+                    }
+                    if (p.write_blur && r >= kAdaptHalf && r < kAdaptHalf + TH && i >= 8 && i < 8 + TW)
+                        b.blur[((size_t)f * H + gy) * W + gx] = (uint8_t)v;
+                }
+                s_bl[r][i] = (uint8_t)v;
+            }
+            __syncthreads();
+            // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
+            for (int idx = tid; idx < T::BH * TW; idx += 256) {
+                const int r = idx / TW, c = idx - r * TW;
+                uint32_t s = 0;
+#pragma unroll
+                for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][c + (8 - kAdaptHalf) + k];
+                s_h11[r][c] = (uint16_t)s;
+            }
+            __syncthreads();
+            // 4. vertical 11-sums + threshold test (window truncated at the image border: cnt = rows * cols)
+            for (int idx = tid; idx < TH * TW; idx += 256) {
+                const int r = idx / TW, c = idx - r * TW;
+                const int gy = y0 + r, gx = x0 + c;
+                uint8_t fg = 0;
+                if (gy < H && gx < W) {
+                    int s = 0;
+#pragma unroll
+                    for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_h11[r + k][c];
+                    const int rows = min(gy + kAdaptHalf, H - 1) - max(gy - kAdaptHalf, 0) + 1;
+                    const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
+                    const int cnt = rows * cols;
+                    const int px = s_bl[r + kAdaptHalf][c + 8];
+                    const bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
+                    fg = t ? 255 : 0;
+                }
+                s_f[r][c] = fg;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 5. outputs: u8 mask, bit-packed mask, label plane ------------------------------------------------------
+    if (flat && x0 + TW <= W && y0 + TH <= H && (W & 15) == 0) {
+        // flat tile fully inside a 16-px aligned image: nothing but wide zero stores (one warp writes one 512-byte
+        // label row per instruction)
+        const int4 z = make_int4(0, 0, 0, 0);
+        if (p.init_labels) {
+#pragma unroll
+            for (int r = tid >> 5; r < TH; r += 8)
+                *reinterpret_cast<int4 *>(labels + (size_t)(y0 + r) * W + x0 + 4 * (tid & 31)) = z;
+        }
+        if (p.write_mask) {
+            for (int idx = tid; idx < TH * (TW / 16); idx += 256) {
+                const int r = idx / (TW / 16), c16 = idx - r * (TW / 16);
+                *reinterpret_cast<int4 *>(mask + (size_t)(y0 + r) * W + x0 + 16 * c16) = z;
+            }
+        }
+        if (tid < TH * (TW / 32)) {
+            const int r = tid / (TW / 32), wq = tid - r * (TW / 32);
+            bits_out[((size_t)f * H + y0 + r) * b.ww + (x0 >> 5) + wq] = 0u;
+        }
+        if (b.rowflags && tid < TH) b.rowflags[(size_t)f * b.rf_stride + (size_t)(y0 + tid) * b.tiles_x + tile_x] = 0;
+        return;
+    }
+    if (x0 + TW <= W && (W & 15) == 0) {
+        // full-width tile of a 16-px aligned image: one thread per 16 pixels, 128-bit stores throughout
+        static_assert(TH * (TW / 16) == 256, "one 16-pixel group per thread");
+        const int r = tid >> 3, c16 = (tid & 7) * 16;
+        const int gy = y0 + r;
+        if (gy < H) {
+            const uint4 m16 = flat ? make_uint4(0u, 0u, 0u, 0u) : *reinterpret_cast<const uint4 *>(&s_f[r][c16]);
+            const size_t o = (size_t)gy * W + x0 + c16;
+            if (p.write_mask) *reinterpret_cast<uint4 *>(mask + o) = m16;
+            if (p.init_labels) {
+                int4 *dst = reinterpret_cast<int4 *>(labels + o);
+                if (!(m16.x | m16.y | m16.z | m16.w)) {
+                    const int4 z = make_int4(0, 0, 0, 0);
+                    dst[0] = z, dst[1] = z, dst[2] = z, dst[3] = z;
+                } else {
+                    // 16 foreground bits, run starts inside the 32-px word, then p+1 at the starts
+                    auto nib = [](uint32_t w) { return ((w & 0x01010101u) * 0x10204080u) >> 28; };
+                    const uint32_t fg = nib(m16.x) | (nib(m16.y) << 4) | (nib(m16.z) << 8) | (nib(m16.w) << 12);
+                    const uint32_t prev = (c16 & 31) ? (s_f[r][c16 - 1] & 1u) : 0u;
+                    const uint32_t starts = fg & ~((fg << 1) | prev);
+                    const int base = gy * W + x0 + c16 + 1;
+                    int lab[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) lab[k] = ((starts >> k) & 1u) ? base + k : 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) dst[k] = make_int4(lab[4 * k], lab[4 * k + 1], lab[4 * k + 2], lab[4 * k + 3]);
+                }
+            }
+        }
+    } else
+        for (int idx = tid; idx < TH * (TW / 4); idx += 256) {
+            const int r = idx / (TW / 4), c4 = (idx - r * (TW / 4)) * 4;
+        const int gy = y0 + r, gx = x0 + c4;
+        if (gy >= H || gx >= W) continue;
+        const uint32_t m4 = flat ? 0u : *reinterpret_cast<const uint32_t *>(&s_f[r][c4]);
+        int4 lab = make_int4(0, 0, 0, 0);
+        if (m4 && p.init_labels) {
+            const uint32_t prev = (c4 & 31) ? s_f[r][c4 - 1] : 0u;
+            const int base = gy * W + gx + 1;
+            const uint32_t f0 = m4 & 0xffu, f1 = (m4 >> 8) & 0xffu, f2 = (m4 >> 16) & 0xffu, f3 = m4 >> 24;
+            lab.x = (f0 && !prev) ? base : 0;
+            lab.y = (f1 && !f0) ? base + 1 : 0;
+            lab.z = (f2 && !f1) ? base + 2 : 0;
+            lab.w = (f3 && !f2) ? base + 3 : 0;
+        }
+        if (vec) {
+            if (p.write_mask) *reinterpret_cast<uint32_t *>(mask + (size_t)gy * W + gx) = m4;
+            if (p.init_labels) *reinterpret_cast<int4 *>(labels + (size_t)gy * W + gx) = lab;
+        } else {
+            const int la[4] = {lab.x, lab.y, lab.z, lab.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (gx + k < W) {
+                    if (p.write_mask) mask[(size_t)gy * W + gx + k] = (uint8_t)(m4 >> (8 * k));
+                    if (p.init_labels) labels[(size_t)gy * W + gx + k] = la[k];
+                }
+        }
+    }
+    static_assert(TW == 128 && TH * (TW / 32) <= 256 && (TH * (TW / 32)) % 32 == 0, "bit-packing stage layout");
+    if (tid < TH * (TW / 32)) {  // whole warps: 8 rows x 4 words per warp
+        const int r = tid >> 2, wq = tid & 3;
+        const int gy = y0 + r, gwx = (x0 >> 5) + wq;
+        const bool inside = gy < H && gwx < b.ww;
+        uint32_t word = 0;
+        if (!flat && inside) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f[r][wq * 32]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                // gather bit 0 of each of the 4 mask bytes into a nibble
+                const uint32_t nib = ((src[k] & 0x01010101u) * 0x10204080u) >> 28;
+                word |= nib << (4 * k);
+            }
+        }
+        if (inside) bits_out[((size_t)f * H + gy) * b.ww + gwx] = word;
+        // occupancy nibble of this (row, tile): which of its 4 words are non-zero
+        const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+        if (b.rowflags && wq == 0 && gy < H)
+            b.rowflags[(size_t)f * b.rf_stride + (size_t)gy * b.tiles_x + tile_x] =
+                (uint8_t)((bal >> (tid & 31)) & 0xfu);
+    }
+}
+
 template <int TW, int TH, int RB>
 __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessParams p, uint32_t *bits_out) {
     using T = Tile<TW, TH, RB>;
     static_assert(TW % 32 == 0, "tile width must cover whole bitmask words");
     __shared__ __align__(16) uint8_t smem[T::G_BYTES + T::U1_BYTES + T::BL_BYTES];
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem);
-    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(smem);  // aliases s_g (dead by then)
-    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(smem + T::G_BYTES);
-    uint8_t(*s_bl)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(smem + T::G_BYTES + T::U1_BYTES);
 
     const int tid = threadIdx.x;
     const int f = blockIdx.z;
@@ -201,9 +390,6 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
     const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
     const size_t gpitch = b.gray_row_stride;
     const bool aligned_in = ((reinterpret_cast<uintptr_t>(gray) | gpitch) & 3) == 0;
-    const bool vec = (W & 3) == 0;
-    uint8_t *mask = b.mask + (size_t)f * H * W;
-    int32_t *labels = b.labels + (size_t)f * H * W;
 
     // ---- 1. stage the gray tile + halo in shared memory and test it for flatness on the way ------------------------
     // Flatness (conservative, exact in effect): if every in-image pixel of the tile + halo satisfies
@@ -272,141 +458,157 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
     }
     // barrier (s_g complete) + block-wide OR in one instruction
     const bool flat = !__syncthreads_or((int)(acc & 0x80808080u)) && try_flat;
-    // interior tile: the blur ring (tile +- 5) lies >= RB pixels inside the image, so no border rule applies anywhere
-    const bool interior = x0 >= T::HALO && y0 >= T::HALO && x0 + TW + T::HALO <= W && y0 + TH + T::HALO <= H;
+    // s_f aliases s_g (dead by the time the mask bytes are written)
+    tile_compute_and_store<TW, TH, RB, 8>(b, p, bits_out, smem, smem, smem + T::G_BYTES, smem + T::G_BYTES + T::U1_BYTES, f,
+                                       blockIdx.x, x0, y0, flat, tid);
+}
 
-    if (!flat) {
-        if (RB == 2 && TW == 128 && TH == 32 && interior && p.inverse && !p.write_blur && cth >= 0 && cth <= 255 &&
-            !p.force_generic) {
-            fast_tile_rb2<128, 32>(smem, tid, cth);
-        } else {
-            // ---- generic path: any border, any c, either comparison direction --------------------------------------
-            // 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior)
-            for (int idx = tid; idx < T::BH * (TW + 2 * kAdaptHalf); idx += 256) {
-                const int r = idx / (TW + 2 * kAdaptHalf), i = idx - r * (TW + 2 * kAdaptHalf) + (T::HX - kAdaptHalf);
-                const int gy = y0 - kAdaptHalf + r, gx = x0 - T::HX + i;
-                const int ry = r + RB;
-                uint32_t v = 0;
-                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                    if (RB > 0 && gy >= RB && gy < H - RB && gx >= RB && gx < W - RB) {
-                        uint32_t s = 0;
-#pragma unroll
-                        for (int dy = -RB; dy <= RB; dy++)
-#pragma unroll
-                            for (int dx = -RB; dx <= RB; dx++) s += s_g[ry + dy][i + dx];
-                        v = (RB == 2) ? div25(s) : s / ((2 * RB + 1) * (2 * RB + 1));
-                    } else {
-                        v = s_g[ry][i];
-                    }
-                    if (p.write_blur && r >= kAdaptHalf && r < kAdaptHalf + TH && i >= T::HX && i < T::HX + TW)
-                        b.blur[((size_t)f * H + gy) * W + gx] = (uint8_t)v;
-                }
-                s_bl[r][i] = (uint8_t)v;
-            }
-            __syncthreads();
-            // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
-            for (int idx = tid; idx < T::BH * TW; idx += 256) {
-                const int r = idx / TW, c = idx - r * TW;
-                uint32_t s = 0;
-#pragma unroll
-                for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][c + (T::HX - kAdaptHalf) + k];
-                s_h11[r][c] = (uint16_t)s;
-            }
-            __syncthreads();
-            // 4. vertical 11-sums + threshold test (window truncated at the image border: cnt = rows * cols)
-            for (int idx = tid; idx < TH * TW; idx += 256) {
-                const int r = idx / TW, c = idx - r * TW;
-                const int gy = y0 + r, gx = x0 + c;
-                uint8_t fg = 0;
-                if (gy < H && gx < W) {
-                    int s = 0;
-#pragma unroll
-                    for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_h11[r + k][c];
-                    const int rows = min(gy + kAdaptHalf, H - 1) - max(gy - kAdaptHalf, 0) + 1;
-                    const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
-                    const int cnt = rows * cols;
-                    const int px = s_bl[r + kAdaptHalf][c + T::HX];
-                    const bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
-                    fg = t ? 255 : 0;
-                }
-                s_f[r][c] = fg;
-            }
-            __syncthreads();
-        }
-    }
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 v3: persistent CTAs, TMA-staged tiles (cp.async.bulk.tensor.3d + mbarrier), double buffering, dynamic tile scheduler.
+// The v2 kernel above is one CTA per tile: load -> barrier -> compute -> store, so every tile exposes a full DRAM latency
+// and needs >= 6 resident CTAs per SM to hide it (ncu: long-scoreboard stalls dominate).  Here a CTA keeps fetching tiles
+// from an atomic counter and the TMA unit loads tile k+1 (zero-filling outside the image) while the threads test, compute
+// and store tile k; no thread ever issues a global load for pixels.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-    // ---- 5. outputs: u8 mask, bit-packed mask, label plane ------------------------------------------------------
-    if (flat && x0 + TW <= W && y0 + TH <= H && (W & 15) == 0) {
-        // flat tile fully inside a 16-px aligned image: nothing but wide zero stores (one warp writes one 512-byte
-        // label row per instruction)
-        const int4 z = make_int4(0, 0, 0, 0);
-        if (p.init_labels) {
-#pragma unroll
-            for (int r = tid >> 5; r < TH; r += 8)
-                *reinterpret_cast<int4 *>(labels + (size_t)(y0 + r) * W + x0 + 4 * (tid & 31)) = z;
-        }
-        if (p.write_mask) {
-            for (int idx = tid; idx < TH * (TW / 16); idx += 256) {
-                const int r = idx / (TW / 16), c16 = idx - r * (TW / 16);
-                *reinterpret_cast<int4 *>(mask + (size_t)(y0 + r) * W + x0 + 16 * c16) = z;
-            }
-        }
-        if (tid < TH * (TW / 32)) {
-            const int r = tid / (TW / 32), wq = tid - r * (TW / 32);
-            bits_out[((size_t)f * H + y0 + r) * b.ww + (x0 >> 5) + wq] = 0u;
-        }
-        if (b.rowflags && tid < TH) b.rowflags[(size_t)f * b.rf_stride + (size_t)(y0 + tid) * b.tiles_x + blockIdx.x] = 0;
-        return;
-    }
-    for (int idx = tid; idx < TH * (TW / 4); idx += 256) {
-        const int r = idx / (TW / 4), c4 = (idx - r * (TW / 4)) * 4;
-        const int gy = y0 + r, gx = x0 + c4;
-        if (gy >= H || gx >= W) continue;
-        const uint32_t m4 = flat ? 0u : *reinterpret_cast<const uint32_t *>(&s_f[r][c4]);
-        int4 lab = make_int4(0, 0, 0, 0);
-        if (m4 && p.init_labels) {
-            const uint32_t prev = (c4 & 31) ? s_f[r][c4 - 1] : 0u;
-            const int base = gy * W + gx + 1;
-            const uint32_t f0 = m4 & 0xffu, f1 = (m4 >> 8) & 0xffu, f2 = (m4 >> 16) & 0xffu, f3 = m4 >> 24;
-            lab.x = (f0 && !prev) ? base : 0;
-            lab.y = (f1 && !f0) ? base + 1 : 0;
-            lab.z = (f2 && !f1) ? base + 2 : 0;
-            lab.w = (f3 && !f2) ? base + 3 : 0;
-        }
-        if (vec) {
-            if (p.write_mask) *reinterpret_cast<uint32_t *>(mask + (size_t)gy * W + gx) = m4;
-            if (p.init_labels) *reinterpret_cast<int4 *>(labels + (size_t)gy * W + gx) = lab;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+constexpr int kTmaStages = 4;  // tiles in flight per CTA: the load of tile k+3 is issued before tile k is processed
+
+template <int TW, int TH>
+struct TmaSmem {
+    using T = Tile<TW, TH, 2, 16>;  // 16-column halo: TMA boxes must start on a 16-byte boundary
+    static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
+    static constexpr int BYTES = kTmaStages * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(256, 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, BatchView b,
+                                                           PreprocessParams p, uint32_t *bits_out, unsigned int *sched) {
+    using T = typename TmaSmem<TW, TH>::T;
+    constexpr int STAGE = TmaSmem<TW, TH>::STAGE;
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar[kTmaStages];
+    __shared__ int s_tile[kTmaStages];
+    uint8_t *f_raw = sm + kTmaStages * STAGE, *u1_raw = f_raw + TH * TW, *bl_raw = u1_raw + T::U1_BYTES;
+
+    const int tid = threadIdx.x;
+    const int H = b.h, W = b.w;
+    const int tiles_x = b.tiles_x, tiles_y = (H + TH - 1) / TH;
+    const int per_frame = tiles_x * tiles_y, total = per_frame * b.n;
+    const int cth = p.c_thresh;
+    const bool try_flat = p.inverse && !p.write_blur && !p.force_generic && cth >= 0;
+    const uint32_t kq = 0x01010101u * (uint32_t)(127 - min(cth >> 1, 127));
+
+    // thread 0 only: take the next tile from the scheduler and start its TMA load into stage st
+    int next_static = blockIdx.x;  // thread 0: static round-robin schedule (HV_K1_STATIC) instead of the atomic counter
+    auto fetch_and_issue = [&](int st) {
+        int t;
+        if (p.static_sched) {
+            t = next_static;
+            next_static += gridDim.x;
         } else {
-            const int la[4] = {lab.x, lab.y, lab.z, lab.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (gx + k < W) {
-                    if (p.write_mask) mask[(size_t)gy * W + gx + k] = (uint8_t)(m4 >> (8 * k));
-                    if (p.init_labels) labels[(size_t)gy * W + gx + k] = la[k];
-                }
+            t = (int)atomicAdd(sched, 1u);
         }
-    }
-    static_assert(TW == 128 && TH * (TW / 32) <= 256 && (TH * (TW / 32)) % 32 == 0, "bit-packing stage layout");
-    if (tid < TH * (TW / 32)) {  // whole warps: 8 rows x 4 words per warp
-        const int r = tid >> 2, wq = tid & 3;
-        const int gy = y0 + r, gwx = (x0 >> 5) + wq;
-        const bool inside = gy < H && gwx < b.ww;
-        uint32_t word = 0;
-        if (!flat && inside) {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f[r][wq * 32]);
+        s_tile[st] = t;
+        if (t < total) {
+            const int f = t / per_frame, r = t - f * per_frame;
+            const int ty = r / tiles_x, tx = r - ty * tiles_x;
+            mbar_expect_tx(&bar[st], (uint32_t)T::G_BYTES);
+            tma_load_3d(sm + st * STAGE, &tmap, &bar[st], tx * TW - T::HX, ty * TH - T::HALO, f);
+        }
+    };
+    if (tid == 0) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                // gather bit 0 of each of the 4 mask bytes into a nibble
-                const uint32_t nib = ((src[k] & 0x01010101u) * 0x10204080u) >> 28;
-                word |= nib << (4 * k);
+        for (int k = 0; k < kTmaStages; k++) mbar_init(&bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < kTmaStages; k++) fetch_and_issue(k);
+    }
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int st = it % kTmaStages;
+        const int cur = s_tile[st];
+        if (cur >= total) break;  // tile numbers only grow: nothing is left for this CTA
+        const int f = cur / per_frame, rr = cur - f * per_frame;
+        const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
+        const int x0 = tx * TW, y0 = ty * TH;
+        unsigned long long t_a = 0, t_b = 0;
+        if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+        mbar_wait(&bar[st], (uint32_t)(it / kTmaStages) & 1u);
+        if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
+
+        // flatness test straight from shared memory, over the in-image part of the tile + halo
+        uint8_t *cur_stage = sm + st * STAGE;
+        uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
+        uint32_t acc = 0;
+        if (try_flat) {
+            // logical columns [GOFF, GOFF + 144) = image x0-8 .. x0+135, clipped to the image (word-aligned: w % 16 == 0)
+            const int r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
+            const int c_lo = max(T::GOFF, T::HX - x0), c_hi = min(T::GOFF + T::BW, W - x0 + T::HX);
+            const uint32_t ref4 = 0x01010101u * s_g[min(T::HALO + TH / 2, r_hi - 1)][min(T::HX + TW / 2, c_hi - 1)];
+            auto flat_test = [&](uint32_t v) {
+                const uint32_t d = __vabsdiffu4(v, ref4);
+                acc |= d | ((d & 0x7f7f7f7fu) + kq);
+            };
+            // 8-byte items (row, 8 columns); c_lo / c_hi are multiples of 8, so an item is entirely inside or outside
+            constexpr int NV = T::GH * (T::BW / 8);
+#pragma unroll
+            for (int k = 0; k < (NV + 255) / 256; k++) {
+                const int idx = tid + 256 * k;
+                const int r = idx / (T::BW / 8), c = T::GOFF + 8 * (idx - r * (T::BW / 8));
+                if (idx < NV && r >= r_lo && r < r_hi && c >= c_lo && c < c_hi) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(&s_g[r][c]);
+                    flat_test(v.x);
+                    flat_test(v.y);
+                }
             }
         }
-        if (inside) bits_out[((size_t)f * H + gy) * b.ww + gwx] = word;
-        // occupancy nibble of this (row, tile): which of its 4 words are non-zero
-        const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
-        if (b.rowflags && wq == 0 && gy < H)
-            b.rowflags[(size_t)f * b.rf_stride + (size_t)gy * b.tiles_x + blockIdx.x] =
-                (uint8_t)((bal >> (tid & 31)) & 0xfu);
+        const bool flat = !__syncthreads_or((int)(acc & 0x80808080u)) && try_flat;
+        tile_compute_and_store<TW, TH, 2, 16>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat, tid);
+        __syncthreads();  // every read of this stage and of the scratch tiles is done: the stage can be refilled
+        if (b.phase_ns && tid == 0) {  // debug: time per tile split into TMA wait and processing, flat vs non-flat
+            unsigned long long t_c;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
+            atomicAdd(b.phase_ns + 200 + (flat ? 0 : 3), t_b - t_a);
+            atomicAdd(b.phase_ns + 201 + (flat ? 0 : 3), t_c - t_b);
+            atomicAdd(b.phase_ns + 202 + (flat ? 0 : 3), 1ull);
+        }
+        if (tid == 0) fetch_and_issue(st);
+    }
+    // the last CTA to leave rearms the scheduler for the next launch (every CTA has made its final fetch by then)
+    if (tid == 0 && !p.static_sched) {
+        __threadfence();
+        const unsigned int d = atomicAdd(sched + 1, 1u);
+        if (d == gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+        }
     }
 }
 
@@ -449,6 +651,76 @@ cudaError_t launch_gray_first3(const uint8_t *d_img, int h, int w, int c, uint8_
     const size_t total = (size_t)h * w;
     const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 16) ? ((total + 255) / 256) : (size_t)(148 * 16));
     k_gray3<<<grid, 256, 0, s>>>(d_img, 1, h, w, c, (size_t)w * c, (size_t)h * w * c, d_gray);
+    return cudaGetLastError();
+}
+
+namespace {
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;  // resolved once; immutable afterwards
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int k1_ctas_per_sm() {
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("HV_K1_CTAS_PER_SM");
+        v = e ? atoi(e) : 4;
+        if (v < 1 || v > 6) v = 4;
+    }
+    return v;
+}
+
+}  // namespace
+
+// per device, once (hv_create): the TMA kernel's stages need more than the 48 KB static shared-memory limit
+cudaError_t configure_preprocess_tma() {
+    cudaError_t e = cudaFuncSetAttribute(k_preprocess_tma<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TmaSmem<128, 32>::BYTES);
+    if (e != cudaSuccess) return e;
+    // ask for the largest shared-memory carve-out: residency of these kernels is limited by shared memory, not by L1
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_preprocess<128, 32, 0>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared);
+}
+
+// TMA path: 3-D tensor map {w, h, n} over the gray frames, box = tile + halo, zero fill outside the image.
+cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
+                                  int num_sms, cudaStream_t s, bool *used) {
+    *used = false;
+    using T = Tile<128, 32, 2, 16>;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(b.gray);
+    if (p.blur_radius != 2 || !sched || (base & 15) || (b.gray_row_stride & 15) || (b.gray_frame_stride & 15) || (b.w & 15) ||
+        getenv("HV_K1_NO_TMA"))
+        return cudaSuccess;
+    auto enc = tensor_map_encoder();
+    if (!enc) return cudaSuccess;
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)b.w, (cuuint64_t)b.h, (cuuint64_t)b.n};
+    const cuuint64_t strides[2] = {(cuuint64_t)b.gray_row_stride, (cuuint64_t)b.gray_frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)T::GW, (cuuint32_t)T::GH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(b.gray), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaSuccess;  // fall back to the non-TMA kernel
+    const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
+    int grid = num_sms * k1_ctas_per_sm();
+    if (grid > tiles) grid = tiles;
+    k_preprocess_tma<128, 32><<<grid, 256, TmaSmem<128, 32>::BYTES, s>>>(tmap, b, p, bits_out, sched);
+    *used = true;
     return cudaGetLastError();
 }
 
