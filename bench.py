@@ -217,8 +217,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         b = base[perm].astype(np.int16) + rng.integers(-1, 2, size=base.shape, dtype=np.int16)
         pool_host.append(np.clip(b, 0, 255).astype(np.uint8))
     pool_dev = [torch.from_numpy(b).to(dev) for b in pool_host]
-    d_mask = torch.empty((nf, h, w), dtype=torch.uint8, device=dev)
-    d_labels = torch.empty((nf, h, w), dtype=torch.int32, device=dev)
+    # two sets of outputs, used alternately: consecutive batches must not share buffers, so that K1 of step i+1 can
+    # overlap the per-frame CCL kernel of step i (programmatic dependent launch inside the library)
+    d_mask = [torch.empty((nf, h, w), dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_labels = [torch.empty((nf, h, w), dtype=torch.int32, device=dev) for _ in range(2)]
 
     det = hc.Detector(local_rank, num_slots=args.slots)
     stream = torch.cuda.current_stream()
@@ -227,17 +229,22 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     # ---- parity gate: the timed configuration must agree with the oracle before any number counts ----------------------
     parity = None
-    res0 = det.detect_device(pool_dev[0].data_ptr(), nf, h, w, 1, params, d_mask.data_ptr(), d_labels.data_ptr())
-    if rank == 0 and not args.skip_parity:
+    def check_against_oracle(res, batch_host, mask_t, labels_t, frames):
         from oracle import oracle as O
         O.build()
-        for f in (0, nf - 1):
-            ref = O.detect_contamination(pool_host[0][f][:, :, None])
-            ok = (np.array_equal(d_mask[f].cpu().numpy(), ref.mask) and
-                  np.array_equal(d_labels[f].cpu().numpy(), ref.labels) and
-                  [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in res0.defects_of(f)] ==
-                  [(d["position"], d["size"], d["confidence"]) for d in ref.defects])
-            parity = ok if parity is None else (parity and ok)
+        ok = True
+        for f in frames:
+            ref = O.detect_contamination(batch_host[f][:, :, None])
+            ok = ok and (np.array_equal(mask_t[f].cpu().numpy(), ref.mask) and
+                         np.array_equal(labels_t[f].cpu().numpy(), ref.labels) and
+                         [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"]))
+                          for d in res.defects_of(f)] ==
+                         [(d["position"], d["size"], d["confidence"]) for d in ref.defects])
+        return ok
+
+    res0 = det.detect_device(pool_dev[0].data_ptr(), nf, h, w, 1, params, d_mask[0].data_ptr(), d_labels[0].data_ptr())
+    if rank == 0 and not args.skip_parity:
+        parity = check_against_oracle(res0, pool_host[0], d_mask[0], d_labels[0], (0, nf - 1))
         if not parity:
             raise SystemExit("parity check against the oracle FAILED; refusing to report a number")
 
@@ -255,7 +262,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             dist.all_reduce(stats_buf)
 
     def step(i):
-        det.enqueue_device(pool_dev[i % pool_n].data_ptr(), nf, h, w, 1, params, d_mask.data_ptr(), d_labels.data_ptr())
+        det.enqueue_device(pool_dev[i % pool_n].data_ptr(), nf, h, w, 1, params, d_mask[i & 1].data_ptr(),
+                           d_labels[i & 1].data_ptr())
         reduce_stats()
 
     # ---- settle clocks under load, then W warm-up steps ------------------------------------------------------------------
@@ -276,7 +284,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------------------------------
-    det.profile_enable([hc._abi.HV_K_PREPROCESS])  # time the dominant kernel live, on its launching stream
+    # no per-kernel events inside the timed region: an event between two kernels would serialise them and hide the
+    # overlap of K1(step i+1) with the per-frame CCL of step i that production runs get
     l0 = det.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -291,10 +300,14 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     torch.cuda.synchronize()
     launches = det.launch_count() - l0
     ev_ms = e0.elapsed_time(e1)
-    prof = det.profile()
-    det.profile_enable([])
     last = det.fetch_results(nf)           # results of the final step: proves the pipeline ran to completion
     clocks = sampler.stop()
+    parity_after = None
+    if rank == 0 and not args.skip_parity:  # the overlapped steady state must still be bit-exact
+        j = K - 1
+        parity_after = check_against_oracle(last, pool_host[j % pool_n], d_mask[j & 1], d_labels[j & 1], (1, nf - 2))
+        if not parity_after:
+            raise SystemExit("parity check of the last timed step FAILED; refusing to report a number")
 
     t = torch.tensor([ev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -302,12 +315,14 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     ms_total = float(t.item())
     value = world * nf * K / (ms_total * 1e-3)
 
-    # ---- per-kernel shares: one extra, untimed, fully profiled pass ---------------------------------------------------------
+    # ---- per-kernel durations: the same K steps again with a CUDA event pair around every kernel, on the launching
+    #      stream (the events serialise the kernels, so these are the isolated per-kernel times) ------------------------------
     det.profile_enable(None)
-    for j in range(min(K, 10)):
+    for j in range(K):
         step(j)
     torch.cuda.synchronize()
-    shares = {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in det.profile().items()}
+    prof = det.profile()
+    shares = {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in prof.items()}
     det.profile_enable([])
 
     # ---- end to end: pinned host frames -> H2D -> pipeline -> D2H of the results, through hv_submit / hv_wait -----------------
@@ -399,19 +414,23 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "l2_policy": f"inputs rotate over a pool of {pool_n} distinct batches ({pool_n * batch_bytes / 1e6:.0f} MB "
                                 f"> 126 MB L2); each step also writes {5 * batch_bytes / 1e6:.0f} MB of mask+labels",
                    "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B stats all-reduce per step)",
-                   "timed": "K x hv_enqueue_device on one stream, CUDA events on that stream; results of every step stay "
-                            "on the device, the last step's are fetched and checked"},
+                   "timed": "K x hv_enqueue_device on one stream, CUDA events on that stream; K1 of step i+1 overlaps the "
+                            "per-frame CCL kernel of step i (programmatic dependent launch, alternating output buffers); "
+                            "results of every step stay on the device, the last step's are fetched and checked against "
+                            "the oracle"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "how": f"hv_submit/hv_wait, {args.slots} batches in flight, pinned host frames, wall clock"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "preprocess_mask (K1)", "kernel_ms": k1_ms,
+                     "kernel_ms_how": "mean over K launches, CUDA events on the launching stream, in a separate pass of "
+                                      "the same K steps (events inside the timed region would serialise the overlap)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                      "pipeline_achieved": alg_bytes / (ms_total / K * 1e-3) / 1e9,
                      "pipeline_frac": alg_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
         "kernel_ms_per_step": shares,
         "clocks": clocks,
-        "parity_checked": bool(parity),
+        "parity_checked": bool(parity) and bool(parity_after),
         "wall_ms_per_step": wall / K * 1e3,
         "line_stats": total_stats,
         "last_step": {"rejected": int(last.rejected.sum()), "defects": int(last.frames["n_defects"].sum())},

@@ -18,6 +18,8 @@ using namespace hv;
 
 namespace {
 
+constexpr int kSyncSlots = 2;
+
 thread_local std::string g_create_error;
 
 template <typename T>
@@ -109,11 +111,16 @@ struct hv_ctx {
     unsigned long long *d_phase_ns = nullptr;
     uint64_t launches = 0;
     int64_t next_ticket = 1;
-    int next_slot = 1;
+    int next_slot = 0;
     // CCL path selection: sparse masks go through the fused per-frame kernel; if a batch needed the global-memory
     // fallback the next batches use the global path directly and the fused kernel is re-tried every 8th batch
     bool dense_hint = false;
     uint32_t dense_batches = 0;
+    int sync_cur = 0;  // which of the two synchronous slots holds the most recent batch
+    // last batch enqueued through the device-resident path (for the programmatic-dependent-launch overlap decision)
+    cudaStream_t last_stream = nullptr;
+    bool last_valid = false, last_fused_tail = false;
+    const void *last_mask = nullptr, *last_labels = nullptr;
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -249,6 +256,7 @@ bool gaussian_kernel_q8(int n, double sigma, uint16_t *k16) {
 }
 
 cudaStream_t sync_stream(hv_ctx *ctx) { return ctx->use_user_stream ? ctx->user_stream : ctx->slots[0].stream; }
+Slot &cur_sync_slot(hv_ctx *ctx) { return ctx->slots[ctx->sync_cur]; }
 
 hv_status validate_shape(hv_ctx *ctx, int n, int h, int w, int c) {
     if (n <= 0 || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "batch, height and width must be positive");
@@ -381,7 +389,6 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
-    pp.static_sched = getenv("HV_K1_DYNAMIC") ? 0 : 1;
     pp.write_mask = morph ? 0 : 1;
     pp.init_labels = morph ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
@@ -414,8 +421,15 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     {
         ProfScope ps(ctx, HV_K_PREPROCESS, st);
         bool used_tma = false;
+        // Programmatic dependent launch: if the kernel right before this one on the stream is the previous batch's fused
+        // per-frame CCL kernel (25 CTAs, latency-bound) and the two batches share no buffers, K1 may start while it is
+        // still running.  Anything else in between (copies, events, other kernels) means plain stream order.
+        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
+                         !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
+                         !getenv("HV_NO_PDL");
+        pp.static_sched = (pdl || getenv("HV_K1_DYNAMIC")) ? 0 : 1;
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
-            HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, st, &used_tma));
+            HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
         ctx->launches++;
     }
@@ -443,6 +457,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     }
     s.used_fused = fused;
     s.score = sp;
+    ctx->last_valid = true;
+    ctx->last_stream = st;
+    ctx->last_fused_tail = fused;
+    ctx->last_mask = b.mask;
+    ctx->last_labels = b.labels;
     s.view = b;
     s.has_batch = true;
     s.have_blur = separate_blur || want_blur;
@@ -645,7 +664,9 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
-    const int nslots = 1 + (ctx->cfg.num_slots > 0 ? ctx->cfg.num_slots : 3);  // slot 0 = synchronous entry points
+    // slots 0 and 1: the synchronous / device-resident entry points, used alternately so that consecutive batches do not
+    // share scratch and K1 of batch i+1 may overlap the per-frame CCL of batch i; slots 2..: hv_submit / hv_wait
+    const int nslots = kSyncSlots + (ctx->cfg.num_slots > 0 ? ctx->cfg.num_slots : 3);
     ctx->slots.resize(nslots);
     for (auto &s : ctx->slots) {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -732,17 +753,19 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
         pr = *params;
     else
         hv_params_default(&pr);
-    return enqueue_pipeline(ctx, ctx->slots[0], sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr, d_mask,
-                            d_labels, (ctx->cfg.flags & 4u) != 0);
+    ctx->sync_cur ^= 1;
+    return enqueue_pipeline(ctx, cur_sync_slot(ctx), sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr,
+                            d_mask, d_labels, (ctx->cfg.flags & 4u) != 0);
 }
 
 hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
                            size_t *n_defects_total) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
-    Slot &s = ctx->slots[0];
+    Slot &s = cur_sync_slot(ctx);
     if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = sync_stream(ctx);
+    ctx->last_valid = false;  // the read-back sits between this batch and the next: no overlap across it
     hv_status rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
@@ -753,9 +776,10 @@ hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *def
 
 hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
-    Slot &s = ctx->slots[0];
+    Slot &s = cur_sync_slot(ctx);
     if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->last_valid = false;
     if (s.used_fused) {  // make sure flagged frames have been completed by the global path before copying
         cudaStream_t st = sync_stream(ctx);
         hv_status rs = enqueue_readback(ctx, s, st);
@@ -789,7 +813,9 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
         pr = *params;
     else
         hv_params_default(&pr);
-    Slot &s = ctx->slots[0];
+    ctx->sync_cur ^= 1;
+    ctx->last_valid = false;
+    Slot &s = cur_sync_slot(ctx);
     cudaStream_t st = sync_stream(ctx);
     rs = upload_frames(ctx, s, st, frames, n, h, w, c, row_stride, frame_stride);
     if (rs != HV_OK) return rs;
@@ -820,15 +846,16 @@ hv_status hv_submit(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, in
     // find a free asynchronous slot (slots 1..)
     int pick = -1;
     const int nslots = (int)ctx->slots.size();
-    for (int k = 0; k < nslots - 1; k++) {
-        const int idx = 1 + (ctx->next_slot - 1 + k) % (nslots - 1);
+    const int nasync = nslots - kSyncSlots;
+    for (int k = 0; k < nasync; k++) {
+        const int idx = kSyncSlots + (ctx->next_slot + k) % nasync;
         if (ctx->slots[idx].ticket < 0) {
             pick = idx;
             break;
         }
     }
     if (pick < 0) return fail(ctx, HV_ERR_CAPACITY, "all slots are in flight: call hv_wait first");
-    ctx->next_slot = 1 + (pick % (nslots - 1));
+    ctx->next_slot = (pick - kSyncSlots + 1) % nasync;
     Slot &s = ctx->slots[pick];
     rs = upload_frames(ctx, s, s.stream, frames, n, h, w, c, row_stride, frame_stride);
     if (rs != HV_OK) return rs;
@@ -845,7 +872,7 @@ hv_status hv_submit(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, in
 hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
                   size_t *n_defects_total) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
-    for (size_t i = 1; i < ctx->slots.size(); i++) {
+    for (size_t i = kSyncSlots; i < ctx->slots.size(); i++) {
         Slot &s = ctx->slots[i];
         if (s.ticket == ticket && ticket > 0) {
             HV_TRY_CUDA(ctx, cudaEventSynchronize(s.done));

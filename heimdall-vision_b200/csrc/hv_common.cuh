@@ -67,7 +67,7 @@ cudaError_t launch_gray3(const uint8_t *d_img, int n, int h, int w, size_t row_s
                          uint8_t *d_gray, cudaStream_t s);
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s);
 cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
-                                  int num_sms, cudaStream_t s, bool *used);
+                                  int num_sms, bool pdl, cudaStream_t s, bool *used);
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);

@@ -120,6 +120,8 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
 }
 
 __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams sp) {
+    // let a programmatically dependent kernel (K1 of the next batch, which shares no buffers with this one) start now
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

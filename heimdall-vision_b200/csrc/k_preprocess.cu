@@ -698,7 +698,7 @@ cudaError_t configure_preprocess_tma() {
 
 // TMA path: 3-D tensor map {w, h, n} over the gray frames, box = tile + halo, zero fill outside the image.
 cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
-                                  int num_sms, cudaStream_t s, bool *used) {
+                                  int num_sms, bool pdl, cudaStream_t s, bool *used) {
     *used = false;
     using T = Tile<128, 32, 2, 16>;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.gray);
@@ -719,9 +719,18 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
     int grid = num_sms * k1_ctas_per_sm();
     if (grid > tiles) grid = tiles;
-    k_preprocess_tma<128, 32><<<grid, 256, TmaSmem<128, 32>::BYTES, s>>>(tmap, b, p, bits_out, sched);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = TmaSmem<128, 32>::BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
     *used = true;
-    return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32>, tmap, b, p, bits_out, sched);
 }
 
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s) {
