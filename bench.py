@@ -30,6 +30,15 @@ for _p in (ROOT, PKG):
 
 import numpy as np  # noqa: E402
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "frames/s (contamination pipeline: blur->threshold->CCL->blob stats->reject), device-resident inputs"
 UNIT = "frames/s"
 ALG_BYTES_PER_PX = 6  # input 1 B + final mask 1 B + i32 label map 4 B per pixel
@@ -186,7 +195,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -261,10 +270,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             stats_buf.copy_(stats_view)
             dist.all_reduce(stats_buf)
 
-    def step(i):
+    def step(i, collective=True):
         det.enqueue_device(pool_dev[i % pool_n].data_ptr(), nf, h, w, 1, params, d_mask[i & 1].data_ptr(),
                            d_labels[i & 1].data_ptr())
-        reduce_stats()
+        if collective:
+            reduce_stats()
 
     # ---- settle clocks under load, then W warm-up steps ------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -273,7 +283,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     i = 0
     while time.perf_counter() < t_end:
         for _ in range(20):
-            step(i)
+            step(i, collective=False)  # time-based loop: ranks do different numbers of iterations, so no collective here
             i += 1
         torch.cuda.synchronize()
     for j in range(W):
@@ -440,13 +450,18 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     bad = [r for r in clocks.get("reasons", []) if r in ClockSampler.BAD]
     if bad:
         line["clock_warning"] = f"throttle reasons seen: {bad}"
-    print(json.dumps(line), flush=True)
+    emit(line)
     det.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main() -> None:
+    # Only the JSON line may reach stdout (NCCL and others print banners there): park fd 1 on stderr until the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
