@@ -383,7 +383,13 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.frame_flags = s.frame_flags.p;
     b.frame_select = nullptr;
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
-    if (b.phase_ns) cudaMemsetAsync(ctx->d_phase_ns + 200, 0, 8 * sizeof(unsigned long long), st);
+    if (b.phase_ns) {
+        cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
+        cudaMemsetAsync(ctx->d_phase_ns + 248, 0xff, sizeof(unsigned long long), st);
+        cudaMemsetAsync(ctx->d_phase_ns + 252, 0xff, sizeof(unsigned long long), st);
+        const char *pf = getenv("HV_PHASE_FRAME");
+        b.phase_frame = pf ? atoi(pf) : 0;
+    }
 
     PreprocessParams pp{};
     pp.c_thresh = clamp_threshold(pr.threshold);
@@ -428,6 +434,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
         pp.static_sched = (pdl || getenv("HV_K1_DYNAMIC")) ? 0 : 1;
+        if (getenv("HV_K1_SKIP_AUX")) pp.static_sched |= 2;
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));

@@ -37,7 +37,8 @@ struct BatchView {
     hv_frame_result *results;  // n
     hv_line_stats *stats;      // 1
     uint32_t *frame_flags;     // n: written by the fused per-frame kernel, 1 = frame needs the global-memory CCL path
-    unsigned long long *phase_ns;  // 16 or NULL: per-phase timestamps of frame 0 in the fused kernel (debug)
+    unsigned long long *phase_ns;  // 256 or NULL: per-phase timestamps of frame `phase_frame` in the fused kernel (debug)
+    int phase_frame;               // which frame's CTA records the stamps (HV_PHASE_FRAME, default 0)
     const uint32_t *frame_select;  // n or NULL: when set, the global-path kernels only touch frames with a non-zero entry
 };
 

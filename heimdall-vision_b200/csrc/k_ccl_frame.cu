@@ -3,18 +3,23 @@
 // Same semantics as the global-memory path (k_ccl.cu K2..K5 + k_score.cu K6; reference:
 // rust/heimdall-core/src/detection.rs:215-311), different data placement.  The global path keeps its union-find
 // parents inside the 4 B/px label plane, so every find/union step is a dependent DRAM round trip and the five
-// kernels are latency-bound (ncu: 5-17 long-scoreboard stalls per issued instruction, < 7 % DRAM throughput).
-// Inspection masks are sparse (a few thousand foreground pixels per 1.3 MP frame), so here the whole working set of
-// a frame lives in shared memory:
-//   phase 0  ordered compaction of the frame's non-zero bitmask words              -> s_widx / s_wbits   (raster order)
-//   phase 1  word-runs become nodes, numbered in raster order (exclusive scan)      -> s_woff
+// kernels are latency-bound.  Inspection masks are sparse (a few thousand foreground pixels per 1.3 MP frame), so
+// here the whole working set of a frame lives in shared memory:
+//   phase 0  ordered compaction of the frame's non-zero bitmask words              -> widx / wbits   (raster order)
+//   phase 1  word-runs become nodes, numbered in raster order (exclusive scan)      -> woff, node_px, node_len
 //   phase 2  unions by minimum node id in shared memory (node id order == raster order of the runs' first pixels,
-//            so every root is its component's raster-first run); vertical neighbours are found by binary search
+//            so every root is its component's raster-first run)
 //   phase 3  flatten, rank the roots with a block scan                              -> canonical label = rank + 1
-//   phase 4  per-run statistics into a shared-memory blob table (warp-aggregated), final labels to the label plane
+//   phase 4  per-run statistics into a shared-memory blob table, final labels to the label plane
 //   phase 5  blob table -> global, scoring (shared with K6), ordered defect compaction, per-frame result, line stats
 // A frame that does not fit (more than kCapW non-zero words, kCapN runs or kCapB components, or a side > 8192) is left
 // untouched and flagged in frame_flags; the host then runs the global path on exactly those frames.
+//
+// The kernel is latency-bound by construction (25 CTAs for the headline batch), and every instruction is executed
+// once per CTA, i.e. from a cold instruction cache: the first version (96 KB of SASS from 8-fold unrolled phase
+// bodies, work split unevenly over the warps) spent 55 us per batch, 70 % of the warp samples waiting at barriers for
+// one straggling warp.  This version keeps the code small (runtime loops, one shared scan routine), gives every
+// thread an equal share of every phase, and has no dependent global-memory round trip that can be avoided.
 #include "hv_common.cuh"
 #include "score_device.cuh"
 
@@ -22,35 +27,33 @@ namespace hv {
 
 namespace {
 
-constexpr int kFT = 512;    // threads per CTA (<= 128 registers per thread: the scoring probe keeps 50 loads in flight)
+constexpr int kFT = 512;       // threads per CTA
 constexpr int kNW = kFT / 32;  // warps per CTA
-constexpr int kEPT = 4096 / kFT;  // compacted words per thread
-constexpr int kNPT = 8192 / kFT;  // nodes per thread
-constexpr int kCapW = 4096; // non-zero words per frame
-constexpr int kCapN = 8192; // word-runs (nodes) per frame
-constexpr int kCapB = 2048; // components per frame
-
-static_assert(kCapW == kEPT * kFT && kCapN == kNPT * kFT, "capacities must be multiples of the CTA size");
+constexpr int kCapW = 4096;    // non-zero words per frame
+constexpr int kCapN = 8192;    // word-runs (nodes) per frame
+constexpr int kCapB = 2048;    // components per frame
+constexpr int kMaxEPT = kCapW / kFT;  // compacted words per thread (blocked partition)
 
 struct FrameSmem {
-    uint32_t widx[kCapW];    // word index (y * ww + wx) of the compacted non-zero words, raster order
+    uint32_t widx[kCapW];      // word index (y * ww + wx) of the compacted non-zero words, raster order
     uint32_t wbits[kCapW];
+    uint32_t parent[kCapN];    // union-find parents (node ids)
+    uint32_t node_px[kCapN];   // pixel index (y * w + x) of the first pixel of the run
     uint16_t woff[kCapW + 8];  // first node of every compacted word
-    uint32_t parent[kCapN];  // union-find parents; after phase 3: exclusive root ranks
-    uint32_t nroot[kCapN];   // root of every node after flattening
-    uint32_t node_px[kCapN]; // pixel index (y * w + x) of the first pixel of the run
+    uint16_t up[kCapW];        // entry of the word directly above when it overlaps this word, else 0xffff
+    uint16_t rnk[kCapN];       // rank of the component among the roots (valid at root nodes)
     uint8_t node_len[kCapN];
     uint32_t b_area[kCapB], b_sy[kCapB], b_sx[kCapB], b_ymin[kCapB], b_ymax[kCapB], b_xmin[kCapB], b_xmax[kCapB];
     uint32_t warp_tmp[32];
-    uint32_t warp_tmp2[32];
-    unsigned long long area_sum;
+    uint32_t warp_fg[32];
+    uint32_t area_sum;
     uint32_t hist[HV_STATS_AREA_BINS];
 };
 static_assert(sizeof(FrameSmem) <= 227 * 1024, "FrameSmem must fit the 227 KB per-CTA shared memory of sm_100");
 
-// exclusive scan of one value per thread across the CTA; returns the exclusive prefix, *total gets the block sum.
-// Contains two __syncthreads(); tmp must hold 32 words.
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total_out) {
+// exclusive scan of one value per thread across the CTA; returns the exclusive prefix, *total_out gets the block sum.
+// Contains two __syncthreads().  One copy in the binary (see the header: code size is latency here).
+__device__ __noinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total_out) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -64,14 +67,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     uint32_t w = lane < kNW ? tmp[lane] : 0u;
     uint32_t wi = w;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < kNW; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
         if (lane >= o) wi += t;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
-    const uint32_t wprefix = __shfl_sync(0xffffffffu, wi - w, wid);
-    *total_out = total;
-    return wprefix + incl - v;
+    *total_out = __shfl_sync(0xffffffffu, wi, kNW - 1);
+    return __shfl_sync(0xffffffffu, wi - w, wid) + incl - v;
 }
 
 __device__ __forceinline__ uint32_t s_find(volatile uint32_t *parent, uint32_t a) {
@@ -83,25 +84,11 @@ __device__ __forceinline__ uint32_t s_find(volatile uint32_t *parent, uint32_t a
     return a;
 }
 
-// find with path halving: every other node on the way is re-pointed at its grandparent (atomicMin keeps parents
-// monotonically decreasing under concurrent unions).  Without it the simultaneous hooks of a long vertical line leave
-// a linked list whose traversal costs O(length) per find.
-__device__ __forceinline__ uint32_t s_find_halve(uint32_t *parent, uint32_t a) {
-    volatile uint32_t *vp = parent;
+// Lock-free union by minimum id (atomicMin keeps parents monotonically decreasing under concurrent unions).
+__device__ __noinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b) {
     while (true) {
-        const uint32_t p = vp[a];
-        if (p == a) return a;
-        const uint32_t gp = vp[p];
-        if (gp == p) return p;
-        atomicMin(parent + a, gp);
-        a = gp;
-    }
-}
-
-__device__ __forceinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b) {
-    while (true) {
-        a = s_find_halve(parent, a);
-        b = s_find_halve(parent, b);
+        a = s_find(parent, a);
+        b = s_find(parent, b);
         if (a == b) return;
         if (a < b) {
             const uint32_t t = a;
@@ -111,6 +98,21 @@ __device__ __forceinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b
         const uint32_t old = atomicMin(parent + a, b);
         if (old == a) return;
         a = old;
+    }
+}
+
+// pointer jumping: every node shortens its own path (parent <- grandparent until the parent is a root); all nodes
+// concurrently, so a chain of length n collapses in O(log n) rounds
+__device__ __forceinline__ void pointer_jump(uint32_t *parent, uint32_t nn, int tid) {
+    volatile uint32_t *vp = parent;
+    for (uint32_t v = tid; v < nn; v += kFT) {
+        uint32_t p = vp[v];
+        while (true) {
+            const uint32_t gp = vp[p];
+            if (gp == p) break;
+            vp[v] = gp;
+            p = gp;
+        }
     }
 }
 
@@ -126,61 +128,55 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int H = b.h, W = b.w, WW = b.ww;
-    const int nwords = H * WW;
-    const uint32_t *bits = b.bits + (size_t)f * nwords;
-    // optional per-phase timestamps of frame 0 (HV_FLAG_PHASE_TIMING): ns since kernel start, for DESIGN.md / tuning
-    // layout: phase_ns[stamp * 16 + warp] = globaltimer at the moment the warp reaches the stamp (BEFORE the barrier that
-    // follows), so per-phase, per-warp work and barrier waits can be told apart
+    const uint32_t *bits = b.bits + (size_t)f * H * WW;
+    // optional per-phase timestamps of one frame (HV_FLAG_PHASE_TIMING): phase_ns[stamp * 16 + warp] = globaltimer at
+    // the moment the warp reaches the stamp (before the barrier that follows)
     int stamp_i = 0;
+    unsigned long long t_start = 0;
+    if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     auto stamp = [&]() {
-        if (b.phase_ns && f == 0 && lane == 0 && stamp_i < 16) {
+        if (b.phase_ns && f == b.phase_frame && lane == 0 && stamp_i < 12) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             b.phase_ns[stamp_i * 16 + wid] = t;
         }
         stamp_i++;
     };
-    stamp();
+    stamp();  // 0
 
     // ---- phase 0: ordered compaction of the non-zero words ------------------------------------------------------------
     // K1 left one occupancy nibble per (row, 128-px tile): bit k set <=> word 4*tile+k of that row is non-zero.  Items
     // (row-major, tile-minor) are in raster order of their words, so thread t takes the contiguous items
-    // [t*ipt, (t+1)*ipt), a block scan of the popcounts gives its first output slot, and only non-zero words are ever
-    // fetched: two dependent memory round trips instead of a scan over every word of the frame.
+    // [t*ipt, (t+1)*ipt) and a block scan of the popcounts gives its first output slot.
     const int TX = b.tiles_x;
     const int nitems = H * TX;
     const uint8_t *rf = b.rowflags + (size_t)f * b.rf_stride;
     const int ipt = (((nitems + kFT - 1) / kFT) + 3) & ~3;  // items per thread, multiple of 4 -> aligned 32-bit loads
     const int it0 = min(tid * ipt, nitems), it1 = min(it0 + ipt, nitems);
     uint32_t cnt = 0;
-    for (int it = it0; it < it1; it += 16) {  // up to 4 independent 32-bit loads in flight
-        uint32_t q[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) q[k] = (it + 4 * k < it1) ? __ldcg(reinterpret_cast<const uint32_t *>(rf + it + 4 * k)) : 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int left = it1 - (it + 4 * k);  // bytes of this word that belong to the chunk (>= 4 except at the end)
-            const uint32_t v = left >= 4 ? q[k] : (left > 0 ? (q[k] & ((1u << (8 * left)) - 1u)) : 0u);
-            cnt += __popc(v & 0x0f0f0f0fu);
-        }
+#pragma unroll 4
+    for (int it = it0; it < it1; it += 4) {
+        uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(rf + it));
+        const int left = it1 - it;
+        if (left < 4) q &= (1u << (8 * left)) - 1u;
+        cnt += __popc(q & 0x0f0f0f0fu);
     }
     if (tid < HV_STATS_AREA_BINS) S.hist[tid] = 0;
     if (tid == 0) S.area_sum = 0;
     uint32_t nw = 0;
     uint32_t pos = block_exclusive_scan(cnt, S.warp_tmp, &nw);
-    const bool dims_ok = H <= 8192 && W <= 8192;
-    if (nw > (uint32_t)kCapW || !dims_ok) {  // block-uniform
+    if (nw > (uint32_t)kCapW || H > 8192 || W > 8192) {  // block-uniform
         if (tid == 0) b.frame_flags[f] = 1u;
         return;
     }
-    if (cnt) {  // index pass: no memory traffic besides the (cached) occupancy bytes
+    if (cnt) {  // index pass: the occupancy bytes come from L1 this time
         for (int it = it0; it < it1; it += 4) {
+            uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(rf + it));
             const int left = it1 - it;
-            uint32_t q = __ldcg(reinterpret_cast<const uint32_t *>(rf + it));
             if (left < 4) q &= (1u << (8 * left)) - 1u;
             q &= 0x0f0f0f0fu;
             while (q) {
-                const int bitpos = __ffs(q) - 1;  // byte k = bitpos >> 3, word j = bitpos & 7
+                const int bitpos = __ffs(q) - 1;  // byte = bitpos >> 3, word within the tile = bitpos & 7
                 q &= q - 1;
                 const int item = it + (bitpos >> 3);
                 const int y = item / TX, tx = item - y * TX;
@@ -188,35 +184,24 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
             }
         }
     }
-    __syncthreads();
-    // load pass: every flagged word is fetched by an independent load (one memory round trip for the whole frame)
-    {
-        uint32_t wv[kEPT];
-#pragma unroll
-        for (int k = 0; k < kEPT; k++) {
-            const uint32_t e = tid + k * kFT;
-            wv[k] = e < nw ? __ldcg(bits + S.widx[e]) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < kEPT; k++) {
-            const uint32_t e = tid + k * kFT;
-            if (e < nw) S.wbits[e] = wv[k];
-        }
-    }
-    stamp();  // end of this warp's compaction work
+    stamp();  // 1
     __syncthreads();
 
-    stamp();
-    // ---- phase 1: nodes = word-runs, numbered in raster order ----------------------------------------------------------
-    // thread t owns entries [kEPT*t, kEPT*(t+1))
-    uint32_t rc[kEPT], local = 0, fgpx = 0;
+    // ---- phase 1: fetch the words; word-runs become nodes, numbered in raster order -----------------------------------------
+    // blocked partition: thread t owns entries [t*ept, (t+1)*ept), so one scan orders the runs of the whole frame
+    const int ept = ((int)nw + kFT - 1) / kFT;  // <= kMaxEPT
+    const int e0 = min(tid * ept, (int)nw), e1 = min(e0 + ept, (int)nw);
+    uint32_t local = 0, fgpx = 0;
+    {
+        uint32_t wv[kMaxEPT];
 #pragma unroll
-    for (int k = 0; k < kEPT; k++) {
-        const uint32_t e = kEPT * tid + k;
-        const uint32_t m = e < nw ? S.wbits[e] : 0u;
-        rc[k] = __popc(m & ~(m << 1));
-        local += rc[k];
-        fgpx += __popc(m);
+        for (int k = 0; k < kMaxEPT; k++) wv[k] = (e0 + k < e1) ? __ldg(bits + S.widx[e0 + k]) : 0u;  // one round trip
+#pragma unroll
+        for (int k = 0; k < kMaxEPT; k++) {
+            if (e0 + k < e1) S.wbits[e0 + k] = wv[k];
+            local += __popc(wv[k] & ~(wv[k] << 1));
+            fgpx += __popc(wv[k]);
+        }
     }
     uint32_t nn = 0;
     uint32_t off = block_exclusive_scan(local, S.warp_tmp, &nn);
@@ -224,177 +209,131 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         if (tid == 0) b.frame_flags[f] = 1u;
         return;
     }
-#pragma unroll
-    for (int k = 0; k < kEPT; k++) {
-        const uint32_t e = kEPT * tid + k;
-        if (e < nw) {
-            S.woff[e] = (uint16_t)off;
-            const uint32_t i = S.widx[e];
-            const uint32_t y = i / WW, wx = i - y * WW;
-            uint32_t rest = S.wbits[e];
-            uint32_t v = off;
-            while (rest) {
-                const int bit = __ffs(rest) - 1;
-                const uint32_t shifted = ~(rest >> bit);
-                const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
-                rest = (bit + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << bit));
-                S.node_px[v] = y * W + wx * 32 + bit;
-                S.node_len[v] = (uint8_t)len;
-                S.parent[v] = v;
-                v++;
-            }
+    for (int e = e0; e < e1; e++) {
+        S.woff[e] = (uint16_t)off;
+        const uint32_t i = S.widx[e];
+        const uint32_t y = i / WW, wx = i - y * WW;
+        uint32_t rest = S.wbits[e];
+        while (rest) {
+            const int bit = __ffs(rest) - 1;
+            const uint32_t shifted = ~(rest >> bit);
+            const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
+            rest = (bit + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << bit));
+            S.node_px[off] = y * W + wx * 32 + bit;
+            S.node_len[off] = (uint8_t)len;
+            off++;
         }
-        off += rc[k];
     }
-    // foreground pixel count of the frame
 #pragma unroll
     for (int o = 16; o; o >>= 1) fgpx += __shfl_xor_sync(0xffffffffu, fgpx, o);
-    if (lane == 0) S.warp_tmp2[wid] = fgpx;
+    if (lane == 0) S.warp_fg[wid] = fgpx;
+    stamp();  // 2
     __syncthreads();
 
-    stamp();
     // ---- phase 2: unions --------------------------------------------------------------------------------------------------
-    // Hooking all the runs of a long vertical line at once would leave a linked list as long as the line, and the first
-    // find down that list costs one dependent shared-memory access per row.  So the forest is built in three steps:
+    // Hooking all the runs of a long vertical line at once would leave a linked list as long as the line.  So the forest is
+    // built in three steps:
     //   (a) every node points at its smallest "previous" neighbour (leftmost overlapping run of the row above, else the
     //       run ending the word to the left); previous neighbours always have smaller ids, so these pointers form trees
     //       whose roots are the trees' minimum ids;
-    //   (b) pointer jumping (parent <- grandparent until stable, all nodes concurrently) collapses every chain of length n
-    //       in O(log n) rounds;
+    //   (b) pointer jumping collapses every chain of length n in O(log n) rounds;
     //   (c) the remaining edges (further overlapping runs above, the left neighbour when an upper one was chosen) are
     //       ordinary unions by minimum between the now depth-1 trees.
-    uint32_t up_e[kEPT];
-#pragma unroll
-    for (int k = 0; k < kEPT; k++) {
-        const uint32_t e = tid + k * kFT;  // cyclic assignment
-        up_e[k] = 0xffffffffu;
-        if (e < nw) {
-            const uint32_t i = S.widx[e], m = S.wbits[e];
-            const uint32_t base = S.woff[e];
-            uint32_t up = 0, ustarts = 0, ubase = 0;
-            if (i >= (uint32_t)WW) {  // look the word above up (entries are sorted by word index)
-                const uint32_t target = i - WW;
-                uint32_t lo = 0, hi = e;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (S.widx[mid] < target)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                if (lo < e && S.widx[lo] == target && (S.wbits[lo] & m)) {
-                    up_e[k] = lo;
-                    up = S.wbits[lo];
-                    ustarts = up & ~(up << 1);
-                    ubase = S.woff[lo];
-                }
+    for (uint32_t e = tid; e < nw; e += kFT) {
+        const uint32_t i = S.widx[e], m = S.wbits[e];
+        const uint32_t base = S.woff[e];
+        uint32_t up = 0, ustarts = 0, ubase = 0, upe = 0xffffu;
+        if (i >= (uint32_t)WW) {
+            // the word above, if present, is at most WW - 1 entries back (entries are sorted by word index)
+            const uint32_t target = i - WW;
+            uint32_t lo = e > (uint32_t)WW ? e - WW : 0u, hi = e;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.widx[mid] < target)
+                    lo = mid + 1;
+                else
+                    hi = mid;
             }
-            const bool left_touch = (m & 1u) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 && (S.wbits[e - 1] >> 31);
-            uint32_t rest = m, v = base;
-            while (rest) {
-                const int bit = __ffs(rest) - 1;
-                const uint32_t shifted = ~(rest >> bit);
-                const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
-                const uint32_t runmask = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bit;
-                rest &= ~runmask;
-                const uint32_t o = runmask & up;
-                uint32_t p = v;
-                if (o)
-                    p = ubase + run_index(ustarts, __ffs(o) - 1);  // leftmost overlapping run above: smallest id
-                else if (bit == 0 && left_touch)
-                    p = base - 1;
-                S.parent[v] = p;
-                v++;
+            if (lo < e && S.widx[lo] == target && (S.wbits[lo] & m)) {
+                upe = lo;
+                up = S.wbits[lo];
+                ustarts = up & ~(up << 1);
+                ubase = S.woff[lo];
             }
         }
-    }
-    __syncthreads();
-    {
-        volatile uint32_t *vp = S.parent;
-        for (uint32_t v = tid; v < nn; v += kFT) {
-            uint32_t p = vp[v];
-            while (true) {
-                const uint32_t gp = vp[p];
-                if (gp == p) break;
-                vp[v] = gp;
-                p = gp;
-            }
+        S.up[e] = (uint16_t)upe;
+        const bool left_touch = (m & 1u) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 && (S.wbits[e - 1] >> 31);
+        uint32_t rest = m, v = base;
+        while (rest) {
+            const int bit = __ffs(rest) - 1;
+            const uint32_t shifted = ~(rest >> bit);
+            const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
+            const uint32_t runmask = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bit;
+            rest &= ~runmask;
+            const uint32_t o = runmask & up;
+            uint32_t p = v;
+            if (o)
+                p = ubase + run_index(ustarts, __ffs(o) - 1);  // leftmost overlapping run above: smallest id
+            else if (bit == 0 && left_touch)
+                p = base - 1;
+            S.parent[v] = p;
+            v++;
         }
     }
+    stamp();  // 3
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kEPT; k++) {
-        const uint32_t e = tid + k * kFT;
-        if (e < nw) {
-            const uint32_t i = S.widx[e], m = S.wbits[e];
-            const uint32_t base = S.woff[e];
-            const uint32_t starts = m & ~(m << 1);
-            const bool left_touch = (m & 1u) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 && (S.wbits[e - 1] >> 31);
-            uint32_t o = 0;
-            if (up_e[k] != 0xffffffffu) {
-                const uint32_t up = S.wbits[up_e[k]];
-                const uint32_t ustarts = up & ~(up << 1), ubase = S.woff[up_e[k]];
-                o = m & up;
-                uint32_t os = o & ~(o << 1);  // one segment per (run here, run above) pair that touches
-                uint32_t seen = 0;            // runs of this word whose first segment (= step (a)'s choice) was passed
-                while (os) {
-                    const int bit = __ffs(os) - 1;
-                    os &= os - 1;
-                    const uint32_t ri = run_index(starts, bit);
-                    if (seen & (1u << ri))
-                        s_union(S.parent, base + ri, ubase + run_index(ustarts, bit));
-                    seen |= 1u << ri;
-                }
-            }
-            if (left_touch && (o & (((m ^ (m + 1u)) & m))))  // first run starts at bit 0 and also touches a run above
-                s_union(S.parent, base, base - 1);
+    pointer_jump(S.parent, nn, tid);
+    stamp();  // 4
+    __syncthreads();
+    for (uint32_t e = tid; e < nw; e += kFT) {
+        const uint32_t upe = S.up[e];
+        const uint32_t m = S.wbits[e];
+        if (upe == 0xffffu) continue;  // no overlap above: step (a) already used the only edge (the left neighbour)
+        const uint32_t i = S.widx[e];
+        const uint32_t base = S.woff[e];
+        const uint32_t starts = m & ~(m << 1);
+        const uint32_t up = S.wbits[upe];
+        const uint32_t ustarts = up & ~(up << 1), ubase = S.woff[upe];
+        const uint32_t o = m & up;
+        uint32_t os = o & ~(o << 1);  // one segment per (run here, run above) pair that touches
+        uint32_t seen = 0;            // runs of this word whose first segment (= step (a)'s choice) was passed
+        while (os) {
+            const int bit = __ffs(os) - 1;
+            os &= os - 1;
+            const uint32_t ri = run_index(starts, bit);
+            if (seen & (1u << ri)) s_union(S.parent, base + ri, ubase + run_index(ustarts, bit));
+            seen |= 1u << ri;
         }
+        // first run starts at bit 0, touches a run above (chosen in (a)) and also the run ending the word to the left
+        if ((m & 1u) && (o & ((m ^ (m + 1u)) & m)) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 &&
+            (S.wbits[e - 1] >> 31))
+            s_union(S.parent, base, base - 1);
     }
+    stamp();  // 5
     __syncthreads();
-    stamp();  // end of the unions
 
-    stamp();
     // ---- phase 3: flatten, rank the roots ---------------------------------------------------------------------------------
-    // thread t owns nodes [kNPT*t, kNPT*(t+1))
-    // pointer jumping first: all nodes shorten their own path concurrently (parent <- grandparent until stable), which
-    // collapses a chain of length n in O(log n) rounds instead of n sequential hops per node
     {
         volatile uint32_t *vp = S.parent;
         for (uint32_t v = tid; v < nn; v += kFT) {
-            uint32_t p = vp[v];
-            while (true) {
-                const uint32_t gp = vp[p];
-                if (gp == p) break;
-                vp[v] = gp;
-                p = gp;
-            }
+            const uint32_t r = s_find(vp, v);
+            vp[v] = r;  // concurrent readers see either the old ancestor or the root: both are valid ancestors
         }
     }
     __syncthreads();
-    uint32_t isroot = 0;
-#pragma unroll
-    for (int k = 0; k < kNPT; k++) {
-        const uint32_t v = kNPT * tid + k;
-        if (v < nn) {
-            const uint32_t r = s_find(S.parent, v);
-            S.nroot[v] = r;
-            isroot |= (r == v ? 1u : 0u) << k;
-        }
-    }
+    // blocked partition: thread t owns nodes [t*npt, (t+1)*npt)
+    const uint32_t npt = (nn + kFT - 1) / kFT;
+    const uint32_t v0 = min((uint32_t)tid * npt, nn), v1 = min(v0 + npt, nn);
+    uint32_t nroots = 0;
+    for (uint32_t v = v0; v < v1; v++) nroots += S.parent[v] == v ? 1u : 0u;
     uint32_t ncomp = 0;
-    uint32_t rk = block_exclusive_scan(__popc(isroot), S.warp_tmp, &ncomp);  // syncs: all finds done before parent is reused
-#pragma unroll
-    for (int k = 0; k < kNPT; k++) {
-        const uint32_t v = kNPT * tid + k;
-        if (v < nn) {
-            S.parent[v] = rk;  // rank of the root at v (only meaningful where v is a root)
-            rk += (isroot >> k) & 1u;
-        }
-    }
+    uint32_t rk = block_exclusive_scan(nroots, S.warp_tmp, &ncomp);
     if (ncomp > (uint32_t)kCapB || ncomp > (uint32_t)b.blob_cap) {  // block-uniform
         if (tid == 0) b.frame_flags[f] = 1u;
         return;
     }
+    for (uint32_t v = v0; v < v1; v++)
+        if (S.parent[v] == v) S.rnk[v] = (uint16_t)rk++;
     for (uint32_t k = tid; k < ncomp; k += kFT) {
         S.b_area[k] = 0;
         S.b_sy[k] = 0;
@@ -404,15 +343,15 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         S.b_xmin[k] = 0xffffffffu;
         S.b_xmax[k] = 0;
     }
+    stamp();  // 6
     __syncthreads();
 
-    stamp();
     // ---- phase 4: labels + statistics, one node (run) per thread-iteration ----------------------------------------------
     int32_t *L = b.labels + (size_t)f * H * W;
     for (uint32_t v = tid; v < nn; v += kFT) {
         const uint32_t px = S.node_px[v], len = S.node_len[v];
-        const uint32_t root = S.nroot[v];
-        const uint32_t rank = S.parent[root];
+        const uint32_t root = S.parent[v];
+        const uint32_t rank = S.rnk[root];
         const uint32_t y = px / W, xs = px - y * W, xe = xs + len - 1;
         atomicAdd(&S.b_area[rank], len);
         atomicAdd(&S.b_sy[rank], y * len);
@@ -424,10 +363,9 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         int32_t *dst = L + px;
         for (uint32_t k = 0; k < len; k++) dst[k] = (int32_t)rank + 1;
     }
-    stamp();  // end of this warp's label/statistics work
+    stamp();  // 7
     __syncthreads();
 
-    stamp();
     // ---- phase 5: blob table -> global, scoring, ordered compaction, result ----------------------------------------------------
     hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;
     hv_defect *out = b.defects + (size_t)f * b.defect_cap;
@@ -450,19 +388,22 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
             sc = score_blob(b, sp, f, k, q);
         }
         uint32_t total = 0;
-        const uint32_t pos = nd_base + block_exclusive_scan(sc.keep ? 1u : 0u, S.warp_tmp, &total);
+        const uint32_t dpos = nd_base + block_exclusive_scan(sc.keep ? 1u : 0u, S.warp_tmp, &total);
+        uint32_t a = sc.keep ? (uint32_t)sc.d.size : 0u;
         if (sc.keep) {
-            if (pos < (uint32_t)b.defect_cap) out[pos] = sc.d;
-            atomicAdd(&S.area_sum, (unsigned long long)sc.d.size);
-            atomicAdd(&S.hist[area_bin((uint32_t)sc.d.size)], 1u);
+            if (dpos < (uint32_t)b.defect_cap) out[dpos] = sc.d;
+            atomicAdd(&S.hist[area_bin(a)], 1u);
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && a) atomicAdd(&S.area_sum, a);
         nd_base += total;
     }
+    stamp();  // 8
     __syncthreads();
-    stamp();
     if (tid == 0) {
         uint32_t fg = 0;
-        for (int w = 0; w < kNW; w++) fg += S.warp_tmp2[w];
+        for (int w = 0; w < kNW; w++) fg += S.warp_fg[w];
         const uint32_t nd = nd_base;
         const bool overflow = nd > (uint32_t)b.defect_cap;
         hv_frame_result r;
@@ -481,12 +422,17 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         atomicAdd(st + 1, (unsigned long long)r.rejected);
         atomicAdd(st + 2, (unsigned long long)nd);
         atomicAdd(st + 3, (unsigned long long)ncomp);
-        atomicAdd(st + 4, S.area_sum);
+        atomicAdd(st + 4, (unsigned long long)S.area_sum);
         atomicAdd(st + 5, (unsigned long long)fg);
         if (overflow) atomicAdd(st + 6 + HV_STATS_AREA_BINS, 1ull);
     }
     if (tid < HV_STATS_AREA_BINS && S.hist[tid])
         atomicAdd(reinterpret_cast<unsigned long long *>(b.stats) + 6 + tid, (unsigned long long)S.hist[tid]);
+    if (b.phase_ns && tid == 0 && f < 40) {  // debug: duration of this frame's CTA and its problem size
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        b.phase_ns[208 + f] = ((t - t_start) << 32) | ((unsigned long long)nw << 16) | (unsigned long long)ncomp;
+    }
 }
 
 }  // namespace

@@ -36,6 +36,65 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // exact floor(s / 25) for s <= 6375
 __device__ __forceinline__ uint32_t div25(uint32_t s) { return (s * 5243u) >> 17; }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Barriers of the tile pipeline.  NAMED = false: the whole CTA (__syncthreads).  NAMED = true: the 256 consumer threads of
+// the warp-specialised TMA kernel only (named barrier 1), so that the producer warp never has to take part.
+template <bool NAMED>
+__device__ __forceinline__ void tile_sync() {
+    if (NAMED)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    else
+        __syncthreads();
+}
+template <bool NAMED>
+__device__ __forceinline__ bool tile_sync_or(uint32_t v) {
+    if (NAMED) {
+        uint32_t r;
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            "setp.ne.u32 p, %1, 0;\n"
+            "bar.red.or.pred q, 1, 256, p;\n"
+            "selp.u32 %0, 1, 0, q;\n"
+            "}\n"
+            : "=r"(r)
+            : "r"(v)
+            : "memory");
+        return r != 0;
+    }
+    return __syncthreads_or((int)v) != 0;
+}
+
 // Shared-memory plan of one tile (TW x TH outputs, 256 threads).  Column index i of s_g / s_bl is image column
 // x0 - 8 + i; row r of s_g is image row y0 - HALO + r; row r of s_v / s_bl / s_h11 is image row y0 - 5 + r.
 //   s_g   [GH][GW]  u8   gray tile + halo                                  (dead after the blur phase)
@@ -65,9 +124,9 @@ struct Tile {
 // ---- fast path, interior tiles only (every blur pixel is an interior pixel, every window has 121 pixels) ---------
 // Packed u16x2 arithmetic: sums of u8 never overflow a 16-bit lane (5x5: 6375, 11x11 of blur: 30855), so plain 32-bit
 // adds/subs act on both lanes at once; VIMNMX.U16x2 gives the lane-wise compare for the threshold test.
-template <int TW, int TH, int HXP>
+template <int TW, int TH, int HXP, bool NAMED>
 __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid,
-                                              int cth) {
+                                              int cth, uint64_t *empty_bar) {
     using T = Tile<TW, TH, 2, HXP>;
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
     uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);  // may alias s_g: only written after s_g is dead
@@ -101,7 +160,8 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
             hi[(k + 4) % 5] = nhi;
         }
     }
-    __syncthreads();
+    tile_sync<NAMED>();
+    if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // the gray stage is dead: the producer may refill it
     // B. horizontal 5-sums + /25 -> s_bl.  thread = (row, group of 36 columns) -> 42 x 4 = 168 threads.
     //    s_v stores column i at index i + 4, so the window i-2..i+2 of output i is s_v[i+2 .. i+6]; a group needs
     //    s_v[36g + 2 .. 36g + 42), loaded as 11 aligned 8-byte words starting at 36g.
@@ -132,7 +192,7 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
             brow[j4] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
         }
     }
-    __syncthreads();
+    tile_sync<NAMED>();
     // C. horizontal 11-sums of the blur.  thread = (row, group of 32 output columns) -> 42 x 4 = 168 threads.
     //    output column c uses s_bl[c + 3 .. c + 13]; a group needs bytes 32g + 3 .. 32g + 44 = words 8g .. 8g + 11.
     if (tid < 42 * 4) {
@@ -156,7 +216,7 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
             s -= by(2 * c2 + 4);
         }
     }
-    __syncthreads();
+    tile_sync<NAMED>();
     // D. vertical 11-sums + threshold test.  thread = (column quad, segment of 8 rows) -> 32 x 4 = 128 threads.
     //    fg  <=>  (px + c + 1) * 121 <= S  <=>  S + 1 > px * 121 + (c + 1) * 121      (all lanes < 65536 for 0 <= c <= 255)
     if (tid < 32 * 4) {
@@ -189,15 +249,16 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
             rh[(k + 10) % 11] = t.y;
         }
     }
-    __syncthreads();
+    tile_sync<NAMED>();
 }
 
 // Everything after the gray tile (+ halo, zero outside the image) sits in shared memory and the flat decision is known:
 // blur + threshold (fast or generic path) and the three outputs.  Block-uniform control flow; contains barriers.
-template <int TW, int TH, int RB, int HXP>
+template <int TW, int TH, int RB, int HXP, bool NAMED>
 __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out,
                                                        uint8_t *g_raw, uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw,
-                                                       int f, int tile_x, int x0, int y0, bool flat, int tid) {
+                                                       int f, int tile_x, int x0, int y0, bool flat, int tid,
+                                                       uint64_t *empty_bar) {
     using T = Tile<TW, TH, RB, HXP>;
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
     uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);
@@ -211,10 +272,11 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
     // interior tile: the blur ring (tile +- 5) lies >= RB pixels inside the image, so no border rule applies anywhere
     const bool interior = x0 >= T::HALO && y0 >= T::HALO && x0 + TW + T::HALO <= W && y0 + TH + T::HALO <= H;
 
+    if (flat && empty_bar && tid == 0) mbar_arrive(empty_bar);  // every thread is past its flat-test reads of the stage
     if (!flat) {
         if (RB == 2 && TW == 128 && TH == 32 && interior && p.inverse && !p.write_blur && cth >= 0 && cth <= 255 &&
             !p.force_generic) {
-            fast_tile_rb2<128, 32, HXP>(g_raw, f_raw, u1_raw, bl_raw, tid, cth);
+            fast_tile_rb2<128, 32, HXP, NAMED>(g_raw, f_raw, u1_raw, bl_raw, tid, cth, empty_bar);
         } else {
             // ---- generic path: any border, any c, either comparison direction --------------------------------------
             // 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior)
@@ -239,7 +301,8 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
                 }
                 s_bl[r][i] = (uint8_t)v;
             }
-            __syncthreads();
+            tile_sync<NAMED>();
+            if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // last read of the gray stage is behind us
             // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
             for (int idx = tid; idx < T::BH * TW; idx += 256) {
                 const int r = idx / TW, c = idx - r * TW;
@@ -248,7 +311,7 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
                 for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][c + (8 - kAdaptHalf) + k];
                 s_h11[r][c] = (uint16_t)s;
             }
-            __syncthreads();
+            tile_sync<NAMED>();
             // 4. vertical 11-sums + threshold test (window truncated at the image border: cnt = rows * cols)
             for (int idx = tid; idx < TH * TW; idx += 256) {
                 const int r = idx / TW, c = idx - r * TW;
@@ -267,7 +330,7 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
                 }
                 s_f[r][c] = fg;
             }
-            __syncthreads();
+            tile_sync<NAMED>();
         }
     }
 
@@ -276,17 +339,18 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         // flat tile fully inside a 16-px aligned image: nothing but wide zero stores (one warp writes one 512-byte
         // label row per instruction)
         const int4 z = make_int4(0, 0, 0, 0);
+        const size_t o0 = (size_t)f * H * W + (size_t)y0 * W + x0;
         if (p.init_labels) {
+            int4 *dst = reinterpret_cast<int4 *>(b.labels + o0 + (size_t)(tid >> 5) * W) + (tid & 31);
+            const size_t step = (size_t)2 * W;  // 8 rows of W int32 = 2*W int4
 #pragma unroll
-            for (int r = tid >> 5; r < TH; r += 8)
-                *reinterpret_cast<int4 *>(labels + (size_t)(y0 + r) * W + x0 + 4 * (tid & 31)) = z;
+            for (int k = 0; k < TH / 8; k++) dst[k * step] = z;
         }
         if (p.write_mask) {
-            for (int idx = tid; idx < TH * (TW / 16); idx += 256) {
-                const int r = idx / (TW / 16), c16 = idx - r * (TW / 16);
-                *reinterpret_cast<int4 *>(mask + (size_t)(y0 + r) * W + x0 + 16 * c16) = z;
-            }
+            static_assert(TH * (TW / 16) == 256, "one 16-pixel group per thread");
+            *reinterpret_cast<int4 *>(b.mask + o0 + (size_t)(tid >> 3) * W + 16 * (tid & 7)) = z;
         }
+        if (p.static_sched & 2) return;  // EXPERIMENT: skip aux outputs of flat tiles
         if (tid < TH * (TW / 32)) {
             const int r = tid / (TW / 32), wq = tid - r * (TW / 32);
             bits_out[((size_t)f * H + y0 + r) * b.ww + (x0 >> 5) + wq] = 0u;
@@ -459,8 +523,8 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
     // barrier (s_g complete) + block-wide OR in one instruction
     const bool flat = !__syncthreads_or((int)(acc & 0x80808080u)) && try_flat;
     // s_f aliases s_g (dead by the time the mask bytes are written)
-    tile_compute_and_store<TW, TH, RB, 8>(b, p, bits_out, smem, smem, smem + T::G_BYTES, smem + T::G_BYTES + T::U1_BYTES, f,
-                                       blockIdx.x, x0, y0, flat, tid);
+    tile_compute_and_store<TW, TH, RB, 8, false>(b, p, bits_out, smem, smem, smem + T::G_BYTES,
+                                                 smem + T::G_BYTES + T::U1_BYTES, f, blockIdx.x, x0, y0, flat, tid, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -470,34 +534,6 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
 // from an atomic counter and the TMA unit loads tile k+1 (zero-filling outside the image) while the threads test, compute
 // and store tile k; no thread ever issues a global load for pixels.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
 constexpr int kTmaStages = 4;  // tiles in flight per CTA: the load of tile k+3 is issued before tile k is processed
 
 template <int TW, int TH>
@@ -507,91 +543,130 @@ struct TmaSmem {
     static constexpr int BYTES = kTmaStages * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
 };
 
+constexpr int kK1Consumers = 256;              // threads that test, compute and store tiles
+constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler + TMA issue)
+
+// Warp-specialised: warp 8 is the producer (one elected lane takes tile numbers from the scheduler and issues the TMA
+// loads, running up to kTmaStages tiles ahead), warps 0..7 are the consumers.  In the first TMA version thread 0 did the
+// refill between two tiles: the TMA issue sits behind that thread's own outstanding global stores, and every barrier of
+// the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
+// producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
 template <int TW, int TH>
-__global__ void __launch_bounds__(256, 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, BatchView b,
-                                                           PreprocessParams p, uint32_t *bits_out, unsigned int *sched) {
+__global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, BatchView b,
+                                                                  PreprocessParams p, uint32_t *bits_out,
+                                                                  unsigned int *sched) {
     using T = typename TmaSmem<TW, TH>::T;
     constexpr int STAGE = TmaSmem<TW, TH>::STAGE;
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t bar[kTmaStages];
-    __shared__ int s_tile[kTmaStages];
+    __shared__ __align__(8) uint64_t full[kTmaStages], empty[kTmaStages];
+    __shared__ int4 s_tile[kTmaStages];  // {tile number, frame, tile x, tile y}, decoded once by the producer
     uint8_t *f_raw = sm + kTmaStages * STAGE, *u1_raw = f_raw + TH * TW, *bl_raw = u1_raw + T::U1_BYTES;
 
     const int tid = threadIdx.x;
     const int H = b.h, W = b.w;
     const int tiles_x = b.tiles_x, tiles_y = (H + TH - 1) / TH;
     const int per_frame = tiles_x * tiles_y, total = per_frame * b.n;
+    unsigned long long t_cta0 = 0;
+    if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
+
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kTmaStages; k++) {
+            mbar_init(&full[k], 1);
+            mbar_init(&empty[k], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kK1Consumers) {
+        // ---- producer warp ---------------------------------------------------------------------------------------------
+        if (tid != kK1Consumers) return;
+        // dynamic schedule: the number handed out now was requested one fetch earlier, so the round trip of the atomic
+        // overlaps the previous issue; static schedule (kernel launched alone, HV_K1_DYNAMIC unset): round robin
+        int pending = (p.static_sched & 1) ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
+        for (int it = 0;; it++) {
+            const int st = it % kTmaStages;
+            if (it >= kTmaStages) mbar_wait(&empty[st], (uint32_t)(it / kTmaStages - 1) & 1u);
+            const int t = pending;
+            pending = (p.static_sched & 1) ? pending + (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            const int f = t / per_frame, r = t - f * per_frame;
+            const int ty = r / tiles_x, tx = r - ty * tiles_x;
+            s_tile[st] = make_int4(t, f, tx, ty);  // published by the arrive below (release) / the consumers' wait (acquire)
+            if (t >= total) {
+                mbar_arrive(&full[st]);  // end marker: tile numbers only grow, nothing is left for this CTA
+                break;
+            }
+            mbar_expect_tx(&full[st], (uint32_t)T::G_BYTES);
+            tma_load_3d(sm + st * STAGE, &tmap, &full[st], tx * TW - T::HX, ty * TH - T::HALO, f);
+        }
+        // the last CTA to finish fetching rearms the scheduler for the next launch
+        if (!(p.static_sched & 1)) {
+            __threadfence();
+            const unsigned int d = atomicAdd(sched + 1, 1u);
+            if (d == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+        return;
+    }
+
+    // ---- consumers -----------------------------------------------------------------------------------------------------
     const int cth = p.c_thresh;
     const bool try_flat = p.inverse && !p.write_blur && !p.force_generic && cth >= 0;
     const uint32_t kq = 0x01010101u * (uint32_t)(127 - min(cth >> 1, 127));
-
-    // thread 0 only: take the next tile from the scheduler and start its TMA load into stage st
-    int next_static = blockIdx.x;  // thread 0: static round-robin schedule (HV_K1_STATIC) instead of the atomic counter
-    auto fetch_and_issue = [&](int st) {
-        int t;
-        if (p.static_sched) {
-            t = next_static;
-            next_static += gridDim.x;
-        } else {
-            t = (int)atomicAdd(sched, 1u);
-        }
-        s_tile[st] = t;
-        if (t < total) {
-            const int f = t / per_frame, r = t - f * per_frame;
-            const int ty = r / tiles_x, tx = r - ty * tiles_x;
-            mbar_expect_tx(&bar[st], (uint32_t)T::G_BYTES);
-            tma_load_3d(sm + st * STAGE, &tmap, &bar[st], tx * TW - T::HX, ty * TH - T::HALO, f);
-        }
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int k = 0; k < kTmaStages; k++) mbar_init(&bar[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < kTmaStages; k++) fetch_and_issue(k);
-    }
-    __syncthreads();
     for (int it = 0;; it++) {
         const int st = it % kTmaStages;
-        const int cur = s_tile[st];
-        if (cur >= total) break;  // tile numbers only grow: nothing is left for this CTA
-        const int f = cur / per_frame, rr = cur - f * per_frame;
-        const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
-        const int x0 = tx * TW, y0 = ty * TH;
         unsigned long long t_a = 0, t_b = 0;
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
-        mbar_wait(&bar[st], (uint32_t)(it / kTmaStages) & 1u);
+        mbar_wait(&full[st], (uint32_t)(it / kTmaStages) & 1u);
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
+        const int4 cur = s_tile[st];
+        if (cur.x >= total) break;
+        const int f = cur.y, tx = cur.z, ty = cur.w;
+        const int x0 = tx * TW, y0 = ty * TH;
 
         // flatness test straight from shared memory, over the in-image part of the tile + halo
         uint8_t *cur_stage = sm + st * STAGE;
         uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
         uint32_t acc = 0;
         if (try_flat) {
-            // logical columns [GOFF, GOFF + 144) = image x0-8 .. x0+135, clipped to the image (word-aligned: w % 16 == 0)
+            // 16-byte items (row, 16 columns) over the staged box; the image is 16-px aligned, so an item lies entirely
+            // inside or outside of it (outside = zero fill, must not be tested).  Only the logical columns
+            // [GOFF, GOFF + BW) = image x0-8 .. x0+135 matter: the outer halves of the first and last item are ignored.
+            static_assert(T::GW % 16 == 0 && T::GOFF == 8 && T::GOFF + T::BW == T::GW - 8, "flat-test item layout");
+            constexpr int IPR = T::GW / 16;  // items per row
             const int r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
-            const int c_lo = max(T::GOFF, T::HX - x0), c_hi = min(T::GOFF + T::BW, W - x0 + T::HX);
-            const uint32_t ref4 = 0x01010101u * s_g[min(T::HALO + TH / 2, r_hi - 1)][min(T::HX + TW / 2, c_hi - 1)];
-            auto flat_test = [&](uint32_t v) {
-                const uint32_t d = __vabsdiffu4(v, ref4);
-                acc |= d | ((d & 0x7f7f7f7fu) + kq);
-            };
-            // 8-byte items (row, 8 columns); c_lo / c_hi are multiples of 8, so an item is entirely inside or outside
-            constexpr int NV = T::GH * (T::BW / 8);
+            const int j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
+            const uint32_t ref4 =
+                0x01010101u * s_g[min(T::HALO + TH / 2, r_hi - 1)][min(T::HX + TW / 2, 16 * j_hi - 1)];
+            constexpr int NV = T::GH * IPR;
 #pragma unroll
-            for (int k = 0; k < (NV + 255) / 256; k++) {
-                const int idx = tid + 256 * k;
-                const int r = idx / (T::BW / 8), c = T::GOFF + 8 * (idx - r * (T::BW / 8));
-                if (idx < NV && r >= r_lo && r < r_hi && c >= c_lo && c < c_hi) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(&s_g[r][c]);
-                    flat_test(v.x);
-                    flat_test(v.y);
+            for (int k = 0; k < (NV + kK1Consumers - 1) / kK1Consumers; k++) {
+                const int idx = tid + kK1Consumers * k;
+                const int r = idx / IPR, j = idx - r * IPR;
+                if (idx < NV && r >= r_lo && r < r_hi && j >= j_lo && j < j_hi) {
+                    uint4 v = *reinterpret_cast<const uint4 *>(&s_g[r][16 * j]);
+                    if (j == 0) v.x = ref4, v.y = ref4;
+                    if (j == IPR - 1) v.z = ref4, v.w = ref4;
+                    uint32_t d = __vabsdiffu4(v.x, ref4);
+                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
+                    d = __vabsdiffu4(v.y, ref4);
+                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
+                    d = __vabsdiffu4(v.z, ref4);
+                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
+                    d = __vabsdiffu4(v.w, ref4);
+                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
                 }
             }
         }
-        const bool flat = !__syncthreads_or((int)(acc & 0x80808080u)) && try_flat;
-        tile_compute_and_store<TW, TH, 2, 16>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat, tid);
-        __syncthreads();  // every read of this stage and of the scratch tiles is done: the stage can be refilled
+        // barrier + block-wide OR in one instruction.  No barrier closes the tile: the scratch tiles of tile k are last
+        // read before (u1, bl) or during (f) its output stage, and tile k+1 first writes them behind at least one
+        // barrier that every consumer reaches only after it has finished tile k.
+        const bool flat = !tile_sync_or<true>(acc & 0x80808080u) && try_flat;
+        tile_compute_and_store<TW, TH, 2, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat, tid,
+                                                    &empty[st]);
         if (b.phase_ns && tid == 0) {  // debug: time per tile split into TMA wait and processing, flat vs non-flat
             unsigned long long t_c;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
@@ -599,16 +674,16 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_tma(const __grid_constant
             atomicAdd(b.phase_ns + 201 + (flat ? 0 : 3), t_c - t_b);
             atomicAdd(b.phase_ns + 202 + (flat ? 0 : 3), 1ull);
         }
-        if (tid == 0) fetch_and_issue(st);
     }
-    // the last CTA to leave rearms the scheduler for the next launch (every CTA has made its final fetch by then)
-    if (tid == 0 && !p.static_sched) {
-        __threadfence();
-        const unsigned int d = atomicAdd(sched + 1, 1u);
-        if (d == gridDim.x - 1) {
-            sched[0] = 0;
-            sched[1] = 0;
-        }
+    if (b.phase_ns && tid == 0) {  // debug: CTA lifetimes
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        atomicMin(b.phase_ns + 248, t_cta0);
+        atomicMax(b.phase_ns + 249, t_end);
+        atomicAdd(b.phase_ns + 250, t_end - t_cta0);
+        atomicMax(b.phase_ns + 251, t_end - t_cta0);
+        atomicMin(b.phase_ns + 252, t_end);
+        atomicMax(b.phase_ns + 253, t_cta0);
     }
 }
 
@@ -721,7 +796,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(kK1Threads);
     cfg.dynamicSmemBytes = TmaSmem<128, 32>::BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
