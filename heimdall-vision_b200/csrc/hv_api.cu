@@ -70,6 +70,7 @@ struct Slot {
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags, sched;
     PinBuf<uint32_t> h_flags;
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
+    bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
     DevBuf<int32_t> labels;
     DevBuf<hv_blob> blobs;
@@ -276,7 +277,7 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     if (need_gauss) HV_TRY_CUDA(ctx, s.gauss_tmp.reserve(px));
     if (need_mask) HV_TRY_CUDA(ctx, s.mask.reserve(px));
     if (need_labels) HV_TRY_CUDA(ctx, s.labels.reserve(px));
-    HV_TRY_CUDA(ctx, s.rowflags.reserve((size_t)n * (((size_t)h * ((w + 127) / 128) + 15) & ~(size_t)15)));
+    HV_TRY_CUDA(ctx, s.rowflags.reserve((size_t)n * ((h + 31) / 32) * ((w + 127) / 128) * 32));
     HV_TRY_CUDA(ctx, s.bits.reserve(words));
     HV_TRY_CUDA(ctx, s.bits_tmp.reserve(words));
     HV_TRY_CUDA(ctx, s.rootbits.reserve(words));
@@ -368,7 +369,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.bits_tmp = s.bits_tmp.p;
     b.rowflags = s.rowflags.p;
     b.tiles_x = (w + 127) / 128;
-    b.rf_stride = ((size_t)h * b.tiles_x + 15) & ~(size_t)15;
+    b.rf_stride = (size_t)((h + 31) / 32) * b.tiles_x * 32;
     b.labels = d_labels ? d_labels : s.labels.p;
     b.rootbits = s.rootbits.p;
     b.rankbase = s.rankbase.p;
@@ -391,7 +392,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         b.phase_frame = pf ? atoi(pf) : 0;
     }
 
+    // CCL path of this batch (decided before K1 runs: the fused kernel lets K1 skip the all-zero bit-mask words)
+    bool fused = !(ctx->cfg.flags & HV_FLAG_GLOBAL_CCL) && ccl_frame_supported(b);
+    if (fused && ctx->dense_hint) {
+        ctx->dense_batches++;
+        if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
+    }
     PreprocessParams pp{};
+    pp.sparse_aux = (fused && !morph) ? 1 : 0;
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
@@ -434,7 +442,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
         pp.static_sched = (pdl || getenv("HV_K1_DYNAMIC")) ? 0 : 1;
-        if (getenv("HV_K1_SKIP_AUX")) pp.static_sched |= 2;
+        if (getenv("HV_K1_DEBUG_SKIP")) pp.static_sched |= atoi(getenv("HV_K1_DEBUG_SKIP")) & ~1;
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
@@ -449,11 +457,6 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ctx->launches += nl + 2;
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
-    bool fused = !(ctx->cfg.flags & HV_FLAG_GLOBAL_CCL) && ccl_frame_supported(b);
-    if (fused && ctx->dense_hint) {
-        ctx->dense_batches++;
-        if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
-    }
     if (fused) {
         ProfScope ps(ctx, HV_K_CCL_FRAME, st);
         HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, st));
@@ -463,6 +466,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         if (rg != HV_OK) return rg;
     }
     s.used_fused = fused;
+    s.sparse_bits = pp.sparse_aux != 0;
     s.score = sp;
     ctx->last_valid = true;
     ctx->last_stream = st;
@@ -499,6 +503,11 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     }
     BatchView b = s.view;
     b.frame_select = b.frame_flags;
+    if (s.sparse_bits) {
+        HV_TRY_CUDA(ctx, launch_densify_bits(b, st));
+        ctx->launches++;
+        s.sparse_bits = false;  // (for the selected frames, which are the only ones anybody reads from now on)
+    }
     hv_status rs = enqueue_global_ccl(ctx, b, s.score, st);
     if (rs != HV_OK) return rs;
     s.used_fused = false;

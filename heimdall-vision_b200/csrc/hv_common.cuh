@@ -22,9 +22,10 @@ struct BatchView {
     uint8_t *mask;             // n*h*w  final mask {0,255}
     uint32_t *bits;            // n*h*ww bit-packed final mask, bit x&31 of word x>>5
     uint32_t *bits_tmp;        // scratch for morphology
-    uint8_t *rowflags;         // n * rf_stride: per (row, 128-px tile) nibble, bit k = word 4*tile+k of that row is non-zero
+    uint8_t *rowflags;         // n * rf_stride: one byte per (row, 128-px tile): bit k = word 4*tile+k of that row is non-zero;
+                               // tile-major: byte (y & 31) of the 32-byte record of tile (y >> 5, tx), see rowflag_index()
     int tiles_x;               // ceil(w / 128)
-    size_t rf_stride;          // bytes per frame in rowflags (h * tiles_x rounded up to 16)
+    size_t rf_stride;          // bytes per frame in rowflags: ceil(h / 32) * tiles_x * 32
     int32_t *labels;           // n*h*w  union-find parents (+1) during CCL, canonical labels afterwards
     uint32_t *rootbits;        // n*h*ww
     uint32_t *rankbase;        // n*h*ww root counts -> exclusive prefix
@@ -51,7 +52,14 @@ struct PreprocessParams {
     int inverse;       // 1: 255 if px < mean - c (detection path); 0: 255 if px > mean - c
     int force_generic; // testing: never take the packed fast path
     int static_sched;  // TMA kernel: static round-robin tile schedule instead of the atomic tile counter
+    int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which
+                       // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)
 };
+
+// byte offset of the occupancy record of (row y, tile tx) inside a frame's rowflags
+__host__ __device__ inline size_t rowflag_index(int y, int tx, int tiles_x) {
+    return ((size_t)(y >> 5) * tiles_x + tx) * 32 + (y & 31);
+}
 
 struct ScoreParams {
     double min_size, max_size, min_confidence;
@@ -71,6 +79,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
                                   int num_sms, bool pdl, cudaStream_t s, bool *used);
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
+cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
 cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);

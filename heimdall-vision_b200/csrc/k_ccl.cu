@@ -317,7 +317,30 @@ __global__ void __launch_bounds__(256) k_rowflags_from_bits(BatchView b) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (4 * tx + k < b.ww && row[4 * tx + k]) nib |= 1u << k;
-        b.rowflags[f * b.rf_stride + j] = (uint8_t)nib;
+        b.rowflags[f * b.rf_stride + rowflag_index(y, tx, b.tiles_x)] = (uint8_t)nib;
+    }
+}
+
+// After a K1 launch with sparse_aux the bit-mask words of flat tiles were left unwritten (their occupancy records are all
+// zero).  Zero them, so that the kernels that scan every word of the frame (global-memory CCL path) see a dense mask.
+// One warp per tile: lane = row of the tile.
+__global__ void __launch_bounds__(256) k_densify_bits(BatchView b) {
+    const int tiles_y = (b.h + 31) / 32;
+    const size_t per_frame = (size_t)tiles_y * b.tiles_x;
+    const size_t total = per_frame * b.n;
+    const int lane = threadIdx.x & 31;
+    for (size_t t = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; t < total; t += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const size_t f = t / per_frame;
+        if (b.frame_select && !b.frame_select[f]) continue;
+        const int j = (int)(t - f * per_frame);
+        const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
+        const int y = ty * 32 + lane;
+        const uint32_t fl = y < b.h ? b.rowflags[f * b.rf_stride + rowflag_index(y, tx, b.tiles_x)] : 0u;
+        if (__any_sync(0xffffffffu, fl != 0) || y >= b.h) continue;
+        uint32_t *row = b.bits + (f * b.h + y) * (size_t)b.ww;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (4 * tx + k < b.ww) row[4 * tx + k] = 0u;
     }
 }
 
@@ -350,6 +373,10 @@ cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s) {
 }
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s) {
     k_rowflags_from_bits<<<grid_for((size_t)b.n * b.h * b.tiles_x, 256), 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s) {
+    k_densify_bits<<<grid_for((size_t)b.n * ((b.h + 31) / 32) * b.tiles_x * 32, 256), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s) {

@@ -20,6 +20,8 @@
 // bodies, work split unevenly over the warps) spent 55 us per batch, 70 % of the warp samples waiting at barriers for
 // one straggling warp.  This version keeps the code small (runtime loops, one shared scan routine), gives every
 // thread an equal share of every phase, and has no dependent global-memory round trip that can be avoided.
+#include <cstddef>
+
 #include "hv_common.cuh"
 #include "score_device.cuh"
 
@@ -145,44 +147,62 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     stamp();  // 0
 
     // ---- phase 0: ordered compaction of the non-zero words ------------------------------------------------------------
-    // K1 left one occupancy nibble per (row, 128-px tile): bit k set <=> word 4*tile+k of that row is non-zero.  Items
-    // (row-major, tile-minor) are in raster order of their words, so thread t takes the contiguous items
-    // [t*ipt, (t+1)*ipt) and a block scan of the popcounts gives its first output slot.
+    // K1 left one occupancy byte per (row, 128-px tile), bit k set <=> word 4*tile+k of that row is non-zero, stored as
+    // 32-byte records per tile (tile-major, see rowflag_index).  The records of a band of 32 rows are contiguous, so
+    // whole bands are staged in shared memory with 16-byte loads (one round trip; the staging area is the still unused
+    // parent + node_px arrays), then thread t takes the contiguous rows [t*rpt, (t+1)*rpt) of the chunk and a block scan
+    // of the popcounts gives its first output slot.  Frames with more bands than fit are staged in several chunks.
+    static_assert(offsetof(FrameSmem, node_px) == offsetof(FrameSmem, parent) + sizeof(uint32_t) * kCapN, "staging area");
     const int TX = b.tiles_x;
-    const int nitems = H * TX;
+    const int nbands = (H + 31) / 32;
+    const int band_bytes = TX * 32;
     const uint8_t *rf = b.rowflags + (size_t)f * b.rf_stride;
-    const int ipt = (((nitems + kFT - 1) / kFT) + 3) & ~3;  // items per thread, multiple of 4 -> aligned 32-bit loads
-    const int it0 = min(tid * ipt, nitems), it1 = min(it0 + ipt, nitems);
-    uint32_t cnt = 0;
-#pragma unroll 4
-    for (int it = it0; it < it1; it += 4) {
-        uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(rf + it));
-        const int left = it1 - it;
-        if (left < 4) q &= (1u << (8 * left)) - 1u;
-        cnt += __popc(q & 0x0f0f0f0fu);
-    }
+    uint8_t *stage = reinterpret_cast<uint8_t *>(S.parent);
+    const int bands_per_chunk = min(nbands, (int)(2 * sizeof(uint32_t) * kCapN) / band_bytes);
     if (tid < HV_STATS_AREA_BINS) S.hist[tid] = 0;
     if (tid == 0) S.area_sum = 0;
     uint32_t nw = 0;
-    uint32_t pos = block_exclusive_scan(cnt, S.warp_tmp, &nw);
-    if (nw > (uint32_t)kCapW || H > 8192 || W > 8192) {  // block-uniform
-        if (tid == 0) b.frame_flags[f] = 1u;
-        return;
-    }
-    if (cnt) {  // index pass: the occupancy bytes come from L1 this time
-        for (int it = it0; it < it1; it += 4) {
-            uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(rf + it));
-            const int left = it1 - it;
-            if (left < 4) q &= (1u << (8 * left)) - 1u;
-            q &= 0x0f0f0f0fu;
-            while (q) {
-                const int bitpos = __ffs(q) - 1;  // byte = bitpos >> 3, word within the tile = bitpos & 7
-                q &= q - 1;
-                const int item = it + (bitpos >> 3);
-                const int y = item / TX, tx = item - y * TX;
-                S.widx[pos++] = (uint32_t)(y * WW + 4 * tx + (bitpos & 7));
+    bool too_big = H > 8192 || W > 8192 || bands_per_chunk < 1;
+    for (int b0 = 0; b0 < nbands && !too_big; b0 += bands_per_chunk) {
+        const int nb = min(bands_per_chunk, nbands - b0);
+        const int bytes = nb * band_bytes;  // multiple of 32
+        if (b0) __syncthreads();            // the previous chunk has been consumed
+        for (int i = tid * 16; i < bytes; i += kFT * 16)
+            *reinterpret_cast<uint4 *>(stage + i) =
+                __ldg(reinterpret_cast<const uint4 *>(rf + (size_t)b0 * band_bytes + i));
+        __syncthreads();
+        const int rows = min(nb * 32, H - b0 * 32);
+        const int rpt = (rows + kFT - 1) / kFT;
+        const int r0 = min(tid * rpt, rows), r1 = min(r0 + rpt, rows);
+        uint32_t cnt = 0;
+        for (int r = r0; r < r1; r++) {
+            const uint8_t *rec = stage + (r >> 5) * band_bytes + (r & 31);
+            for (int tx = 0; tx < TX; tx++) cnt += __popc(rec[tx * 32] & 0xfu);
+        }
+        uint32_t tot = 0;
+        uint32_t pos = nw + block_exclusive_scan(cnt, S.warp_tmp, &tot);
+        nw += tot;
+        if (nw > (uint32_t)kCapW) {  // block-uniform
+            too_big = true;
+            break;
+        }
+        if (cnt) {
+            for (int r = r0; r < r1; r++) {
+                const uint8_t *rec = stage + (r >> 5) * band_bytes + (r & 31);
+                const uint32_t wrow = (uint32_t)(b0 * 32 + r) * WW;
+                for (int tx = 0; tx < TX; tx++) {
+                    uint32_t q = rec[tx * 32] & 0xfu;
+                    while (q) {
+                        S.widx[pos++] = wrow + 4 * tx + (__ffs(q) - 1);
+                        q &= q - 1;
+                    }
+                }
             }
         }
+    }
+    if (too_big) {  // block-uniform
+        if (tid == 0) b.frame_flags[f] = 1u;
+        return;
     }
     stamp();  // 1
     __syncthreads();

@@ -340,22 +340,22 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         // label row per instruction)
         const int4 z = make_int4(0, 0, 0, 0);
         const size_t o0 = (size_t)f * H * W + (size_t)y0 * W + x0;
-        if (p.init_labels) {
+        if (p.init_labels && !(p.static_sched & 4)) {
             int4 *dst = reinterpret_cast<int4 *>(b.labels + o0 + (size_t)(tid >> 5) * W) + (tid & 31);
             const size_t step = (size_t)2 * W;  // 8 rows of W int32 = 2*W int4
 #pragma unroll
             for (int k = 0; k < TH / 8; k++) dst[k * step] = z;
         }
-        if (p.write_mask) {
+        if (p.write_mask && !(p.static_sched & 8)) {
             static_assert(TH * (TW / 16) == 256, "one 16-pixel group per thread");
             *reinterpret_cast<int4 *>(b.mask + o0 + (size_t)(tid >> 3) * W + 16 * (tid & 7)) = z;
         }
-        if (p.static_sched & 2) return;  // EXPERIMENT: skip aux outputs of flat tiles
         if (tid < TH * (TW / 32)) {
             const int r = tid / (TW / 32), wq = tid - r * (TW / 32);
             bits_out[((size_t)f * H + y0 + r) * b.ww + (x0 >> 5) + wq] = 0u;
         }
-        if (b.rowflags && tid < TH) b.rowflags[(size_t)f * b.rf_stride + (size_t)(y0 + tid) * b.tiles_x + tile_x] = 0;
+        if (b.rowflags && tid < TH && y0 + tid < H)
+            b.rowflags[(size_t)f * b.rf_stride + rowflag_index(y0 + tid, tile_x, b.tiles_x)] = 0;
         return;
     }
     if (x0 + TW <= W && (W & 15) == 0) {
@@ -435,7 +435,7 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         // occupancy nibble of this (row, tile): which of its 4 words are non-zero
         const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
         if (b.rowflags && wq == 0 && gy < H)
-            b.rowflags[(size_t)f * b.rf_stride + (size_t)gy * b.tiles_x + tile_x] =
+            b.rowflags[(size_t)f * b.rf_stride + rowflag_index(gy, tile_x, b.tiles_x)] =
                 (uint8_t)((bal >> (tid & 31)) & 0xfu);
     }
 }
@@ -592,10 +592,18 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
             pending = (p.static_sched & 1) ? pending + (int)gridDim.x : (int)atomicAdd(sched, 1u);
             const int f = t / per_frame, r = t - f * per_frame;
             const int ty = r / tiles_x, tx = r - ty * tiles_x;
-            s_tile[st] = make_int4(t, f, tx, ty);  // published by the arrive below (release) / the consumers' wait (acquire)
+            // bit 16 of .w: the whole staged box lies inside the image; bit 17: the whole tile lies inside the image
+            const int x0p = tx * TW, y0p = ty * TH;
+            const int fl = ((x0p >= T::HX && x0p + TW + T::HX <= W && y0p >= T::HALO && y0p + TH + T::HALO <= H) ? 0x10000 : 0) |
+                           ((x0p + TW <= W && y0p + TH <= H) ? 0x20000 : 0);
+            s_tile[st] = make_int4(t, f, tx, ty | fl);  // published by the arrive below (release) / the consumers' wait (acquire)
             if (t >= total) {
                 mbar_arrive(&full[st]);  // end marker: tile numbers only grow, nothing is left for this CTA
                 break;
+            }
+            if (p.static_sched & 32) {  // EXPERIMENT: no loads at all
+                mbar_arrive(&full[st]);
+                continue;
             }
             mbar_expect_tx(&full[st], (uint32_t)T::G_BYTES);
             tma_load_3d(sm + st * STAGE, &tmap, &full[st], tx * TW - T::HX, ty * TH - T::HALO, f);
@@ -613,9 +621,30 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
     }
 
     // ---- consumers -----------------------------------------------------------------------------------------------------
+    // Most tiles are flat and do nothing but test 7 KB of shared memory and store 20 KB of zeros, so the instruction count
+    // of that path is what the SMs' issue slots see (ncu, uniform frames: 2400 warp instructions per tile, IPC 2.0, issue
+    // slots 50 % busy before this was hoisted).  Everything that depends only on the thread is computed here, once.
     const int cth = p.c_thresh;
     const bool try_flat = p.inverse && !p.write_blur && !p.force_generic && cth >= 0;
+    const bool skip_test = (p.static_sched & 16) != 0;  // EXPERIMENT: every tile counts as flat, untested
     const uint32_t kq = 0x01010101u * (uint32_t)(127 - min(cth >> 1, 127));
+    // flat test of a box that lies entirely inside the image: columns [8, 152) of all GH rows as
+    //   - 16-byte items over columns [16, 144): 8 per row -> rows 0..31 one per thread, rows 32..45 threads 0..111
+    //   - 8-byte edge items (columns 8..15 and 144..151): 2 per row -> threads 128..219
+    static_assert(TW == 128 && TH == 32 && T::GW == 160 && T::GH == 46 && T::GOFF == 8, "flat-test thread mapping");
+    const uint32_t ft0 = (uint32_t)((tid >> 3) * T::GW + 16 + (tid & 7) * 16);
+    const uint32_t ft1 = (uint32_t)((32 + (tid >> 3)) * T::GW + 16 + (tid & 7) * 16);  // tid < 112
+    const uint32_t fte = (uint32_t)((((tid - 128) >> 1)) * T::GW + (((tid - 128) & 1) ? 144 : 8));  // 128 <= tid < 220
+    const uint32_t ftref = (uint32_t)((T::HALO + TH / 2) * T::GW + T::HX + TW / 2);
+    // zero stores of a flat tile that lies entirely inside the image (element offsets from the tile's first pixel / word)
+    const uint32_t so_lab = (uint32_t)((tid >> 5) * W + 4 * (tid & 31)), so_lab_step = (uint32_t)(8 * W);
+    const uint32_t so_mask = (uint32_t)((tid >> 3) * W + 16 * (tid & 7));
+    const uint32_t so_bits = (uint32_t)((tid >> 2) * b.ww + (tid & 3));
+    const bool fast_store_ok = (W & 15) == 0;
+    auto absd = [&](uint32_t v, uint32_t ref4, uint32_t &acc) {
+        const uint32_t d = __vabsdiffu4(v, ref4);
+        acc |= d | ((d & 0x7f7f7f7fu) + kq);
+    };
     for (int it = 0;; it++) {
         const int st = it % kTmaStages;
         unsigned long long t_a = 0, t_b = 0;
@@ -624,40 +653,44 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
         const int4 cur = s_tile[st];
         if (cur.x >= total) break;
-        const int f = cur.y, tx = cur.z, ty = cur.w;
+        const int f = cur.y, tx = cur.z, ty = cur.w & 0xffff;
+        const bool box_inside = (cur.w & 0x10000) != 0, tile_inside = (cur.w & 0x20000) != 0;
         const int x0 = tx * TW, y0 = ty * TH;
 
         // flatness test straight from shared memory, over the in-image part of the tile + halo
         uint8_t *cur_stage = sm + st * STAGE;
-        uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
         uint32_t acc = 0;
-        if (try_flat) {
-            // 16-byte items (row, 16 columns) over the staged box; the image is 16-px aligned, so an item lies entirely
-            // inside or outside of it (outside = zero fill, must not be tested).  Only the logical columns
-            // [GOFF, GOFF + BW) = image x0-8 .. x0+135 matter: the outer halves of the first and last item are ignored.
-            static_assert(T::GW % 16 == 0 && T::GOFF == 8 && T::GOFF + T::BW == T::GW - 8, "flat-test item layout");
-            constexpr int IPR = T::GW / 16;  // items per row
-            const int r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
-            const int j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
-            const uint32_t ref4 =
-                0x01010101u * s_g[min(T::HALO + TH / 2, r_hi - 1)][min(T::HX + TW / 2, 16 * j_hi - 1)];
-            constexpr int NV = T::GH * IPR;
-#pragma unroll
-            for (int k = 0; k < (NV + kK1Consumers - 1) / kK1Consumers; k++) {
-                const int idx = tid + kK1Consumers * k;
-                const int r = idx / IPR, j = idx - r * IPR;
-                if (idx < NV && r >= r_lo && r < r_hi && j >= j_lo && j < j_hi) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(&s_g[r][16 * j]);
-                    if (j == 0) v.x = ref4, v.y = ref4;
-                    if (j == IPR - 1) v.z = ref4, v.w = ref4;
-                    uint32_t d = __vabsdiffu4(v.x, ref4);
-                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
-                    d = __vabsdiffu4(v.y, ref4);
-                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
-                    d = __vabsdiffu4(v.z, ref4);
-                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
-                    d = __vabsdiffu4(v.w, ref4);
-                    acc |= d | ((d & 0x7f7f7f7fu) + kq);
+        if (try_flat && !skip_test) {
+            if (box_inside) {
+                const uint32_t ref4 = 0x01010101u * cur_stage[ftref];
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(cur_stage + ft0);
+                absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
+                if (tid < 112) {
+                    const uint4 v1 = *reinterpret_cast<const uint4 *>(cur_stage + ft1);
+                    absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
+                } else if (tid >= 128 && tid < 220) {
+                    const uint2 v1 = *reinterpret_cast<const uint2 *>(cur_stage + fte);
+                    absd(v1.x, ref4, acc), absd(v1.y, ref4, acc);
+                }
+            } else {
+                // clipped box: 16-byte items (row, 16 columns); the image is 16-px aligned, so an item lies entirely inside
+                // or outside of it (outside = zero fill, must not be tested).  Only the logical columns [8, 152) matter:
+                // the outer halves of the first and last item of a row are ignored.
+                uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
+                constexpr int IPR = T::GW / 16;  // items per row
+                const int r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
+                const int j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
+                const uint32_t ref4 =
+                    0x01010101u * s_g[min(T::HALO + TH / 2, r_hi - 1)][min(T::HX + TW / 2, 16 * j_hi - 1)];
+                constexpr int NV = T::GH * IPR;
+                for (int idx = tid; idx < NV; idx += kK1Consumers) {
+                    const int r = idx / IPR, j = idx - r * IPR;
+                    if (r >= r_lo && r < r_hi && j >= j_lo && j < j_hi) {
+                        uint4 v = *reinterpret_cast<const uint4 *>(&s_g[r][16 * j]);
+                        if (j == 0) v.x = ref4, v.y = ref4;
+                        if (j == IPR - 1) v.z = ref4, v.w = ref4;
+                        absd(v.x, ref4, acc), absd(v.y, ref4, acc), absd(v.z, ref4, acc), absd(v.w, ref4, acc);
+                    }
                 }
             }
         }
@@ -665,8 +698,33 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
         // read before (u1, bl) or during (f) its output stage, and tile k+1 first writes them behind at least one
         // barrier that every consumer reaches only after it has finished tile k.
         const bool flat = !tile_sync_or<true>(acc & 0x80808080u) && try_flat;
-        tile_compute_and_store<TW, TH, 2, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat, tid,
-                                                    &empty[st]);
+        if (flat && tile_inside && fast_store_ok) {
+            // flat tile fully inside a 16-px aligned image: nothing but wide zero stores (one warp writes one 512-byte
+            // label row per instruction)
+            if (tid == 0) mbar_arrive(&empty[st]);  // every thread is past its flat-test reads of the stage
+            const size_t row0 = (size_t)f * H + y0;
+            const size_t pix0 = row0 * W + x0;
+            const int4 z = make_int4(0, 0, 0, 0);
+            if (p.init_labels && !(p.static_sched & 4)) {
+                int32_t *dst = b.labels + pix0 + so_lab;
+                if (p.static_sched & 64) {
+#pragma unroll
+                    for (int k = 0; k < TH / 8; k++) __stcs(reinterpret_cast<int4 *>(dst + k * so_lab_step), z);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TH / 8; k++) *reinterpret_cast<int4 *>(dst + k * so_lab_step) = z;
+                }
+            }
+            if (p.write_mask && !(p.static_sched & 8)) *reinterpret_cast<int4 *>(b.mask + pix0 + so_mask) = z;
+            // occupancy record of the tile: 32 bytes, one per row, all zero.  The 128 all-zero bit-mask words follow unless
+            // only the fused per-frame CCL kernel reads this batch (it never looks at unflagged words).
+            if (b.rowflags && tid < 2)
+                *reinterpret_cast<int4 *>(b.rowflags + (size_t)f * b.rf_stride + rowflag_index(y0, tx, tiles_x) + 16 * tid) = z;
+            if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
+        } else {
+            tile_compute_and_store<TW, TH, 2, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
+                                                        tid, &empty[st]);
+        }
         if (b.phase_ns && tid == 0) {  // debug: time per tile split into TMA wait and processing, flat vs non-flat
             unsigned long long t_c;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
@@ -788,7 +846,11 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     const cuuint32_t box[3] = {(cuuint32_t)T::GW, (cuuint32_t)T::GH, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(b.gray), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            getenv("HV_K1_L2PROM") ? (atoi(getenv("HV_K1_L2PROM")) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : atoi(getenv("HV_K1_L2PROM")) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                                            : CU_TENSOR_MAP_L2_PROMOTION_NONE)
+                                   : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;

@@ -23,30 +23,21 @@ __device__ __forceinline__ Scored score_blob(const BatchView &b, const ScorePara
     const int y_lo = max(icy - 2, 0), y_hi = min(icy + 2, H - 1);
     const int x_lo = max(icx - 2, 0), x_hi = min(icx + 2, W - 1);
     const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
-    // the mask test `mask == 255` (detection.rs:275) reads the bit-packed mask: 5 rows x at most 2 words instead of 25
-    // byte loads (mask bytes are 0 or 255 exactly where the bit is 0 or 1)
-    const uint32_t *bits = b.bits + (size_t)f * H * b.ww;
+    const uint8_t *mask = b.mask + (size_t)f * H * W;
     uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
-    // 5x5 probe, fully unrolled with clamped coordinates so that all loads are in flight together
-    uint32_t gv[25], w0[5], w1[5];
-    const int wa = x_lo >> 5, wb = x_hi >> 5;
+    // 5x5 probe, fully unrolled with clamped coordinates so that all 50 loads are in flight together
+    uint32_t gv[25], mv[25];
 #pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const int y = min(max(icy - 2 + r, 0), H - 1);
-        w0[r] = bits[(size_t)y * b.ww + wa];
-        w1[r] = bits[(size_t)y * b.ww + wb];
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            const int x = min(max(icx - 2 + c, 0), W - 1);
-            gv[r * 5 + c] = gray[(size_t)y * b.gray_row_stride + x];
-        }
+    for (int k = 0; k < 25; k++) {
+        const int y = min(max(icy - 2 + k / 5, 0), H - 1), x = min(max(icx - 2 + k % 5, 0), W - 1);
+        gv[k] = gray[(size_t)y * b.gray_row_stride + x];
+        mv[k] = mask[(size_t)y * W + x];
     }
 #pragma unroll
     for (int k = 0; k < 25; k++) {
         const int y = icy - 2 + k / 5, x = icx - 2 + k % 5;
         if (y >= y_lo && y <= y_hi && x >= x_lo && x <= x_hi) {
-            const uint32_t wsel = (x >> 5) == wa ? w0[k / 5] : w1[k / 5];
-            if ((wsel >> (x & 31)) & 1u) {
+            if (mv[k] == 255) {
                 fg_sum += gv[k];
                 fg_cnt++;
             } else {

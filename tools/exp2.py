@@ -2,13 +2,13 @@
 import os, sys, numpy as np, torch
 sys.path.insert(0, 'heimdall-vision_b200'); sys.path.insert(0, '.')
 import heimdall_core as hc, synth
-n, h, w = 25, 1024, 1280
+n, h, w = int(os.environ.get('NFR', 25)), 1024, 1280
 pool = [torch.from_numpy(synth.bottle_batch(n, h, w, start_index=1000 * i)).cuda() for i in range(8)]
 uni = [torch.full((n, h, w), 220, dtype=torch.uint8, device='cuda') for _ in range(8)]
 st = torch.cuda.current_stream().cuda_stream
 outs = [(torch.empty((n, h, w), dtype=torch.uint8, device='cuda'), torch.empty((n, h, w), dtype=torch.int32, device='cuda')) for _ in range(2)]
 def run(tag, env, data):
-    for k in ('HV_K1_DYNAMIC', 'HV_K1_SKIP_AUX', 'HV_NO_PDL', 'HV_K1_CTAS_PER_SM'): os.environ.pop(k, None)
+    for k in ('HV_K1_DYNAMIC', 'HV_K1_SKIP_AUX', 'HV_NO_PDL', 'HV_K1_DEBUG_SKIP', 'HV_K1_L2PROM'): os.environ.pop(k, None)
     os.environ.update(env)
     det = hc.Detector(0, profile=True); det.set_stream(st)
     def step(i): det.enqueue_device(data[i % 8].data_ptr(), n, h, w, 1, None, outs[i & 1][0].data_ptr(), outs[i & 1][1].data_ptr())
@@ -34,5 +34,10 @@ def run(tag, env, data):
 for a in sys.argv[1:]:
     tag, _, rest = a.partition(':')
     env = dict(kv.split('=') for kv in rest.split(',') if kv)
-    data = uni if env.pop('DATA', 'bottle') == 'uniform' else pool
+    dk = env.pop('DATA', 'bottle')
+    if dk == 'noise':
+        rng = np.random.default_rng(0)
+        data = [torch.from_numpy((128 + rng.integers(-8, 9, size=(n, h, w))).astype(np.uint8)).cuda() for _ in range(8)]
+    else:
+        data = uni if dk == 'uniform' else pool
     run(tag, env, data)

@@ -6,7 +6,9 @@ import heimdall_core as hc, synth
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 kind = sys.argv[2] if len(sys.argv) > 2 else 'bottle'
 n, h, w = 25, 1024, 1280
-if kind == 'bottle':
+if kind == 'uniform':
+    batch = np.full((n, h, w), 220, np.uint8)
+elif kind == 'bottle':
     batch = synth.bottle_batch(n, h, w, start_index=0)
 else:
     batch = np.random.default_rng(0).integers(0, 256, (n, h, w), dtype=np.uint8)
