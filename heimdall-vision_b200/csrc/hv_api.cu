@@ -442,7 +442,6 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
         pp.static_sched = (pdl || getenv("HV_K1_DYNAMIC")) ? 0 : 1;
-        if (getenv("HV_K1_DEBUG_SKIP")) pp.static_sched |= atoi(getenv("HV_K1_DEBUG_SKIP")) & ~1;
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));

@@ -35,6 +35,7 @@ constexpr int kCapW = 4096;    // non-zero words per frame
 constexpr int kCapN = 8192;    // word-runs (nodes) per frame
 constexpr int kCapB = 2048;    // components per frame
 constexpr int kMaxEPT = kCapW / kFT;  // compacted words per thread (blocked partition)
+constexpr int kCapE = 4096;    // residual union edges per frame
 
 struct FrameSmem {
     uint32_t widx[kCapW];      // word index (y * ww + wx) of the compacted non-zero words, raster order
@@ -42,7 +43,8 @@ struct FrameSmem {
     uint32_t parent[kCapN];    // union-find parents (node ids)
     uint32_t node_px[kCapN];   // pixel index (y * w + x) of the first pixel of the run
     uint16_t woff[kCapW + 8];  // first node of every compacted word
-    uint16_t up[kCapW];        // entry of the word directly above when it overlaps this word, else 0xffff
+    uint32_t edges[kCapE];     // residual union edges (u << 16 | v), see phase 2
+    uint32_t n_edges;
     uint16_t rnk[kCapN];       // rank of the component among the roots (valid at root nodes)
     uint8_t node_len[kCapN];
     uint32_t b_area[kCapB], b_sy[kCapB], b_sx[kCapB], b_ymin[kCapB], b_ymax[kCapB], b_xmin[kCapB], b_xmax[kCapB];
@@ -87,7 +89,7 @@ __device__ __forceinline__ uint32_t s_find(volatile uint32_t *parent, uint32_t a
 }
 
 // Lock-free union by minimum id (atomicMin keeps parents monotonically decreasing under concurrent unions).
-__device__ __noinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b) {
     while (true) {
         a = s_find(parent, a);
         b = s_find(parent, b);
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     uint8_t *stage = reinterpret_cast<uint8_t *>(S.parent);
     const int bands_per_chunk = min(nbands, (int)(2 * sizeof(uint32_t) * kCapN) / band_bytes);
     if (tid < HV_STATS_AREA_BINS) S.hist[tid] = 0;
-    if (tid == 0) S.area_sum = 0;
+    if (tid == 0) S.area_sum = 0, S.n_edges = 0;
     uint32_t nw = 0;
     bool too_big = H > 8192 || W > 8192 || bands_per_chunk < 1;
     for (int b0 = 0; b0 < nbands && !too_big; b0 += bands_per_chunk) {
@@ -255,14 +257,16 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     // built in three steps:
     //   (a) every node points at its smallest "previous" neighbour (leftmost overlapping run of the row above, else the
     //       run ending the word to the left); previous neighbours always have smaller ids, so these pointers form trees
-    //       whose roots are the trees' minimum ids;
+    //       whose roots are the trees' minimum ids.  Every other adjacency of the node (further overlapping runs above,
+    //       the left neighbour when an upper one was chosen) goes to an edge list;
     //   (b) pointer jumping collapses every chain of length n in O(log n) rounds;
-    //   (c) the remaining edges (further overlapping runs above, the left neighbour when an upper one was chosen) are
-    //       ordinary unions by minimum between the now depth-1 trees.
+    //   (c) the listed edges are ordinary unions by minimum between the now depth-1 trees, ONE edge per thread: inside
+    //       the per-word loops a union (a few hundred cycles of dependent shared-memory accesses and an atomic per
+    //       retry) was serialised by the SIMT execution of the nested loops of all 32 lanes -- 8 us for 76 unions.
     for (uint32_t e = tid; e < nw; e += kFT) {
         const uint32_t i = S.widx[e], m = S.wbits[e];
         const uint32_t base = S.woff[e];
-        uint32_t up = 0, ustarts = 0, ubase = 0, upe = 0xffffu;
+        uint32_t up = 0, ustarts = 0, ubase = 0;
         if (i >= (uint32_t)WW) {
             // the word above, if present, is at most WW - 1 entries back (entries are sorted by word index)
             const uint32_t target = i - WW;
@@ -274,14 +278,12 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
                 else
                     hi = mid;
             }
-            if (lo < e && S.widx[lo] == target && (S.wbits[lo] & m)) {
-                upe = lo;
+            if (lo < e && S.widx[lo] == target) {
                 up = S.wbits[lo];
                 ustarts = up & ~(up << 1);
                 ubase = S.woff[lo];
             }
         }
-        S.up[e] = (uint16_t)upe;
         const bool left_touch = (m & 1u) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 && (S.wbits[e - 1] >> 31);
         uint32_t rest = m, v = base;
         while (rest) {
@@ -292,42 +294,42 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
             rest &= ~runmask;
             const uint32_t o = runmask & up;
             uint32_t p = v;
-            if (o)
+            if (o) {
                 p = ubase + run_index(ustarts, __ffs(o) - 1);  // leftmost overlapping run above: smallest id
-            else if (bit == 0 && left_touch)
+                // one segment per further run above that touches this run, plus the left neighbour
+                uint32_t os = o & ~(o << 1);
+                os &= os - 1;
+                uint32_t extra = __popc(os) + ((bit == 0 && left_touch) ? 1u : 0u);
+                if (extra) {
+                    uint32_t slot = atomicAdd(&S.n_edges, extra);
+                    if (slot + extra <= (uint32_t)kCapE) {
+                        while (os) {
+                            S.edges[slot++] = (v << 16) | (ubase + run_index(ustarts, __ffs(os) - 1));
+                            os &= os - 1;
+                        }
+                        if (bit == 0 && left_touch) S.edges[slot] = (v << 16) | (base - 1);
+                    }
+                }
+            } else if (bit == 0 && left_touch) {
                 p = base - 1;
+            }
             S.parent[v] = p;
             v++;
         }
     }
     stamp();  // 3
     __syncthreads();
+    const uint32_t ne = S.n_edges;
+    if (ne > (uint32_t)kCapE) {  // block-uniform
+        if (tid == 0) b.frame_flags[f] = 1u;
+        return;
+    }
     pointer_jump(S.parent, nn, tid);
     stamp();  // 4
     __syncthreads();
-    for (uint32_t e = tid; e < nw; e += kFT) {
-        const uint32_t upe = S.up[e];
-        const uint32_t m = S.wbits[e];
-        if (upe == 0xffffu) continue;  // no overlap above: step (a) already used the only edge (the left neighbour)
-        const uint32_t i = S.widx[e];
-        const uint32_t base = S.woff[e];
-        const uint32_t starts = m & ~(m << 1);
-        const uint32_t up = S.wbits[upe];
-        const uint32_t ustarts = up & ~(up << 1), ubase = S.woff[upe];
-        const uint32_t o = m & up;
-        uint32_t os = o & ~(o << 1);  // one segment per (run here, run above) pair that touches
-        uint32_t seen = 0;            // runs of this word whose first segment (= step (a)'s choice) was passed
-        while (os) {
-            const int bit = __ffs(os) - 1;
-            os &= os - 1;
-            const uint32_t ri = run_index(starts, bit);
-            if (seen & (1u << ri)) s_union(S.parent, base + ri, ubase + run_index(ustarts, bit));
-            seen |= 1u << ri;
-        }
-        // first run starts at bit 0, touches a run above (chosen in (a)) and also the run ending the word to the left
-        if ((m & 1u) && (o & ((m ^ (m + 1u)) & m)) && e > 0 && S.widx[e - 1] == i - 1 && (i % WW) != 0 &&
-            (S.wbits[e - 1] >> 31))
-            s_union(S.parent, base, base - 1);
+    for (uint32_t k = tid; k < ne; k += kFT) {
+        const uint32_t ed = S.edges[k];
+        s_union(S.parent, ed >> 16, ed & 0xffffu);
     }
     stamp();  // 5
     __syncthreads();

@@ -340,13 +340,13 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         // label row per instruction)
         const int4 z = make_int4(0, 0, 0, 0);
         const size_t o0 = (size_t)f * H * W + (size_t)y0 * W + x0;
-        if (p.init_labels && !(p.static_sched & 4)) {
+        if (p.init_labels) {
             int4 *dst = reinterpret_cast<int4 *>(b.labels + o0 + (size_t)(tid >> 5) * W) + (tid & 31);
             const size_t step = (size_t)2 * W;  // 8 rows of W int32 = 2*W int4
 #pragma unroll
             for (int k = 0; k < TH / 8; k++) dst[k * step] = z;
         }
-        if (p.write_mask && !(p.static_sched & 8)) {
+        if (p.write_mask) {
             static_assert(TH * (TW / 16) == 256, "one 16-pixel group per thread");
             *reinterpret_cast<int4 *>(b.mask + o0 + (size_t)(tid >> 3) * W + 16 * (tid & 7)) = z;
         }
@@ -584,12 +584,12 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
         if (tid != kK1Consumers) return;
         // dynamic schedule: the number handed out now was requested one fetch earlier, so the round trip of the atomic
         // overlaps the previous issue; static schedule (kernel launched alone, HV_K1_DYNAMIC unset): round robin
-        int pending = (p.static_sched & 1) ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
+        int pending = p.static_sched ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
         for (int it = 0;; it++) {
             const int st = it % kTmaStages;
             if (it >= kTmaStages) mbar_wait(&empty[st], (uint32_t)(it / kTmaStages - 1) & 1u);
             const int t = pending;
-            pending = (p.static_sched & 1) ? pending + (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            pending = p.static_sched ? pending + (int)gridDim.x : (int)atomicAdd(sched, 1u);
             const int f = t / per_frame, r = t - f * per_frame;
             const int ty = r / tiles_x, tx = r - ty * tiles_x;
             // bit 16 of .w: the whole staged box lies inside the image; bit 17: the whole tile lies inside the image
@@ -601,15 +601,11 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
                 mbar_arrive(&full[st]);  // end marker: tile numbers only grow, nothing is left for this CTA
                 break;
             }
-            if (p.static_sched & 32) {  // EXPERIMENT: no loads at all
-                mbar_arrive(&full[st]);
-                continue;
-            }
             mbar_expect_tx(&full[st], (uint32_t)T::G_BYTES);
             tma_load_3d(sm + st * STAGE, &tmap, &full[st], tx * TW - T::HX, ty * TH - T::HALO, f);
         }
         // the last CTA to finish fetching rearms the scheduler for the next launch
-        if (!(p.static_sched & 1)) {
+        if (!p.static_sched) {
             __threadfence();
             const unsigned int d = atomicAdd(sched + 1, 1u);
             if (d == gridDim.x - 1) {
@@ -626,7 +622,6 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
     // slots 50 % busy before this was hoisted).  Everything that depends only on the thread is computed here, once.
     const int cth = p.c_thresh;
     const bool try_flat = p.inverse && !p.write_blur && !p.force_generic && cth >= 0;
-    const bool skip_test = (p.static_sched & 16) != 0;  // EXPERIMENT: every tile counts as flat, untested
     const uint32_t kq = 0x01010101u * (uint32_t)(127 - min(cth >> 1, 127));
     // flat test of a box that lies entirely inside the image: columns [8, 152) of all GH rows as
     //   - 16-byte items over columns [16, 144): 8 per row -> rows 0..31 one per thread, rows 32..45 threads 0..111
@@ -660,7 +655,7 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
         // flatness test straight from shared memory, over the in-image part of the tile + halo
         uint8_t *cur_stage = sm + st * STAGE;
         uint32_t acc = 0;
-        if (try_flat && !skip_test) {
+        if (try_flat) {
             if (box_inside) {
                 const uint32_t ref4 = 0x01010101u * cur_stage[ftref];
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(cur_stage + ft0);
@@ -705,17 +700,12 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
             const size_t row0 = (size_t)f * H + y0;
             const size_t pix0 = row0 * W + x0;
             const int4 z = make_int4(0, 0, 0, 0);
-            if (p.init_labels && !(p.static_sched & 4)) {
+            if (p.init_labels) {
                 int32_t *dst = b.labels + pix0 + so_lab;
-                if (p.static_sched & 64) {
 #pragma unroll
-                    for (int k = 0; k < TH / 8; k++) __stcs(reinterpret_cast<int4 *>(dst + k * so_lab_step), z);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < TH / 8; k++) *reinterpret_cast<int4 *>(dst + k * so_lab_step) = z;
-                }
+                for (int k = 0; k < TH / 8; k++) *reinterpret_cast<int4 *>(dst + k * so_lab_step) = z;
             }
-            if (p.write_mask && !(p.static_sched & 8)) *reinterpret_cast<int4 *>(b.mask + pix0 + so_mask) = z;
+            if (p.write_mask) *reinterpret_cast<int4 *>(b.mask + pix0 + so_mask) = z;
             // occupancy record of the tile: 32 bytes, one per row, all zero.  The 128 all-zero bit-mask words follow unless
             // only the fused per-frame CCL kernel reads this batch (it never looks at unflagged words).
             if (b.rowflags && tid < 2)
@@ -847,10 +837,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(b.gray), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            getenv("HV_K1_L2PROM") ? (atoi(getenv("HV_K1_L2PROM")) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                      : atoi(getenv("HV_K1_L2PROM")) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                                                            : CU_TENSOR_MAP_L2_PROMOTION_NONE)
-                                   : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;

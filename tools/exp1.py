@@ -36,9 +36,9 @@ os.environ['HV_PHASE_FRAME'] = str(slow)
 det = hc.Detector(0, profile=True, phase_timing=True); det.set_stream(st)
 for it in range(3): det.detect_device(pool[0].data_ptr(), n, h, w)
 pt = np.array(det.phase_times()[:192], dtype=np.int64).reshape(12, 16); t0 = pt[0].min()
-print('stamps of frame', slow, 'unions/steps/maxsteps/maxunions per thread', det.phase_times()[192:196])
+print('   warp1 iteration start cycles', det.phase_times()[196:203]); q2 = det.phase_times()[193:196]; print('   max steps thread: find steps', (q2[0] >> 32) & 0xffff, 'union iters', q2[0] >> 48, 'tid', q2[0] & 0xffff, '| totals: find steps', q2[1], 'union iters', q2[2]); q = det.phase_times()[192]; print('stamps of frame', slow, 'P2c slowest thread: cycles', q >> 32, 'tid', (q >> 20) & 0xfff, 'vert unions', (q >> 8) & 0xff, 'left unions', (q >> 16) & 0xf, 'segs', q & 0xff)
 for i in range(12):
-    if pt[i].max() > 0: print('  stamp', i, 'warps min/max us %.2f %.2f' % ((pt[i].min() - t0) / 1e3, (pt[i].max() - t0) / 1e3))
+    if pt[i].max() > 0: print('  stamp', i, 'warps min/max us %.2f %.2f' % ((pt[i].min() - t0) / 1e3, (pt[i].max() - t0) / 1e3), ' per warp:', ' '.join('%.1f' % ((x - t0) / 1e3) for x in pt[i]))
 det.close()
 for env in ({}, {'HV_NO_PDL': '1'}):
     for k in ('HV_NO_PDL',): os.environ.pop(k, None)

@@ -8,7 +8,7 @@ uni = [torch.full((n, h, w), 220, dtype=torch.uint8, device='cuda') for _ in ran
 st = torch.cuda.current_stream().cuda_stream
 outs = [(torch.empty((n, h, w), dtype=torch.uint8, device='cuda'), torch.empty((n, h, w), dtype=torch.int32, device='cuda')) for _ in range(2)]
 def run(tag, env, data):
-    for k in ('HV_K1_DYNAMIC', 'HV_K1_SKIP_AUX', 'HV_NO_PDL', 'HV_K1_DEBUG_SKIP', 'HV_K1_L2PROM'): os.environ.pop(k, None)
+    for k in ('HV_K1_DYNAMIC', 'HV_K1_SKIP_AUX', 'HV_NO_PDL', 'HV_K1_DEBUG_SKIP', 'HV_K1_L2PROM', 'HV_CCL_REPEAT'): os.environ.pop(k, None)
     os.environ.update(env)
     det = hc.Detector(0, profile=True); det.set_stream(st)
     def step(i): det.enqueue_device(data[i % 8].data_ptr(), n, h, w, 1, None, outs[i & 1][0].data_ptr(), outs[i & 1][1].data_ptr())
