@@ -69,6 +69,7 @@ struct Slot {
     DevBuf<uint16_t> gauss_tmp;
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags, sched;
     PinBuf<uint32_t> h_flags;
+    PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
     bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
@@ -90,7 +91,7 @@ struct Slot {
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
         frame_flags.release(), h_flags.release(), sched.release();
-        h_results.release(), h_defects.release();
+        h_results.release(), h_defects.release(), h_stage.release();
         if (done) cudaEventDestroy(done);
         if (stream) cudaStreamDestroy(stream);
         done = nullptr;
@@ -898,6 +899,169 @@ hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defe
         }
     }
     return fail(ctx, HV_ERR_BAD_TICKET, "unknown or already consumed ticket");
+}
+
+// ---- frame feed (N1) --------------------------------------------------------------------------------------------------
+int32_t hv_frame_channels(int32_t fmt) {
+    switch (fmt) {
+        case HV_PIX_MONO8: return 1;
+        case HV_PIX_RGB8:
+        case HV_PIX_BGR8: return 3;
+        case HV_PIX_RGBA8:
+        case HV_PIX_BGRA8: return 4;
+        case HV_PIX_YUV422:
+        case HV_PIX_YUV422_PACKED:
+        case HV_PIX_BAYER_RG8:
+        case HV_PIX_BAYER_GB8:
+        case HV_PIX_BAYER_GR8:
+        case HV_PIX_BAYER_BG8: return 3;
+        default: return 0;
+    }
+}
+
+}  // extern "C"
+
+namespace {
+
+bool is_bayer(int32_t fmt) { return fmt >= HV_PIX_BAYER_RG8 && fmt <= HV_PIX_BAYER_BG8; }
+bool is_yuyv(int32_t fmt) { return fmt == HV_PIX_YUV422 || fmt == HV_PIX_YUV422_PACKED; }
+
+// bytes per pixel of the raw frame, 0 = unknown format
+size_t raw_bytes_per_px(int32_t fmt) {
+    switch (fmt) {
+        case HV_PIX_MONO8: return 1;
+        case HV_PIX_MONO16: return 2;
+        case HV_PIX_RGB8:
+        case HV_PIX_BGR8: return 3;
+        case HV_PIX_RGBA8:
+        case HV_PIX_BGRA8: return 4;
+        case HV_PIX_YUV422:
+        case HV_PIX_YUV422_PACKED: return 2;
+        default: return is_bayer(fmt) ? 1 : 0;
+    }
+}
+
+hv_status check_frame(hv_ctx *ctx, const hv_camera_frame &fr) {
+    if (!fr.data || fr.width == 0 || fr.height == 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "empty camera frame");
+    const size_t bpp = raw_bytes_per_px(fr.pixel_format);
+    if (!bpp) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "unknown pixel format");
+    if ((unsigned long long)fr.width * fr.height >= 2147483647ULL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    if (fr.size < (size_t)fr.width * fr.height * bpp)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "camera frame data shorter than width * height * bytes per pixel");
+    if (is_yuyv(fr.pixel_format) && (fr.width & 1))
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "YUV422 frames need an even width");
+    return HV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+hv_status hv_convert_frame(hv_ctx *ctx, const hv_camera_frame *frame, uint8_t *out, int32_t *out_channels) {
+    if (!ctx || !frame || !out) return HV_ERR_INVALID_ARGUMENT;
+    hv_status rs = check_frame(ctx, *frame);
+    if (rs != HV_OK) return rs;
+    const int32_t fmt = frame->pixel_format;
+    const int32_t oc = hv_frame_channels(fmt);
+    if (!oc)  // lib.rs:266-269 / 217-219
+        return fail(ctx, HV_ERR_UNSUPPORTED, "Erreur de conversion d'image: Format de pixel non supporte pour la conversion");
+    if (out_channels) *out_channels = oc;
+    const int h = (int)frame->height, w = (int)frame->width;
+    const size_t px = (size_t)h * w;
+    if (!is_bayer(fmt) && !is_yuyv(fmt)) {  // to_ndarray: the bytes are the image
+        std::memcpy(out, frame->data, px * oc);
+        return HV_OK;
+    }
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    const size_t raw = px * raw_bytes_per_px(fmt);
+    HV_TRY_CUDA(ctx, ctx->u_a.reserve(raw));
+    HV_TRY_CUDA(ctx, ctx->u_b.reserve(px * 3));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->u_a.p, frame->data, raw, cudaMemcpyHostToDevice, st));
+    if (is_bayer(fmt))
+        HV_TRY_CUDA(ctx, launch_bayer(ctx->u_a.p, 1, h, w, fmt - HV_PIX_BAYER_RG8, false, ctx->u_b.p, st));
+    else
+        HV_TRY_CUDA(ctx, launch_yuyv(ctx->u_a.p, 1, h, w, false, ctx->u_b.p, st));
+    ctx->launches++;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(out, ctx->u_b.p, px * 3, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
+hv_status hv_submit_frames(hv_ctx *ctx, const hv_camera_frame *frames, int32_t n, const hv_params *params,
+                           int64_t *ticket) {
+    if (!ctx || !frames || !ticket || n <= 0) return HV_ERR_INVALID_ARGUMENT;
+    const int32_t fmt = frames[0].pixel_format;
+    const int h = (int)frames[0].height, w = (int)frames[0].width;
+    for (int f = 0; f < n; f++) {
+        hv_status rs = check_frame(ctx, frames[f]);
+        if (rs != HV_OK) return rs;
+        if (frames[f].pixel_format != fmt || (int)frames[f].height != h || (int)frames[f].width != w)
+            return fail(ctx, HV_ERR_INVALID_ARGUMENT, "all frames of a batch must share geometry and pixel format");
+    }
+    const int32_t oc = hv_frame_channels(fmt);
+    if (!oc) return fail(ctx, HV_ERR_UNSUPPORTED, "Erreur de conversion d'image: Format de pixel non supporte pour la conversion");
+    if (oc != 1 && oc != 3) return fail(ctx, HV_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: expected 3D array");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    hv_params pr;
+    if (params)
+        pr = *params;
+    else
+        hv_params_default(&pr);
+    int pick = -1;
+    const int nslots = (int)ctx->slots.size();
+    const int nasync = nslots - kSyncSlots;
+    for (int k = 0; k < nasync; k++) {
+        const int idx = kSyncSlots + (ctx->next_slot + k) % nasync;
+        if (ctx->slots[idx].ticket < 0) {
+            pick = idx;
+            break;
+        }
+    }
+    if (pick < 0) return fail(ctx, HV_ERR_CAPACITY, "all slots are in flight: call hv_wait first");
+    ctx->next_slot = (pick - kSyncSlots + 1) % nasync;
+    Slot &s = ctx->slots[pick];
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    const size_t raw = px * raw_bytes_per_px(fmt);
+    HV_TRY_CUDA(ctx, s.in.reserve(raw * n));
+    // frames already in page-locked memory go straight to the device; pageable ones pass through the slot's pinned
+    // staging buffer so that the copy engine, not a hidden driver bounce buffer, moves them
+    bool all_pinned = true;
+    for (int f = 0; f < n && all_pinned; f++) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, frames[f].data) != cudaSuccess || at.type != cudaMemoryTypeHost) all_pinned = false;
+    }
+    cudaGetLastError();
+    if (!all_pinned) {
+        HV_TRY_CUDA(ctx, s.h_stage.reserve(raw * n));
+        for (int f = 0; f < n; f++) std::memcpy(s.h_stage.p + raw * f, frames[f].data, raw);
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, s.h_stage.p, raw * n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < n; f++)
+            HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p + raw * f, frames[f].data, raw, cudaMemcpyHostToDevice, st));
+    }
+    hv_status rs;
+    if (is_bayer(fmt) || is_yuyv(fmt)) {
+        // mosaic / YUV -> the gray the detector's A1 stage computes from the converted RGB image, in one kernel
+        HV_TRY_CUDA(ctx, s.gray.reserve(px * n));
+        ProfScope ps(ctx, HV_K_GRAY, st);
+        if (is_bayer(fmt))
+            HV_TRY_CUDA(ctx, launch_bayer(s.in.p, n, h, w, fmt - HV_PIX_BAYER_RG8, true, s.gray.p, st));
+        else
+            HV_TRY_CUDA(ctx, launch_yuyv(s.in.p, n, h, w, true, s.gray.p, st));
+        ctx->launches++;
+        rs = enqueue_pipeline(ctx, s, st, s.gray.p, n, h, w, 1, 0, 0, pr, nullptr, nullptr, false);
+    } else {
+        rs = enqueue_pipeline(ctx, s, st, s.in.p, n, h, w, oc, 0, 0, pr, nullptr, nullptr, false);
+    }
+    if (rs != HV_OK) return rs;
+    rs = enqueue_readback(ctx, s, st);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaEventRecord(s.done, st));
+    s.ticket = ctx->next_ticket++;
+    *ticket = s.ticket;
+    return HV_OK;
 }
 
 // ---- single-frame utilities ---------------------------------------------------------------------------------------

@@ -65,6 +65,21 @@ struct ScoreParams {
     double min_size, max_size, min_confidence;
 };
 
+#ifdef __CUDACC__
+// f64 gray with the reference's expression order: (0.299*c0 + 0.587*c1) + 0.114*c2, truncated
+// (detection.rs:138-150).  __dmul_rn/__dadd_rn keep the compiler from contracting into FMAs.
+__device__ __forceinline__ uint8_t gray_f64(uint32_t c0, uint32_t c1, uint32_t c2) {
+    const double t0 = __dmul_rn(0.299, (double)c0);
+    const double t1 = __dmul_rn(0.587, (double)c1);
+    const double t2 = __dmul_rn(0.114, (double)c2);
+    const double s = __dadd_rn(__dadd_rn(t0, t1), t2);
+    int v = __double2int_rz(s);
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    return (uint8_t)v;
+}
+
+#endif
+
 #define HV_CUDA_TRY(expr)                         \
     do {                                          \
         cudaError_t _e = (expr);                  \
@@ -104,6 +119,9 @@ cudaError_t launch_visualise(const uint8_t *mask, int h, int w, const hv_center 
 cudaError_t launch_gray_first3(const uint8_t *d_img, int h, int w, int c, uint8_t *d_gray, cudaStream_t s);
 cudaError_t launch_collect_centers(const BatchView &b, uint32_t min_area, hv_center *d_centers, uint32_t *d_count,
                                    int cap, cudaStream_t s);
+cudaError_t launch_bayer(const uint8_t *d_src, int n, int h, int w, int pattern, bool to_gray, uint8_t *d_dst,
+                         cudaStream_t s);
+cudaError_t launch_yuyv(const uint8_t *d_src, int n, int h, int w, bool to_gray, uint8_t *d_dst, cudaStream_t s);
 cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
                                     uint32_t *d_count, int cap, cudaStream_t s);
 

@@ -735,18 +735,6 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
     }
 }
 
-// f64 gray with the reference's expression order: (0.299*c0 + 0.587*c1) + 0.114*c2, truncated
-// (detection.rs:138-150).  __dmul_rn/__dadd_rn keep the compiler from contracting into FMAs.
-__device__ __forceinline__ uint8_t gray_f64(uint32_t c0, uint32_t c1, uint32_t c2) {
-    const double t0 = __dmul_rn(0.299, (double)c0);
-    const double t1 = __dmul_rn(0.587, (double)c1);
-    const double t2 = __dmul_rn(0.114, (double)c2);
-    const double s = __dadd_rn(__dadd_rn(t0, t1), t2);
-    int v = __double2int_rz(s);
-    v = v < 0 ? 0 : (v > 255 ? 255 : v);
-    return (uint8_t)v;
-}
-
 __global__ void __launch_bounds__(256) k_gray3(const uint8_t *img, int n, int h, int w, int c, size_t row_stride,
                                                size_t frame_stride, uint8_t *gray) {
     const size_t total = (size_t)n * h * w;

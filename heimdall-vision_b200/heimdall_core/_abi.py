@@ -88,6 +88,17 @@ class hv_center(C.Structure):
     _fields_ = [("y", C.c_int32), ("x", C.c_int32), ("confidence", C.c_double)]
 
 
+(HV_PIX_MONO8, HV_PIX_MONO16, HV_PIX_RGB8, HV_PIX_BGR8, HV_PIX_RGBA8, HV_PIX_BGRA8, HV_PIX_YUV422,
+ HV_PIX_YUV422_PACKED, HV_PIX_BAYER_RG8, HV_PIX_BAYER_GB8, HV_PIX_BAYER_GR8, HV_PIX_BAYER_BG8) = range(12)
+
+
+class hv_camera_frame(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("pixel_format", C.c_int32), ("camera", C.c_uint32), ("frame_id", C.c_uint64),
+                ("timestamp_ns", C.c_uint64)]
+
+
+assert C.sizeof(hv_camera_frame) == 48
 assert C.sizeof(hv_defect) == 48 and C.sizeof(hv_frame_result) == 24 and C.sizeof(hv_blob) == 40
 assert C.sizeof(hv_line_stats) == 256
 
@@ -117,6 +128,9 @@ PROTOTYPES = {
     "hv_fetch_debug": (_i32, [_vp, _P(hv_debug_outputs)]),
     "hv_submit": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _P(_i64)]),
     "hv_wait": (_i32, [_vp, _i64, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
+    "hv_frame_channels": (_i32, [_i32]),
+    "hv_convert_frame": (_i32, [_vp, _P(hv_camera_frame), _vp, _P(_i32)]),
+    "hv_submit_frames": (_i32, [_vp, _P(hv_camera_frame), _i32, _P(hv_params), _P(_i64)]),
     "hv_preprocess_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hv_apply_threshold": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_uint8, _i32, _i32, _vp]),
     "hv_find_contours": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _f64, _P(hv_contour), _sz, _P(_sz), _vp]),

@@ -188,6 +188,39 @@ class Detector:
                 _raise(st, self._ctx)
         return BatchResult(res, dfx[:total.value], st)
 
+    # ---- frame feed (N1): raw camera frames ----------------------------------------------------------------------
+    def convert_frame(self, frame) -> np.ndarray:
+        """One `camera.CameraFrame` -> the (h, w, c) u8 image the reference hands to the detector."""
+        fa = frame.as_abi()
+        ch = int(_lib.hv_frame_channels(fa.pixel_format))
+        out = np.empty((int(fa.height), int(fa.width), max(ch, 1)), np.uint8)
+        oc = C.c_int32(0)
+        with self._lock:
+            st = _lib.hv_convert_frame(self._ctx, C.byref(fa), out.ctypes.data, C.byref(oc))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        return out
+
+    def submit_frames(self, frames, params: Optional[A.hv_params] = None) -> int:
+        """Asynchronous batch of raw camera frames (identical geometry and pixel format); collect with `wait`."""
+        arr = (A.hv_camera_frame * len(frames))(*[f.as_abi() for f in frames])
+        t = C.c_int64(0)
+        p = params if params is not None else make_params()
+        with self._lock:
+            st = _lib.hv_submit_frames(self._ctx, arr, len(frames), C.byref(p), C.byref(t))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        self._inflight_frames = getattr(self, "_inflight_frames", {})
+        self._inflight_frames[t.value] = (arr, list(frames))  # the raw data must outlive the copy
+        return t.value
+
+    def detect_frames(self, frames, params: Optional[A.hv_params] = None) -> BatchResult:
+        t = self.submit_frames(frames, params)
+        try:
+            return self.wait(t, len(frames))
+        finally:
+            self._inflight_frames.pop(t, None)
+
     def host_alloc(self, nbytes: int) -> int:
         p = _lib.hv_host_alloc(self._ctx, nbytes)
         if not p:

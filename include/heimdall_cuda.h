@@ -222,6 +222,47 @@ HV_API hv_status hv_submit(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_
 HV_API hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects,
                          size_t defects_cap, size_t *n_defects_total);
 
+/* ---- frame feed (next-row N1) ----------------------------------------------------------------------------
+ * Camera frames as heimdall-camera delivers them: `CameraFrame` (rust/heimdall-camera/src/lib.rs:111-132) with
+ * `PixelFormat` (lib.rs:34-47).  The raw bytes cross PCIe once (1 B/px for Mono8 / Bayer, 2 B/px for YUV422) and are
+ * converted on the device. */
+enum {
+    HV_PIX_MONO8 = 0,
+    HV_PIX_MONO16 = 1,
+    HV_PIX_RGB8 = 2,
+    HV_PIX_BGR8 = 3,
+    HV_PIX_RGBA8 = 4,
+    HV_PIX_BGRA8 = 5,
+    HV_PIX_YUV422 = 6,
+    HV_PIX_YUV422_PACKED = 7,
+    HV_PIX_BAYER_RG8 = 8,
+    HV_PIX_BAYER_GB8 = 9,
+    HV_PIX_BAYER_GR8 = 10,
+    HV_PIX_BAYER_BG8 = 11
+};
+typedef struct {
+    const uint8_t *data; /* raw frame bytes, host memory (pinned memory from hv_host_alloc avoids a staging copy) */
+    size_t size;         /* bytes in data */
+    uint32_t width, height;
+    int32_t pixel_format; /* HV_PIX_* */
+    uint32_t camera;      /* index of the camera / stream the frame came from (free for the caller) */
+    uint64_t frame_id;
+    uint64_t timestamp_ns;
+} hv_camera_frame;
+
+/* Channels of the image a frame converts to, or 0 when the format has no conversion: to_ndarray (lib.rs:260-278) gives
+ * 1 / 3 / 4 channels for Mono8 / RGB8,BGR8 / RGBA8,BGRA8 (bytes unchanged); the cv2.cvtColor conversions named by
+ * to_opencv_mat (lib.rs:226-252) give 3 (RGB) for the Bayer and YUV422 formats; Mono16 has none. */
+HV_API int32_t hv_frame_channels(int32_t pixel_format);
+/* One frame -> (height, width, channels) u8 image in host memory (the array the reference hands to the detector). */
+HV_API hv_status hv_convert_frame(hv_ctx *ctx, const hv_camera_frame *frame, uint8_t *out_hwc, int32_t *out_channels);
+/* hv_submit for n camera frames of identical geometry and pixel format: staging -> H2D -> conversion -> detect.
+ * Formats that convert to 1 or 3 channels are accepted (detection.rs:138-160 rejects everything else:
+ * HV_ERR_INVALID_DIMENSIONS); results are those of detect_contamination on the converted images.  Collect with
+ * hv_wait.  The frames' data must stay valid until hv_wait returns. */
+HV_API hv_status hv_submit_frames(hv_ctx *ctx, const hv_camera_frame *frames, int32_t n, const hv_params *params,
+                                  int64_t *ticket);
+
 /* ---- stage entry points (single frame, host memory) ----------------------------------------------------
  * heimdall_core.processing.preprocess_image (processing.rs:30-101): out has (grayscale ? 1 : c) channels;
  * blur_size <= 0 -> no blur.  grayscale != 0 requires c >= 3 (the reference indexes channels 1 and 2). */

@@ -586,3 +586,56 @@ int hvo_morph(const uint8_t *src, int h, int w, int op, int k, uint8_t *dst) {
     free(tmp);
     return HVO_OK;
 }
+
+/* ---- N1: camera pixel formats (see hv_oracle.h) ------------------------------------------------------------------- */
+/* Which neighbourhood average feeds output channel ch at a site of type t:
+ *   0 centre, 1 horizontal pair, 2 vertical pair, 3 cross (4-neighbours), 4 diagonal (4 corners). */
+static const uint8_t k_site[4][3] = {{4, 3, 0}, {0, 3, 4}, {2, 0, 1}, {1, 0, 2}};
+/* site type at (y & 1, x & 1) for RG, GB, GR, BG (derived from cv2 by impulse responses, then checked exhaustively) */
+static const uint8_t k_pat[4][2][2] = {{{0, 2}, {3, 1}}, {{3, 1}, {0, 2}}, {{2, 0}, {1, 3}}, {{1, 3}, {2, 0}}};
+
+int hvo_bayer_to_rgb(const uint8_t *b, int h, int w, int pattern, uint8_t *rgb) {
+    if (h <= 0 || w <= 0 || pattern < 0 || pattern > 3) return HVO_ERR_ARG;
+    if (h < 3 || w < 3) {
+        memset(rgb, 0, (size_t)h * w * 3);
+        return HVO_OK;
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            /* border pixels copy the nearest interior result */
+            int yy = y < 1 ? 1 : (y > h - 2 ? h - 2 : y), xx = x < 1 ? 1 : (x > w - 2 ? w - 2 : x);
+            const uint8_t *p = b + (size_t)yy * w + xx;
+            int v[5];
+            v[0] = p[0];
+            v[1] = (p[-1] + p[1] + 1) >> 1;
+            v[2] = (p[-w] + p[w] + 1) >> 1;
+            v[3] = (p[-1] + p[1] + p[-w] + p[w] + 2) >> 2;
+            v[4] = (p[-w - 1] + p[-w + 1] + p[w - 1] + p[w + 1] + 2) >> 2;
+            const uint8_t *t = k_site[k_pat[pattern][yy & 1][xx & 1]];
+            for (int ch = 0; ch < 3; ch++) rgb[((size_t)y * w + x) * 3 + ch] = (uint8_t)v[t[ch]];
+        }
+    return HVO_OK;
+}
+
+static uint8_t sat_u8(int64_t v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+int hvo_yuyv_to_rgb(const uint8_t *s, int h, int w, uint8_t *rgb) {
+    if (h <= 0 || w <= 0 || (w & 1)) return HVO_ERR_ARG;
+    const int64_t CY = 1220542, CUB = 2116026, CUG = -409993, CVG = -852492, CVR = 1673527, HALF = 1 << 19;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x += 2) {
+            const uint8_t *q = s + ((size_t)y * w + x) * 2; /* Y0 U Y1 V */
+            int64_t u = (int64_t)q[1] - 128, v = (int64_t)q[3] - 128;
+            int64_t ruv = HALF + CVR * v, guv = HALF + CVG * v + CUG * u, buv = HALF + CUB * u;
+            for (int k = 0; k < 2; k++) {
+                int64_t yy = (int64_t)q[2 * k] - 16;
+                if (yy < 0) yy = 0;
+                yy *= CY;
+                uint8_t *o = rgb + ((size_t)y * w + x + k) * 3;
+                o[0] = sat_u8((yy + ruv) >> 20);
+                o[1] = sat_u8((yy + guv) >> 20);
+                o[2] = sat_u8((yy + buv) >> 20);
+            }
+        }
+    return HVO_OK;
+}

@@ -128,6 +128,15 @@ int hvo_gaussian_kernel_q8(int ksize, double sigma, uint16_t *k16);
  * anchor at k/2. op: 0 erode, 1 dilate, 2 open, 3 close. */
 int hvo_morph(const uint8_t *src, int h, int w, int op, int k, uint8_t *dst);
 
+/* N1 (frame feed): camera pixel formats -> interleaved RGB, the conversions named by the reference's
+ * to_opencv_mat (rust/heimdall-camera/src/lib.rs:226-252; note that in the reference itself these branches are
+ * unreachable, the `mat_type` match at :207-216 returns ConversionError for Bayer and YUV frames first).
+ * Semantics = cv2.cvtColor with COLOR_Bayer{RG,GB,GR,BG}2RGB (bilinear, 1-px border replicated from the interior;
+ * frames smaller than 3x3 give zeros) and COLOR_YUV2RGB_YUYV (BT.601 limited range, 20-bit fixed point); pinned
+ * against opencv-python 4.13.0 in tests/golden/cv2_pixfmt.npz.  pattern: 0 RG, 1 GB, 2 GR, 3 BG. */
+int hvo_bayer_to_rgb(const uint8_t *bayer, int h, int w, int pattern, uint8_t *rgb);
+int hvo_yuyv_to_rgb(const uint8_t *yuyv, int h, int w, uint8_t *rgb);
+
 const char *hvo_version(void);
 
 #ifdef __cplusplus

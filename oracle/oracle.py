@@ -102,6 +102,10 @@ def lib() -> C.CDLL:
         L.hvo_gaussian_kernel_q8.restype = C.c_int
         L.hvo_morph.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.hvo_morph.restype = C.c_int
+        L.hvo_bayer_to_rgb.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
+        L.hvo_bayer_to_rgb.restype = C.c_int
+        L.hvo_yuyv_to_rgb.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.hvo_yuyv_to_rgb.restype = C.c_int
         L.hvo_version.restype = C.c_char_p
         _lib = L
     return _lib
@@ -309,4 +313,27 @@ def morph(src, op: int, k: int) -> np.ndarray:
     h, w = src.shape
     out = np.empty((h, w), np.uint8)
     _check(lib().hvo_morph(_p(src), h, w, op, k, _p(out)))
+    return out
+
+
+BAYER_PATTERNS = {"RG": 0, "GB": 1, "GR": 2, "BG": 3}
+
+
+def bayer_to_rgb(bayer, pattern: str) -> np.ndarray:
+    """cv2.cvtColor(bayer, COLOR_Bayer<pattern>2RGB): the conversion rust/heimdall-camera/src/lib.rs:226-245 names."""
+    b = _u8(np.asarray(bayer))
+    if b.ndim != 2:
+        raise OracleError("bayer frame must be (h, w)")
+    out = np.empty(b.shape + (3,), np.uint8)
+    _check(lib().hvo_bayer_to_rgb(_p(b), b.shape[0], b.shape[1], BAYER_PATTERNS[pattern], _p(out)))
+    return out
+
+
+def yuyv_to_rgb(yuyv) -> np.ndarray:
+    """cv2.cvtColor(yuyv, COLOR_YUV2RGB_YUYV) for an (h, w, 2) u8 frame (lib.rs:246-250)."""
+    s = _u8(np.asarray(yuyv))
+    if s.ndim != 3 or s.shape[2] != 2:
+        raise OracleError("YUYV frame must be (h, w, 2)")
+    out = np.empty(s.shape[:2] + (3,), np.uint8)
+    _check(lib().hvo_yuyv_to_rgb(_p(s), s.shape[0], s.shape[1], _p(out)))
     return out

@@ -4,7 +4,7 @@ opencv-python and, for the reference-derived vectors, /root/reference); the test
 touch /root/reference.
 
 Sources of truth:
-  cv2_gaussian.npz / cv2_morph.npz / cv2_ccl.npz : outputs of opencv-python (the reference's real third-party
+  cv2_gaussian.npz / cv2_morph.npz / cv2_ccl.npz / cv2_pixfmt.npz : outputs of opencv-python (the reference's real third-party
       dependency for its Python path; version printed into meta.json) on seeded inputs.
   reference_python.json : outputs of the UNMODIFIED reference Python code imported from /root/reference
       (heimdall/rust_bridge.py RustBridge.detect_contamination -> heimdall/detectors/contamination_detector.py) on
@@ -45,7 +45,28 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def pixfmt():
+    """cv2_pixfmt.npz: camera pixel-format conversions named by rust/heimdall-camera/src/lib.rs:226-252 (next-row N1)."""
+    rng = np.random.default_rng(20261019)
+    d = {}
+    bayer_a = rng.integers(0, 256, (37, 50), dtype=np.uint8)
+    bayer_b = synth.bottle_frame(96, 128, 11, contaminants=2)  # a structured mosaic
+    d["bayer_a"], d["bayer_b"] = bayer_a, bayer_b
+    for pat in ("RG", "GB", "GR", "BG"):
+        code = getattr(cv2, f"COLOR_Bayer{pat}2RGB")
+        d[f"a_{pat}"] = cv2.cvtColor(bayer_a, code)
+        d[f"b_{pat}"] = cv2.cvtColor(bayer_b, code)
+    yuyv = rng.integers(0, 256, (24, 34, 2), dtype=np.uint8)
+    d["yuyv"] = yuyv
+    d["yuyv_rgb"] = cv2.cvtColor(yuyv, cv2.COLOR_YUV2RGB_YUYV)
+    np.savez_compressed(os.path.join(HERE, "cv2_pixfmt.npz"), **d)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pixfmt":
+        pixfmt()
+        return
+    pixfmt()
     rng = np.random.default_rng(20261018)
     meta = {"opencv": cv2.__version__, "numpy": np.__version__}
 
