@@ -407,7 +407,25 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.write_mask = morph ? 0 : 1;
     pp.init_labels = morph ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
-    if (separate_blur) {
+    // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
+    bool gauss_fused = false;
+    if (gauss && pr.blur_ksize <= 15 && !(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) && !getenv("HV_NO_FUSED_GAUSS")) {
+        PreprocessParams gp = pp;
+        gp.gauss_ksize = pr.blur_ksize;
+        for (int t = 0; t < 16; t++) gp.gk[t] = t < pr.blur_ksize ? gk[t] : 0;
+        gp.blur_radius = 0;
+        gp.write_blur = want_blur ? 1 : 0;
+        ProfScope ps(ctx, HV_K_PREPROCESS, st);
+        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
+                         ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
+                         !getenv("HV_NO_PDL");
+        gp.static_sched = pdl ? 0 : 1;
+        HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, gp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &gauss_fused));
+        if (gauss_fused) ctx->launches++;
+    }
+    if (gauss_fused) {
+        // nothing else to do before morphology / CCL
+    } else if (separate_blur) {
         if (gauss) {
             // tightly packed gray required by the simple Gaussian kernels
             if (c == 1 && (b.gray_row_stride != (size_t)w || b.gray_frame_stride != (size_t)h * w))
@@ -433,7 +451,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         pp.blur_radius = fused_box ? 2 : 0;
         pp.write_blur = want_blur ? 1 : 0;
     }
-    {
+    if (!gauss_fused) {
         ProfScope ps(ctx, HV_K_PREPROCESS, st);
         bool used_tma = false;
         // Programmatic dependent launch: if the kernel right before this one on the stream is the previous batch's fused
@@ -452,9 +470,8 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ProfScope ps(ctx, HV_K_MORPH, st);
         int nl = 0;
         HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
-        HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b, st));
-        HV_TRY_CUDA(ctx, launch_rowflags_from_bits(b, st));
-        ctx->launches += nl + 2;
+        HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
+        ctx->launches += nl + 1;
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
     if (fused) {
@@ -475,7 +492,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     ctx->last_labels = b.labels;
     s.view = b;
     s.has_batch = true;
-    s.have_blur = separate_blur || want_blur;
+    s.have_blur = (separate_blur && !gauss_fused) || want_blur;
     s.c = c;
     s.d_input = d_frames;
     return HV_OK;

@@ -52,6 +52,8 @@ struct PreprocessParams {
     int inverse;       // 1: 255 if px < mean - c (detection path); 0: 255 if px > mean - c
     int force_generic; // testing: never take the packed fast path
     int static_sched;  // TMA kernel: static round-robin tile schedule instead of the atomic tile counter
+    int gauss_ksize;   // > 0: the TMA kernel's Gaussian variant blurs with these taps (blur_radius is ignored), k <= 15
+    uint16_t gk[16];   // OpenCV's 8.8 fixed-point kernel, sums to 256
     int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which
                        // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)
 };
@@ -95,6 +97,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s);
+cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
 cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);

@@ -114,7 +114,9 @@ struct Tile {
     static constexpr int BH = TH + 2 * kAdaptHalf;
     static constexpr int VP = BW + 8;  // pitch of s_v in u16 (column i is stored at i + 4; 4 spare on each side)
     static constexpr int G_BYTES = GH * GW;
-    static constexpr int U1_BYTES = (BH * VP * 2 > BH * TW * 2) ? BH * VP * 2 : BH * TW * 2;
+    static constexpr int GR_BYTES = RB > 2 ? GH * BW * 2 : 0;  // Gaussian variant: row-filtered u16 tile, all GH rows
+    static constexpr int U1_BASE = (BH * VP * 2 > BH * TW * 2) ? BH * VP * 2 : BH * TW * 2;
+    static constexpr int U1_BYTES = GR_BYTES > U1_BASE ? GR_BYTES : U1_BASE;
     static constexpr int BL_BYTES = BH * BW;
     static_assert(HX >= 8 && (HX % 8) == 0, "column halo");
     static_assert(TH * TW <= G_BYTES, "s_f must fit inside s_g");
@@ -125,13 +127,11 @@ struct Tile {
 // Packed u16x2 arithmetic: sums of u8 never overflow a 16-bit lane (5x5: 6375, 11x11 of blur: 30855), so plain 32-bit
 // adds/subs act on both lanes at once; VIMNMX.U16x2 gives the lane-wise compare for the threshold test.
 template <int TW, int TH, int HXP, bool NAMED>
-__device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid,
-                                              int cth, uint64_t *empty_bar) {
+__device__ __forceinline__ void fast_blur_rb2(uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid,
+                                              uint64_t *empty_bar) {
     using T = Tile<TW, TH, 2, HXP>;
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
-    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);  // may alias s_g: only written after s_g is dead
     uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(u1_raw);
-    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(u1_raw);
     uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
     static_assert(TW == 128 && TH == 32, "thread mappings below are written for 128x32 tiles");
 
@@ -193,6 +193,16 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
         }
     }
     tile_sync<NAMED>();
+}
+
+// Phases C and D of the fast path: 11x11 window sums of the blurred tile (+ 5-px ring) in s_bl and the threshold test.
+// BWP = pitch of s_bl.
+template <int TW, int TH, int BWP, bool NAMED>
+__device__ __forceinline__ void fast_threshold(uint8_t *f_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid, int cth) {
+    uint8_t(*s_f)[TW] = reinterpret_cast<uint8_t(*)[TW]>(f_raw);
+    uint16_t(*s_h11)[TW] = reinterpret_cast<uint16_t(*)[TW]>(u1_raw);
+    uint8_t(*s_bl)[BWP] = reinterpret_cast<uint8_t(*)[BWP]>(bl_raw);
+    static_assert(TW == 128 && TH == 32, "thread mappings below are written for 128x32 tiles");
     // C. horizontal 11-sums of the blur.  thread = (row, group of 32 output columns) -> 42 x 4 = 168 threads.
     //    output column c uses s_bl[c + 3 .. c + 13]; a group needs bytes 32g + 3 .. 32g + 44 = words 8g .. 8g + 11.
     if (tid < 42 * 4) {
@@ -252,6 +262,62 @@ __device__ __forceinline__ void fast_tile_rb2(uint8_t *g_raw, uint8_t *f_raw, ui
     tile_sync<NAMED>();
 }
 
+// ---- Gaussian variant (A7): cv2.GaussianBlur(k, k, sigma) of the staged tile, k <= 15 ------------------------------
+// OpenCV's CV_8U path: rows in 8.8 fixed point (u16), columns in 16.16, result (s + 32768) >> 16, BORDER_REFLECT_101.
+// The staged box has RB = 7 more rows than the box-blur variant needs, its out-of-image cells have been filled by
+// reflection (see the consumer loop), so both passes are uniform.  Row pass over all GH rows and the BW logical columns
+// into u1 (u16), column pass over the BH rows of the blur ring into s_bl; blur pixels outside the image are 0 (the
+// truncated-window threshold test sums them).  4 outputs per thread-iteration share their taps' loads.
+constexpr int kGaussRB = 7;
+template <int TW, int TH, int HXP, bool NAMED>
+__device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const PreprocessParams &p, uint8_t *g_raw, uint8_t *u1_raw,
+                                                uint8_t *bl_raw, int f, int x0, int y0, int tid, uint64_t *empty_bar) {
+    using T = Tile<TW, TH, kGaussRB, HXP>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint16_t(*s_r)[T::BW] = reinterpret_cast<uint16_t(*)[T::BW]>(u1_raw);
+    uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
+    const int ks = p.gauss_ksize, R = ks >> 1;
+    const int H = b.h, W = b.w;
+    for (int idx = tid; idx < T::GH * (T::BW / 4); idx += 256) {
+        const int r = idx / (T::BW / 4), i = 4 * (idx - r * (T::BW / 4));
+        const uint8_t *src = &s_g[r][T::GOFF + i - R];  // tap t of output j reads src[j + t]
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+        for (int t = 0; t < ks; t++) {
+            const uint32_t w3 = src[t + 3], kk = p.gk[t];
+            a0 += kk * w0, a1 += kk * w1, a2 += kk * w2, a3 += kk * w3;
+            w0 = w1, w1 = w2, w2 = w3;
+        }
+        *reinterpret_cast<uint2 *>(&s_r[r][i]) = make_uint2(min(a0, 65535u) | (min(a1, 65535u) << 16),
+                                                            min(a2, 65535u) | (min(a3, 65535u) << 16));
+    }
+    tile_sync<NAMED>();
+    if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // the gray stage is dead: the producer may refill it
+    for (int idx = tid; idx < T::BH * (T::BW / 4); idx += 256) {
+        const int r = idx / (T::BW / 4), i = 4 * (idx - r * (T::BW / 4));
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int t = 0; t < ks; t++) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(&s_r[r + kGaussRB - R + t][i]);
+            const uint32_t kk = p.gk[t];
+            a0 += kk * (v.x & 0xffffu), a1 += kk * (v.x >> 16), a2 += kk * (v.y & 0xffffu), a3 += kk * (v.y >> 16);
+        }
+        const int gy = y0 - kAdaptHalf + r, gx = x0 - 8 + i;
+        uint32_t o[4] = {min((a0 + 32768u) >> 16, 255u), min((a1 + 32768u) >> 16, 255u), min((a2 + 32768u) >> 16, 255u),
+                         min((a3 + 32768u) >> 16, 255u)};
+        const bool row_in = gy >= 0 && gy < H;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (!row_in || gx + j < 0 || gx + j >= W) o[j] = 0;
+        *reinterpret_cast<uint32_t *>(&s_bl[r][i]) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        if (p.write_blur && row_in && r >= kAdaptHalf && r < kAdaptHalf + TH) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i + j >= 8 && i + j < 8 + TW && gx + j < W) b.blur[((size_t)f * H + gy) * W + gx + j] = (uint8_t)o[j];
+        }
+    }
+    tile_sync<NAMED>();
+}
+
 // Everything after the gray tile (+ halo, zero outside the image) sits in shared memory and the flat decision is known:
 // blur + threshold (fast or generic path) and the three outputs.  Block-uniform control flow; contains barriers.
 template <int TW, int TH, int RB, int HXP, bool NAMED>
@@ -274,9 +340,13 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
 
     if (flat && empty_bar && tid == 0) mbar_arrive(empty_bar);  // every thread is past its flat-test reads of the stage
     if (!flat) {
-        if (RB == 2 && TW == 128 && TH == 32 && interior && p.inverse && !p.write_blur && cth >= 0 && cth <= 255 &&
-            !p.force_generic) {
-            fast_tile_rb2<128, 32, HXP, NAMED>(g_raw, f_raw, u1_raw, bl_raw, tid, cth, empty_bar);
+        const bool fast_thr = TW == 128 && TH == 32 && interior && p.inverse && cth >= 0 && cth <= 255 && !p.force_generic;
+        if (RB == kGaussRB && p.gauss_ksize > 0) {
+            gauss_blur_tile<TW, TH, HXP, NAMED>(b, p, g_raw, u1_raw, bl_raw, f, x0, y0, tid, empty_bar);
+            if (fast_thr) fast_threshold<128, 32, T::BW, NAMED>(f_raw, u1_raw, bl_raw, tid, cth);
+        } else if (RB == 2 && fast_thr && !p.write_blur) {
+            fast_blur_rb2<128, 32, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
+            fast_threshold<128, 32, T::BW, NAMED>(f_raw, u1_raw, bl_raw, tid, cth);
         } else {
             // ---- generic path: any border, any c, either comparison direction --------------------------------------
             // 2. blur over the tile + 5-px ring (zero outside the image, pass-through outside the interior)
@@ -303,6 +373,8 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
             }
             tile_sync<NAMED>();
             if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // last read of the gray stage is behind us
+        }
+        if (!((RB == kGaussRB && p.gauss_ksize > 0) ? fast_thr : (RB == 2 && fast_thr && !p.write_blur))) {
             // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
             for (int idx = tid; idx < T::BH * TW; idx += 256) {
                 const int r = idx / TW, c = idx - r * TW;
@@ -536,9 +608,9 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kTmaStages = 4;  // tiles in flight per CTA: the load of tile k+3 is issued before tile k is processed
 
-template <int TW, int TH>
+template <int TW, int TH, int RB>
 struct TmaSmem {
-    using T = Tile<TW, TH, 2, 16>;  // 16-column halo: TMA boxes must start on a 16-byte boundary
+    using T = Tile<TW, TH, RB, 16>;  // 16-column halo: TMA boxes must start on a 16-byte boundary
     static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
     static constexpr int BYTES = kTmaStages * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
 };
@@ -551,12 +623,13 @@ constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler
 // refill between two tiles: the TMA issue sits behind that thread's own outstanding global stores, and every barrier of
 // the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
 // producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
-template <int TW, int TH>
-__global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, BatchView b,
-                                                                  PreprocessParams p, uint32_t *bits_out,
-                                                                  unsigned int *sched) {
-    using T = typename TmaSmem<TW, TH>::T;
-    constexpr int STAGE = TmaSmem<TW, TH>::STAGE;
+template <int TW, int TH, int RB>
+__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
+                                                                            const __grid_constant__ BatchView b,
+                                                                            const __grid_constant__ PreprocessParams p,
+                                                                            uint32_t *bits_out, unsigned int *sched) {
+    using T = typename TmaSmem<TW, TH, RB>::T;
+    constexpr int STAGE = TmaSmem<TW, TH, RB>::STAGE;
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t full[kTmaStages], empty[kTmaStages];
     __shared__ int4 s_tile[kTmaStages];  // {tile number, frame, tile x, tile y}, decoded once by the producer
@@ -626,7 +699,7 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
     // flat test of a box that lies entirely inside the image: columns [8, 152) of all GH rows as
     //   - 16-byte items over columns [16, 144): 8 per row -> rows 0..31 one per thread, rows 32..45 threads 0..111
     //   - 8-byte edge items (columns 8..15 and 144..151): 2 per row -> threads 128..219
-    static_assert(TW == 128 && TH == 32 && T::GW == 160 && T::GH == 46 && T::GOFF == 8, "flat-test thread mapping");
+    static_assert(TW == 128 && TH == 32 && T::GW == 160 && T::GOFF == 8 && (RB != 2 || T::GH == 46), "flat-test thread mapping");
     const uint32_t ft0 = (uint32_t)((tid >> 3) * T::GW + 16 + (tid & 7) * 16);
     const uint32_t ft1 = (uint32_t)((32 + (tid >> 3)) * T::GW + 16 + (tid & 7) * 16);  // tid < 112
     const uint32_t fte = (uint32_t)((((tid - 128) >> 1)) * T::GW + (((tid - 128) & 1) ? 144 : 8));  // 128 <= tid < 220
@@ -655,7 +728,32 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
         // flatness test straight from shared memory, over the in-image part of the tile + halo
         uint8_t *cur_stage = sm + st * STAGE;
         uint32_t acc = 0;
-        if (try_flat) {
+        if (RB != 2) {
+            // Gaussian variant.  BORDER_REFLECT_101: cells of the box that lie outside the image (TMA zero fill) but within
+            // reach of the filters (RB + 5 <= 12 px) take the value of their mirror image, which is inside the box.
+            uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
+            if (!box_inside) {
+                for (int idx = tid; idx < T::GH * T::GW; idx += kK1Consumers) {
+                    const int r = idx / T::GW, c = idx - r * T::GW;
+                    const int gy = y0 - T::HALO + r, gx = x0 - T::HX + c;
+                    if ((gy < 0 || gy >= H || gx < 0 || gx >= W) && gy >= -T::HALO && gy < H + T::HALO && gx >= -T::HALO &&
+                        gx < W + T::HALO) {
+                        const int sy = gy < 0 ? -gy : (gy >= H ? 2 * (H - 1) - gy : gy);
+                        const int sx = gx < 0 ? -gx : (gx >= W ? 2 * (W - 1) - gx : gx);
+                        s_g[r][c] = s_g[sy - (y0 - T::HALO)][sx - (x0 - T::HX)];
+                    }
+                }
+                tile_sync<true>();
+            }
+            if (try_flat) {  // every row of the box, all its 16-byte items (4 px more than needed on either side)
+                const uint32_t ref4 = 0x01010101u * s_g[T::HALO + TH / 2][T::HX + TW / 2];
+                constexpr int NV = T::GH * (T::GW / 16);
+                for (int idx = tid; idx < NV; idx += kK1Consumers) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(cur_stage + 16 * idx);
+                    absd(v.x, ref4, acc), absd(v.y, ref4, acc), absd(v.z, ref4, acc), absd(v.w, ref4, acc);
+                }
+            }
+        } else if (try_flat) {
             if (box_inside) {
                 const uint32_t ref4 = 0x01010101u * cur_stage[ftref];
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(cur_stage + ft0);
@@ -712,8 +810,8 @@ __global__ void __launch_bounds__(kK1Threads, 4) k_preprocess_tma(const __grid_c
                 *reinterpret_cast<int4 *>(b.rowflags + (size_t)f * b.rf_stride + rowflag_index(y0, tx, tiles_x) + 16 * tid) = z;
             if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
         } else {
-            tile_compute_and_store<TW, TH, 2, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
-                                                        tid, &empty[st]);
+            tile_compute_and_store<TW, TH, RB, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
+                                                         tid, &empty[st]);
         }
         if (b.phase_ns && tid == 0) {  // debug: time per tile split into TMA wait and processing, flat vs non-flat
             unsigned long long t_c;
@@ -793,11 +891,17 @@ int k1_ctas_per_sm() {
 
 // per device, once (hv_create): the TMA kernel's stages need more than the 48 KB static shared-memory limit
 cudaError_t configure_preprocess_tma() {
-    cudaError_t e = cudaFuncSetAttribute(k_preprocess_tma<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TmaSmem<128, 32>::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TmaSmem<128, 32, 2>::BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TmaSmem<128, 32, kGaussRB>::BYTES);
     if (e != cudaSuccess) return e;
     // ask for the largest shared-memory carve-out: residency of these kernels is limited by shared memory, not by L1
-    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_preprocess<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -808,33 +912,35 @@ cudaError_t configure_preprocess_tma() {
 }
 
 // TMA path: 3-D tensor map {w, h, n} over the gray frames, box = tile + halo, zero fill outside the image.
+// p.gauss_ksize > 0 selects the Gaussian variant (A7 fused into K1): same pipeline, RB = 7 rows more halo.
 cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
                                   int num_sms, bool pdl, cudaStream_t s, bool *used) {
     *used = false;
-    using T = Tile<128, 32, 2, 16>;
+    const bool gauss = p.gauss_ksize > 0;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.gray);
-    if (p.blur_radius != 2 || !sched || (base & 15) || (b.gray_row_stride & 15) || (b.gray_frame_stride & 15) || (b.w & 15) ||
-        getenv("HV_K1_NO_TMA"))
+    if ((!gauss && p.blur_radius != 2) || !sched || (base & 15) || (b.gray_row_stride & 15) || (b.gray_frame_stride & 15) ||
+        (b.w & 15) || getenv("HV_K1_NO_TMA"))
         return cudaSuccess;
+    if (gauss && (p.gauss_ksize > 2 * kGaussRB + 1 || !(p.gauss_ksize & 1) || b.h < 16 || b.w < 16)) return cudaSuccess;
     auto enc = tensor_map_encoder();
     if (!enc) return cudaSuccess;
+    const int gh = gauss ? Tile<128, 32, kGaussRB, 16>::GH : Tile<128, 32, 2, 16>::GH;
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)b.w, (cuuint64_t)b.h, (cuuint64_t)b.n};
     const cuuint64_t strides[2] = {(cuuint64_t)b.gray_row_stride, (cuuint64_t)b.gray_frame_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)T::GW, (cuuint32_t)T::GH, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)Tile<128, 32, 2, 16>::GW, (cuuint32_t)gh, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(b.gray), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
-    int grid = num_sms * k1_ctas_per_sm();
+    int grid = num_sms * (gauss ? 3 : k1_ctas_per_sm());
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kK1Threads);
-    cfg.dynamicSmemBytes = TmaSmem<128, 32>::BYTES;
+    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES : TmaSmem<128, 32, 2>::BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -842,7 +948,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     *used = true;
-    return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32>, tmap, b, p, bits_out, sched);
+    if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, p, bits_out, sched);
+    return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, p, bits_out, sched);
 }
 
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s) {

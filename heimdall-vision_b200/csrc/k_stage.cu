@@ -1,6 +1,8 @@
 // k_stage.cu -- the stages around the fused hot kernel: morphology on the bit-packed mask (A8), the OpenCV-exact
 // Gaussian blur (A7), and the single-frame utilities behind heimdall_core.processing.* / process_image
 // (rust/heimdall-core/src/processing.rs).  None of these is on the default (Rust-exact) detect path.
+#include <algorithm>
+
 #include "hv_common.cuh"
 
 namespace hv {
@@ -22,40 +24,124 @@ __device__ __forceinline__ uint32_t load_word(const uint32_t *rowp, int wx, int 
     return v;
 }
 
+// Separable: a k x k rectangle is a 1 x k row window followed by a k x 1 column window (min and max commute with the
+// product structure), and "out of the image never wins" holds per pass.  The first version did the full k x k fold per
+// word (k rows x 2k funnel shifts: 156 us per pass for 16 x 5 MP at k = 15); the two passes cost k shifts + k loads.
 template <bool DILATE>
-__global__ void __launch_bounds__(256) k_morph(const uint32_t *src, uint32_t *dst, int n, int h, int ww, int w,
-                                               int k) {
-    const int a = k / 2;             // anchor
+__global__ void __launch_bounds__(256) k_morph_h(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int n,
+                                                 int h, int ww, int w, int k) {
+    const int a = k / 2;                // anchor
     const int lo = -a, hi = k - 1 - a;  // window offsets [lo, hi]
     const uint32_t tail_mask = (w & 31) ? ((1u << (w & 31)) - 1u) : 0xffffffffu;
+    const size_t total = (size_t)n * h * ww;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int wx = (int)(i % ww);
+        const uint32_t *rowp = src + (i - wx);
+        const uint32_t L = load_word<DILATE>(rowp, wx - 1, ww, tail_mask);
+        const uint32_t M = load_word<DILATE>(rowp, wx, ww, tail_mask);
+        const uint32_t R = load_word<DILATE>(rowp, wx + 1, ww, tail_mask);
+        uint32_t acc = M;
+        for (int dx = 1; dx <= hi; dx++) {  // pixel x + dx
+            const uint32_t t = __funnelshift_r(M, R, dx);
+            acc = DILATE ? (acc | t) : (acc & t);
+        }
+        for (int dx = 1; dx <= -lo; dx++) {  // pixel x - dx
+            const uint32_t t = __funnelshift_l(L, M, dx);
+            acc = DILATE ? (acc | t) : (acc & t);
+        }
+        if (wx == ww - 1) acc &= tail_mask;
+        dst[i] = acc;
+    }
+}
+
+template <bool DILATE>
+__global__ void __launch_bounds__(256) k_morph_v(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int n,
+                                                 int h, int ww, int k) {
+    const int a = k / 2;
+    const int lo = -a, hi = k - 1 - a;
     const size_t words_per_frame = (size_t)h * ww;
     const size_t total = words_per_frame * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t f = i / words_per_frame;
         const int wi = (int)(i - f * words_per_frame);
-        const int y = wi / ww, wx = wi - y * ww;
-        const uint32_t *frame = src + f * words_per_frame;
+        const int y = wi / ww;
+        const int y0 = max(y + lo, 0), y1 = min(y + hi, h - 1);
+        const uint32_t *colp = src + i - (size_t)(y - y0) * ww;
         uint32_t acc = DILATE ? 0u : 0xffffffffu;
-        for (int dy = lo; dy <= hi; dy++) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= h) continue;
-            const uint32_t *rowp = frame + (size_t)yy * ww;
-            const uint32_t L = load_word<DILATE>(rowp, wx - 1, ww, tail_mask);
-            const uint32_t M = load_word<DILATE>(rowp, wx, ww, tail_mask);
-            const uint32_t R = load_word<DILATE>(rowp, wx + 1, ww, tail_mask);
-            uint32_t hacc = M;
-            for (int dx = 1; dx <= hi; dx++) {  // pixel x+dx -> bit position shifts right
-                const uint32_t s = __funnelshift_r(M, R, dx);
-                hacc = DILATE ? (hacc | s) : (hacc & s);
-            }
-            for (int dx = 1; dx <= -lo; dx++) {  // pixel x-dx
-                const uint32_t s = __funnelshift_l(L, M, dx);
-                hacc = DILATE ? (hacc | s) : (hacc & s);
-            }
-            acc = DILATE ? (acc | hacc) : (acc & hacc);
-        }
-        if (wx == ww - 1) acc &= tail_mask;
+        for (int yy = y0; yy <= y1; yy++, colp += ww) acc = DILATE ? (acc | __ldg(colp)) : (acc & __ldg(colp));
         dst[i] = acc;
+    }
+}
+
+// Mask bytes, label-plane initialisation (p + 1 at the first pixel of every word-run, see k_preprocess.cu) and the
+// occupancy records from a bit-packed mask, one 128 x 32 tile per CTA-iteration with the store pattern of K1: all-zero
+// tiles (most of an inspection frame) are nothing but 128-bit zero stores.  Used after morphology.
+__global__ void __launch_bounds__(256) k_expand_bits(BatchView b) {
+    __shared__ uint32_t s_w[32][4];
+    const int tid = threadIdx.x;
+    const int H = b.h, W = b.w;
+    const int tiles_y = (H + 31) / 32;
+    const size_t per_frame = (size_t)tiles_y * b.tiles_x, total = per_frame * b.n;
+    const bool vec = (W & 15) == 0;
+    for (size_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const size_t f = t / per_frame;
+        const int j = (int)(t - f * per_frame);
+        const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
+        const int x0 = tx * 128, y0 = ty * 32;
+        uint32_t word = 0;
+        if (tid < 128) {
+            const int r = tid >> 2, wq = tid & 3;
+            if (y0 + r < H && 4 * tx + wq < b.ww) word = __ldg(b.bits + (f * H + y0 + r) * (size_t)b.ww + 4 * tx + wq);
+            s_w[r][wq] = word;
+            const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+            if (wq == 0 && y0 + r < H && b.rowflags)
+                b.rowflags[f * b.rf_stride + rowflag_index(y0 + r, tx, b.tiles_x)] = (uint8_t)((bal >> (tid & 31)) & 0xfu);
+        }
+        const bool any = __syncthreads_or(word != 0);
+        const size_t pix0 = (f * H + y0) * (size_t)W + x0;
+        if (vec && x0 + 128 <= W) {
+            // one thread per 16 pixels, 128-bit stores throughout
+            const int r = tid >> 3, c16 = (tid & 7) * 16;
+            if (y0 + r < H) {
+                const uint32_t m16 = any ? (s_w[r][c16 >> 5] >> (c16 & 31)) & 0xffffu : 0u;
+                const size_t o = pix0 + (size_t)r * W + c16;
+                uint4 mv;
+                uint32_t *mp = &mv.x;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {  // 4 bits -> 4 bytes of 0x00 / 0xff
+                    const uint32_t nib = (m16 >> (4 * q)) & 0xfu;
+                    mp[q] = (((nib * 0x00204081u) & 0x01010101u) * 0xffu);
+                }
+                *reinterpret_cast<uint4 *>(b.mask + o) = mv;
+                int4 *dst = reinterpret_cast<int4 *>(b.labels + o);
+                if (!m16) {
+                    const int4 z = make_int4(0, 0, 0, 0);
+                    dst[0] = z, dst[1] = z, dst[2] = z, dst[3] = z;
+                } else {
+                    const uint32_t prev = (c16 & 31) ? (s_w[r][c16 >> 5] >> ((c16 & 31) - 1)) & 1u : 0u;
+                    const uint32_t starts = m16 & ~((m16 << 1) | prev);
+                    const int base = (y0 + r) * W + x0 + c16 + 1;
+                    int lab[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) lab[q] = ((starts >> q) & 1u) ? base + q : 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) dst[q] = make_int4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
+                }
+            }
+        } else {
+            for (int idx = tid; idx < 32 * 128; idx += 256) {
+                const int r = idx >> 7, c = idx & 127;
+                const int gy = y0 + r, gx = x0 + c;
+                if (gy >= H || gx >= W) continue;
+                const uint32_t m = s_w[r][c >> 5];
+                const int bit = c & 31;
+                const bool fg = (m >> bit) & 1u;
+                const bool start = fg && (bit == 0 || !((m >> (bit - 1)) & 1u));
+                b.mask[pix0 + (size_t)r * W + c] = fg ? 255 : 0;
+                b.labels[pix0 + (size_t)r * W + c] = start ? (gy * W + gx + 1) : 0;
+            }
+        }
+        __syncthreads();  // s_w is rewritten by the next tile
     }
 }
 
@@ -196,21 +282,20 @@ int grid_for(size_t work_items, int per_block) {
 }  // namespace
 
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s) {
-    // K1 wrote the pre-morphology mask into b.bits; every erode/dilate ping-pongs between bits and bits_tmp and the
-    // chain always has an even number of steps, so the result lands in b.bits again.
+    // K1 wrote the pre-morphology mask into b.bits; every erode/dilate is a row pass into bits_tmp and a column pass back
+    // into bits, so the result lands in b.bits again.
     const size_t total = (size_t)b.n * b.h * b.ww;
     const int grid = grid_for(total, 256);
-    uint32_t *cur = b.bits, *nxt = b.bits_tmp;
     int launches = 0;
     auto step = [&](bool dilate, int k) {
-        if (dilate)
-            k_morph<true><<<grid, 256, 0, s>>>(cur, nxt, b.n, b.h, b.ww, b.w, k);
-        else
-            k_morph<false><<<grid, 256, 0, s>>>(cur, nxt, b.n, b.h, b.ww, b.w, k);
-        uint32_t *t = cur;
-        cur = nxt;
-        nxt = t;
-        launches++;
+        if (dilate) {
+            k_morph_h<true><<<grid, 256, 0, s>>>(b.bits, b.bits_tmp, b.n, b.h, b.ww, b.w, k);
+            k_morph_v<true><<<grid, 256, 0, s>>>(b.bits_tmp, b.bits, b.n, b.h, b.ww, k);
+        } else {
+            k_morph_h<false><<<grid, 256, 0, s>>>(b.bits, b.bits_tmp, b.n, b.h, b.ww, b.w, k);
+            k_morph_v<false><<<grid, 256, 0, s>>>(b.bits_tmp, b.bits, b.n, b.h, b.ww, k);
+        }
+        launches += 2;
     };
     if (open_k > 0) {
         step(false, open_k);
@@ -221,6 +306,12 @@ cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_lau
         step(false, close_k);
     }
     if (n_launches) *n_launches = launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s) {
+    const size_t tiles = (size_t)b.n * ((b.h + 31) / 32) * b.tiles_x;
+    k_expand_bits<<<(int)std::min<size_t>(tiles, 148 * 8), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 

@@ -98,6 +98,19 @@ class hv_camera_frame(C.Structure):
                 ("timestamp_ns", C.c_uint64)]
 
 
+HV_SYNC_FREERUN, HV_SYNC_SOFTWARE, HV_SYNC_HARDWARE = 0, 1, 2
+
+
+class hv_frameset_config(C.Structure):
+    _fields_ = [("n_cameras", C.c_int32), ("sets_per_batch", C.c_int32), ("sync_mode", C.c_int32),
+                ("max_pending_sets", C.c_int32)]
+
+
+class hv_frameset_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("frames_pushed", "sets_completed", "sets_dropped", "frames_dropped",
+                                          "duplicates", "batches_submitted", "max_skew_ns", "sets_pending")]
+
+
 assert C.sizeof(hv_camera_frame) == 48
 assert C.sizeof(hv_defect) == 48 and C.sizeof(hv_frame_result) == 24 and C.sizeof(hv_blob) == 40
 assert C.sizeof(hv_line_stats) == 256
@@ -131,6 +144,13 @@ PROTOTYPES = {
     "hv_frame_channels": (_i32, [_i32]),
     "hv_convert_frame": (_i32, [_vp, _P(hv_camera_frame), _vp, _P(_i32)]),
     "hv_submit_frames": (_i32, [_vp, _P(hv_camera_frame), _i32, _P(hv_params), _P(_i64)]),
+    "hv_frameset_create": (_i32, [_vp, _P(hv_frameset_config), _P(_vp)]),
+    "hv_frameset_destroy": (None, [_vp]),
+    "hv_frameset_last_error": (C.c_char_p, [_vp]),
+    "hv_frameset_push": (_i32, [_vp, _P(hv_camera_frame), _P(hv_params), _P(_i64)]),
+    "hv_frameset_batch_ids": (_i32, [_vp, _i64, _P(C.c_uint64), _i32, _P(_i32)]),
+    "hv_frameset_wait": (_i32, [_vp, _i64, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
+    "hv_frameset_get_stats": (_i32, [_vp, _P(hv_frameset_stats)]),
     "hv_preprocess_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hv_apply_threshold": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_uint8, _i32, _i32, _vp]),
     "hv_find_contours": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _f64, _P(hv_contour), _sz, _P(_sz), _vp]),

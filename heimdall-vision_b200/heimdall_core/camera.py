@@ -86,3 +86,76 @@ def to_image(frame: CameraFrame, detector=None) -> np.ndarray:
     from .batch import default_detector
     det = detector or default_detector()
     return det.convert_frame(frame)
+
+
+class SyncMode(enum.IntEnum):
+    """rust/heimdall-gige/src/sync.rs:18-27."""
+    Freerun = A.HV_SYNC_FREERUN
+    Software = A.HV_SYNC_SOFTWARE
+    Hardware = A.HV_SYNC_HARDWARE
+
+
+class FrameSetBatcher:
+    """N2: groups frames arriving camera by camera into `FrameSet`s (rust/heimdall-gige/src/frame.rs:127-185) and feeds
+    `sets_per_batch` complete sets at a time to the detector (set-major, camera-minor).  `detector=None` gives the
+    dry mode: the batching rules run, nothing is submitted (CPU tests)."""
+
+    def __init__(self, detector, n_cameras: int, sets_per_batch: int = 1, sync_mode: SyncMode = SyncMode.Hardware,
+                 max_pending_sets: int = 0, params=None):
+        import ctypes as C
+        self._C = C
+        self._det = detector
+        self._params = params
+        self.n_cameras, self.sets_per_batch = int(n_cameras), int(sets_per_batch)
+        cfg = A.hv_frameset_config(self.n_cameras, self.sets_per_batch, int(sync_mode), int(max_pending_sets))
+        h = C.c_void_p()
+        st = A.lib.hv_frameset_create(detector._ctx if detector is not None else None, C.byref(cfg), C.byref(h))
+        if st != A.HV_OK:
+            raise ValueError(f"hv_frameset_create: {A.lib.hv_status_string(st).decode()}")
+        self._h = h
+
+    def close(self) -> None:
+        if self._h:
+            A.lib.hv_frameset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def push(self, frame: "CameraFrame") -> int:
+        """Returns the ticket of the batch this frame completed, else 0 (dry mode: -1, -2, ...)."""
+        C = self._C
+        t = C.c_int64(0)
+        fa = frame.as_abi()
+        p = self._params
+        st = A.lib.hv_frameset_push(self._h, C.byref(fa), C.byref(p) if p is not None else None, C.byref(t))
+        if st != A.HV_OK:
+            raise ValueError(A.lib.hv_frameset_last_error(self._h).decode() or A.lib.hv_status_string(st).decode())
+        return t.value
+
+    def batch_ids(self, ticket: int):
+        C = self._C
+        ids = (C.c_uint64 * self.sets_per_batch)()
+        n = C.c_int32(0)
+        st = A.lib.hv_frameset_batch_ids(self._h, ticket, ids, self.sets_per_batch, C.byref(n))
+        if st != A.HV_OK:
+            raise ValueError(A.lib.hv_frameset_last_error(self._h).decode())
+        return [int(ids[k]) for k in range(n.value)]
+
+    def wait(self, ticket: int):
+        """BatchResult of a submitted batch: frame f = set f // n_cameras (see batch_ids), camera f % n_cameras."""
+        from .batch import BatchResult
+        C = self._C
+        n = self.n_cameras * self.sets_per_batch
+        res, dfx, cap = self._det._out_arrays(n, None)
+        total = C.c_size_t(0)
+        st = A.lib.hv_frameset_wait(self._h, ticket, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
+                                    dfx.ctypes.data_as(C.POINTER(A.hv_defect)), cap, C.byref(total))
+        if st not in (A.HV_OK, A.HV_ERR_CAPACITY):
+            raise ValueError(A.lib.hv_frameset_last_error(self._h).decode() or A.lib.hv_status_string(st).decode())
+        return BatchResult(res, dfx[:total.value], st)
+
+    def stats(self) -> Dict[str, int]:
+        s = A.hv_frameset_stats()
+        A.lib.hv_frameset_get_stats(self._h, self._C.byref(s))
+        return {n: int(getattr(s, n)) for n, _ in A.hv_frameset_stats._fields_}

@@ -263,6 +263,44 @@ HV_API hv_status hv_convert_frame(hv_ctx *ctx, const hv_camera_frame *frame, uin
 HV_API hv_status hv_submit_frames(hv_ctx *ctx, const hv_camera_frame *frames, int32_t n, const hv_params *params,
                                   int64_t *ticket);
 
+/* ---- multi-camera frame sets (next-row N2) ------------------------------------------------------------------
+ * `FrameSet` (rust/heimdall-gige/src/frame.rs:127-185): the frames all cameras of the line acquired for one trigger,
+ * built by GigESystem::acquire_frames (rust/heimdall-gige/src/lib.rs:529-648; at most 4 Mono8 cameras, lib.rs:206-234)
+ * under one of the three sync modes of rust/heimdall-gige/src/sync.rs:18-27.  The batcher takes frames as they arrive,
+ * groups them into sets (by trigger number, or by arrival order in Freerun), and submits `sets_per_batch` complete
+ * sets at a time to the detector: frame order inside a batch is set-major, camera-minor. */
+typedef struct hv_frameset hv_frameset;
+enum { HV_SYNC_FREERUN = 0, HV_SYNC_SOFTWARE = 1, HV_SYNC_HARDWARE = 2 };
+typedef struct {
+    int32_t n_cameras;        /* cameras per set, 1..16 (the reference configures up to 4) */
+    int32_t sets_per_batch;   /* complete sets per detector batch */
+    int32_t sync_mode;        /* HV_SYNC_*: Freerun matches the k-th frame of every camera, the others match frame_id */
+    int32_t max_pending_sets; /* incomplete sets kept while cameras are late; the oldest is dropped beyond (0 -> 8) */
+} hv_frameset_config;
+typedef struct {
+    uint64_t frames_pushed;
+    uint64_t sets_completed;
+    uint64_t sets_dropped;   /* incomplete sets given up (a camera never delivered: lib.rs:590-606 fails the set) */
+    uint64_t frames_dropped; /* frames of dropped sets + frames that arrived after their set was gone */
+    uint64_t duplicates;     /* second delivery of the same (set, camera) */
+    uint64_t batches_submitted;
+    uint64_t max_skew_ns;    /* largest timestamp spread inside a completed set */
+    uint64_t sets_pending;   /* open + complete-but-not-yet-batched sets right now */
+} hv_frameset_stats;
+HV_API hv_status hv_frameset_create(hv_ctx *ctx, const hv_frameset_config *cfg, hv_frameset **out);
+HV_API void hv_frameset_destroy(hv_frameset *fs);
+HV_API const char *hv_frameset_last_error(const hv_frameset *fs);
+/* One frame (frame->camera = camera index, frame->frame_id = trigger number).  Its bytes are copied into a page-locked
+ * slab before the call returns.  *ticket = the batch's ticket when this frame completed a batch, else 0. */
+HV_API hv_status hv_frameset_push(hv_frameset *fs, const hv_camera_frame *frame, const hv_params *params,
+                                  int64_t *ticket);
+/* Set ids (trigger numbers / Freerun indices) of a submitted batch, ascending. */
+HV_API hv_status hv_frameset_batch_ids(hv_frameset *fs, int64_t ticket, uint64_t *set_ids, int32_t cap, int32_t *n_sets);
+/* hv_wait for a batch submitted by the batcher (also recycles its slabs): n_cameras * sets_per_batch results. */
+HV_API hv_status hv_frameset_wait(hv_frameset *fs, int64_t ticket, hv_frame_result *results, hv_defect *defects,
+                                  size_t defects_cap, size_t *n_defects_total);
+HV_API hv_status hv_frameset_get_stats(const hv_frameset *fs, hv_frameset_stats *out);
+
 /* ---- stage entry points (single frame, host memory) ----------------------------------------------------
  * heimdall_core.processing.preprocess_image (processing.rs:30-101): out has (grayscale ? 1 : c) channels;
  * blur_size <= 0 -> no blur.  grayscale != 0 requires c >= 3 (the reference indexes channels 1 and 2). */

@@ -310,6 +310,19 @@ def test_gaussian_blur_mode(oracle, detector, golden_dir, k, s):
         assert np.array_equal(got, z[key])  # bit-exact vs cv2 (north star allows +-1 LSB)
 
 
+@pytest.mark.parametrize("k,s", [(3, 0.0), (5, 0.0), (7, 1.0), (11, 0.0), (13, 2.0), (15, 3.0)])
+@pytest.mark.parametrize("shape", [(224, 320), (96, 128), (33, 16), (160, 1296)])
+def test_gaussian_fused_into_k1(oracle, detector, k, s, shape):
+    """16-px aligned frames take the Gaussian variant of the TMA kernel (A7 fused into K1): interior and border tiles,
+    flat and non-flat tiles, reflect-101 borders, a partial last tile column (1296 = 10 x 128 + 16)."""
+    h, w = shape
+    fr = synth.bottle_frame(h, w, 31, contaminants=2)
+    check_frame(oracle, detector, fr[:, :, None], min_size=1.0, gauss=(k, s))
+    rng = np.random.default_rng(k * 100 + h)
+    tex = rng.integers(0, 256, (h, w, 1), dtype=np.uint8)      # every tile non-flat, foreground everywhere
+    check_frame(oracle, detector, tex, min_size=1.0, threshold=5.0, gauss=(k, s), check_blur=(w <= 320))
+
+
 def _gauss_params(k, s):
     import heimdall_core as hc
     return hc.make_params(blur_mode=hc._abi.HV_BLUR_GAUSSIAN, blur_ksize=k, gauss_sigma=s)
