@@ -67,7 +67,7 @@ struct Slot {
     cudaEvent_t done = nullptr;
     DevBuf<uint8_t> in, gray, blur, mask, rowflags;
     DevBuf<uint16_t> gauss_tmp;
-    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, ncomp, fgcount, frame_flags, sched;
+    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
     PinBuf<uint32_t> h_flags;
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
@@ -89,6 +89,7 @@ struct Slot {
     void release() {
         in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release(), rowflags.release();
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
+        segbase.release(), score_state.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
         frame_flags.release(), h_flags.release(), sched.release();
         h_results.release(), h_defects.release(), h_stage.release();
@@ -283,6 +284,14 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     HV_TRY_CUDA(ctx, s.bits_tmp.reserve(words));
     HV_TRY_CUDA(ctx, s.rootbits.reserve(words));
     HV_TRY_CUDA(ctx, s.rankbase.reserve(words));
+    HV_TRY_CUDA(ctx, s.segbase.reserve(2 * (size_t)n * (((size_t)h * ww + 255) / 256)));
+    {
+        const size_t need = (size_t)n * (((size_t)blob_cap_for(ctx, h, w) + 255) / 256 + 1);
+        if (need > s.score_state.cap) {  // all zero between launches: the scoring kernel cleans up after itself
+            HV_TRY_CUDA(ctx, s.score_state.reserve(need));
+            HV_TRY_CUDA(ctx, cudaMemset(s.score_state.p, 0, need * sizeof(uint32_t)));
+        }
+    }
     HV_TRY_CUDA(ctx, s.ncomp.reserve(n));
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
     HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
@@ -374,10 +383,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.labels = d_labels ? d_labels : s.labels.p;
     b.rootbits = s.rootbits.p;
     b.rankbase = s.rankbase.p;
+    b.segbase = s.segbase.p;
+    b.nseg = (int)(((size_t)h * b.ww + 255) / 256);
+    b.score_state = s.score_state.p;
     b.ncomp = s.ncomp.p;
     b.fgcount = s.fgcount.p;
     b.blobs = s.blobs.p;
     b.blob_cap = blob_cap_for(ctx, h, w);
+    b.score_chunks = (b.blob_cap + 255) / 256;
     b.defects = s.defects.p;
     b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p;
@@ -408,7 +421,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.init_labels = morph ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
     // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
-    bool gauss_fused = false;
+    bool gauss_fused = false, k1_tma = false;
     if (gauss && pr.blur_ksize <= 15 && !(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) && !getenv("HV_NO_FUSED_GAUSS")) {
         PreprocessParams gp = pp;
         gp.gauss_ksize = pr.blur_ksize;
@@ -422,6 +435,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         gp.static_sched = pdl ? 0 : 1;
         HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, gp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &gauss_fused));
         if (gauss_fused) ctx->launches++;
+        k1_tma = gauss_fused;
     }
     if (gauss_fused) {
         // nothing else to do before morphology / CCL
@@ -464,6 +478,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
+        k1_tma = used_tma;
         ctx->launches++;
     }
     if (morph) {
@@ -476,7 +491,10 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
     if (fused) {
         ProfScope ps(ctx, HV_K_CCL_FRAME, st);
-        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, st));
+        // launched ahead of K1's completion when K1 (TMA kernel, which releases its dependents at once) is the kernel
+        // right before it on the stream; the kernel waits for K1 itself (griddepcontrol.wait)
+        const bool pdl_tail = k1_tma && !morph && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") && !getenv("HV_NO_PDL_TAIL");
+        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, st));
         ctx->launches += 1;
     } else {
         hv_status rg = enqueue_global_ccl(ctx, b, sp, st);
@@ -1160,7 +1178,9 @@ static void fill_view(hv_ctx *ctx, Slot &s, BatchView &b, int h, int w) {
     b.n = 1, b.h = h, b.w = w, b.ww = (w + 31) / 32;
     b.mask = s.mask.p, b.bits = s.bits.p, b.bits_tmp = s.bits_tmp.p, b.labels = s.labels.p;
     b.rootbits = s.rootbits.p, b.rankbase = s.rankbase.p, b.ncomp = s.ncomp.p, b.fgcount = s.fgcount.p;
+    b.segbase = s.segbase.p, b.nseg = (int)(((size_t)h * b.ww + 255) / 256);
     b.blobs = s.blobs.p, b.blob_cap = blob_cap_for(ctx, h, w);
+    b.score_state = s.score_state.p, b.score_chunks = (b.blob_cap + 255) / 256;
     b.defects = s.defects.p, b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p, b.stats = ctx->d_stats;
     b.frame_flags = s.frame_flags.p, b.frame_select = nullptr;

@@ -28,7 +28,12 @@ struct BatchView {
     size_t rf_stride;          // bytes per frame in rowflags: ceil(h / 32) * tiles_x * 32
     int32_t *labels;           // n*h*w  union-find parents (+1) during CCL, canonical labels afterwards
     uint32_t *rootbits;        // n*h*ww
-    uint32_t *rankbase;        // n*h*ww root counts -> exclusive prefix
+    uint32_t *rankbase;        // n*h*ww: number of roots in the words before this one inside its 256-word segment
+    uint32_t *segbase;         // 2*n*nseg: roots per 256-word segment (K3), then their exclusive prefixes per frame (K4)
+    int nseg;                  // ceil(h*ww / 256)
+    uint32_t *score_state;     // n*(score_chunks+1): per-chunk defect counts of the scoring kernel + a completion counter
+                               // per frame; all zero between launches (the kernel cleans up after itself, see k_score.cu)
+    int score_chunks;          // ceil(blob_cap / 256)
     uint32_t *ncomp;           // n
     uint32_t *fgcount;         // n
     hv_blob *blobs;            // n*blob_cap
@@ -104,7 +109,7 @@ cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s);
 cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s);
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, cudaStream_t s);
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, cudaStream_t s);
 bool ccl_frame_supported(const BatchView &b);
 cudaError_t configure_ccl_frame();
 cudaError_t configure_preprocess_tma();

@@ -107,16 +107,23 @@ __global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
     }
 }
 
+// K3.  One block-iteration per (frame, segment of 256 consecutive words): every node of the segment is pointed at its
+// root, the roots are flagged, and a block scan leaves in rankbase the number of roots in the words before each word
+// inside the segment; the segment's total goes to segbase for K4.
 __global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
-    const size_t words_per_frame = (size_t)b.h * b.ww;
-    const size_t total = words_per_frame * b.n;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t m = b.bits[i];
+    __shared__ uint32_t s_warp[8];
+    const int words_per_frame = b.h * b.ww;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t total = (size_t)b.nseg * b.n;
+    for (size_t si = blockIdx.x; si < total; si += gridDim.x) {
+        const size_t f = si / b.nseg;
+        const int seg = (int)(si - f * b.nseg);
+        if (b.frame_select && !b.frame_select[f]) continue;  // block-uniform
+        const int wi = seg * 256 + tid;
+        const size_t i = f * (size_t)words_per_frame + wi;
+        const uint32_t m = wi < words_per_frame ? b.bits[i] : 0u;
         uint32_t roots = 0;
-        if (b.frame_select && !b.frame_select[i / words_per_frame]) continue;
         if (m) {
-            const size_t f = i / words_per_frame;
-            const int wi = (int)(i - f * words_per_frame);
             const int y = wi / b.ww, wx = wi - y * b.ww;
             int32_t *L = b.labels + f * (size_t)b.h * b.w;
             const int row = y * b.w + wx * 32;
@@ -132,34 +139,55 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
                     L[s] = r + 1;
             }
         }
-        b.rootbits[i] = roots;
-        b.rankbase[i] = __popc(roots);
+        const uint32_t c = __popc(roots);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();  // s_warp of the previous iteration has been read
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            if (w < wid) before += s_warp[w];
+            tot += s_warp[w];
+        }
+        if (wi < words_per_frame) {
+            b.rootbits[i] = roots;
+            b.rankbase[i] = before + incl - c;
+        }
+        if (tid == 0) b.segbase[si] = tot;
     }
 }
 
-// One CTA per frame: exclusive scan of the per-word root counts (raster order), component count, blob-table reset.
-// Each of the 32 warps owns a contiguous chunk of the frame's words and walks it 32 words (128 B, coalesced) at a
-// time.  Only words that contain a root ever have their prefix read back (K5 looks up rankbase[word of the root]), so
-// groups of 32 words without any root are skipped after one load + ballot.
+// K4.  Exclusive scan of the per-segment root counts of a frame -> rank of every root (segbase[segment] +
+// rankbase[word] + roots before it in its word); the canonical label of a component is that rank + 1, the reference's
+// discovery order.  grid = (frames, R): every CTA sums the frame's counts (a few thousand values) to get the component
+// count and resets its share of the blob table; CTA (f, 0) also writes the prefixes, ncomp and fgcount.
 __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const int f = blockIdx.x;
     if (b.frame_select && !b.frame_select[f]) return;
-    const int nwords = b.h * b.ww;
-    uint32_t *cnt = b.rankbase + (size_t)f * nwords;
+    // counts in the first half of segbase, prefixes in the second: the other CTAs of the frame read the counts too
+    const uint32_t *cnt = b.segbase + (size_t)f * b.nseg;
+    uint32_t *pre = b.segbase + ((size_t)b.n + f) * b.nseg;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int groups = (nwords + 31) / 32;              // 32-word groups in the frame
-    const int gper = (groups + 31) / 32;                // groups per warp
-    const int g0 = min(wid * gper, groups), g1 = min(g0 + gper, groups);
+    const int nseg = b.nseg;
+    const int per = (nseg + 1023) / 1024;  // consecutive segments per thread
+    const int i0 = min(tid * per, nseg), i1 = min(i0 + per, nseg);
     uint32_t sum = 0;
-    for (int g = g0; g < g1; g++) {
-        const int i = g * 32 + lane;
-        sum += i < nwords ? cnt[i] : 0u;
-    }
+    for (int i = i0; i < i1; i++) sum += cnt[i];
+    uint32_t incl = sum;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_warp[wid] = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     if (wid == 0) {
         const uint32_t w = s_warp[lane];
@@ -173,30 +201,21 @@ __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
         if (lane == 31) s_total = wi;
     }
     __syncthreads();
-    uint32_t run = s_warp[wid];
-    if (sum) {  // warp-uniform: chunks without roots need no prefixes at all
-        for (int g = g0; g < g1; g++) {
-            const int i = g * 32 + lane;
-            const uint32_t c = i < nwords ? cnt[i] : 0u;
-            if (!__any_sync(0xffffffffu, c != 0)) continue;
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (c) cnt[i] = run + incl - c;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-    }
     const uint32_t ncomp = s_total;
-    if (tid == 0) {
-        b.ncomp[f] = ncomp;
-        b.fgcount[f] = 0;
+    if (blockIdx.y == 0) {
+        uint32_t run = s_warp[wid] + incl - sum;
+        for (int i = i0; i < i1; i++) {
+            pre[i] = run;
+            run += cnt[i];
+        }
+        if (tid == 0) {
+            b.ncomp[f] = ncomp;
+            b.fgcount[f] = 0;
+        }
     }
     hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;
     const uint32_t nb = min(ncomp, (uint32_t)b.blob_cap);
-    for (uint32_t k = tid; k < nb; k += 1024) {
+    for (uint32_t k = blockIdx.y * 1024u + tid; k < nb; k += gridDim.y * 1024u) {
         hv_blob z;
         z.area = 0;
         z.ymin = 0xffffffffu;
@@ -234,6 +253,7 @@ __global__ void __launch_bounds__(256) k_ccl_label(BatchView b) {
         int32_t *L = b.labels + f * (size_t)b.h * b.w;
         const uint32_t *rootbits = b.rootbits + f * words_per_frame;
         const uint32_t *rankbase = b.rankbase + f * words_per_frame;
+        const uint32_t *segbase = b.segbase + ((size_t)b.n + f) * b.nseg;  // the prefixes (second half)
         hv_blob *blobs = b.blobs + f * (size_t)b.blob_cap;
         const int row = y * b.w + wx * 32;
         uint32_t fgsum = __popc(m);
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(256) k_ccl_label(BatchView b) {
                 const int r = L[s] - 1;  // flattened by K3: the root itself
                 const int ry = r / b.w, rx = r - ry * b.w;
                 const int rw = ry * b.ww + (rx >> 5);
-                const uint32_t rank = rankbase[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u));
+                const uint32_t rank = segbase[rw >> 8] + rankbase[rw] + __popc(rootbits[rw] & ((1u << (rx & 31)) - 1u));
                 const int label = (int)rank + 1;
                 for (int k = 0; k < len; k++) L[s + k] = label;
                 const uint32_t xs = wx * 32 + bit, xe = xs + len - 1;
@@ -359,11 +379,12 @@ cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s) {
-    k_ccl_flatten<<<grid_for((size_t)b.n * b.h * b.ww, 256), 256, 0, s>>>(b);
+    k_ccl_flatten<<<grid_for((size_t)b.n * b.nseg * 256, 256), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s) {
-    k_ccl_scan<<<b.n, 1024, 0, s>>>(b);
+    // the blob-table reset is shared by a few CTAs per frame when the table can be large
+    k_ccl_scan<<<dim3(b.n, b.blob_cap > 8192 ? 8 : 1), 1024, 0, s>>>(b);
     return cudaGetLastError();
 }
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s) {

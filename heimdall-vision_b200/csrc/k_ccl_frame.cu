@@ -126,7 +126,13 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
 }
 
 __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams sp) {
-    // let a programmatically dependent kernel (K1 of the next batch, which shares no buffers with this one) start now
+    // Programmatic dependent launch, both ways.  (1) This kernel may have been launched while K1 of its own batch was
+    // still running (its CTAs become resident as K1's CTAs retire): wait until that grid has completed and its stores
+    // are visible.  (2) Then let K1 of the next batch start (it shares no buffers with this batch).  Order matters: a K1
+    // that has started implies every CTA here is past the wait, i.e. K1 of this batch has completed, and that K1 does not
+    // complete before the per-frame kernel of the batch before it has (it waits at its end) -- so the slot the new K1
+    // overwrites is no longer in use.  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
@@ -466,9 +472,18 @@ cudaError_t configure_ccl_frame() {
     return cudaFuncSetAttribute(k_ccl_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem));
 }
 
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, cudaStream_t s) {
-    k_ccl_frame<<<b.n, kFT, sizeof(FrameSmem), s>>>(b, p);
-    return cudaGetLastError();
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(b.n);
+    cfg.blockDim = dim3(kFT);
+    cfg.dynamicSmemBytes = sizeof(FrameSmem);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_ccl_frame, b, p);
 }
 
 }  // namespace hv

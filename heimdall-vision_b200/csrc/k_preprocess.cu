@@ -642,6 +642,9 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(
     unsigned long long t_cta0 = 0;
     if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
 
+    // the per-frame CCL kernel of this batch may be launched now (programmatic dependent launch): its CTAs become
+    // resident as ours retire and wait there for this grid to complete, which takes its launch latency off the step
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < kTmaStages; k++) {
@@ -821,6 +824,10 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(
             atomicAdd(b.phase_ns + 202 + (flat ? 0 : 3), 1ull);
         }
     }
+    // Launched ahead of the previous batch's per-frame CCL kernel's completion (programmatic dependent launch): this grid
+    // must not complete before that one has, because the kernel after us relies on "K1 complete => everything before it
+    // complete" when it lets the next K1 overwrite that batch's buffers (see k_ccl_frame).  A no-op otherwise.
+    if (tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (b.phase_ns && tid == 0) {  // debug: CTA lifetimes
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));

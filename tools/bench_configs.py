@@ -26,6 +26,7 @@ try:
 except Exception:
     pass
 quick = "--quick" in sys.argv
+only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]  # run only the configs whose name contains one
 out_md = next((a for a in sys.argv[1:] if not a.startswith("--")), None)
 st = torch.cuda.current_stream().cuda_stream
 rows = []
@@ -41,6 +42,8 @@ def tile_batch(distinct, n):
 
 
 def run(name, batch, params, okw, steps, check_frames=(0,)):
+    if only and not any(o in name for o in only):
+        return True
     n, h, w = batch.shape
     det = hc.Detector(0, max_defects_per_frame=512 if h * w < 8_000_000 else 32768)
     det.set_stream(st)
@@ -71,6 +74,14 @@ def run(name, batch, params, okw, steps, check_frames=(0,)):
     ms = e0.elapsed_time(e1) / steps
     launches = (det.launch_count() - l0) / steps
     last = det.fetch_results(n)
+    # per-kernel times of the same steps (a separate pass: the events serialise the overlap)
+    det.profile_enable(None)
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    prof = {k: round(v["ms"] / steps, 4) for k, v in det.profile().items() if v["launches"]}
+    det.profile_enable([])
+    print("   per-kernel ms/step:", prof, flush=True)
     fps = n / ms * 1e3
     gbs = 6.0 * n * h * w / ms / 1e6
     rows.append((name, f"{n} x {w}x{h}", "yes" if ok else "NO", f"{ms:.3f}", f"{fps:,.0f}", f"{gbs:,.0f}", f"{gbs / PEAK:.2f}",
