@@ -1,6 +1,7 @@
 // hv_api.cu -- host side of the C ABI (include/heimdall_cuda.h): contexts, device scratch, pinned staging, streams,
 // batch orchestration, result marshalling.  Mirrors the reference's PyO3 layer (rust/heimdall-core/src/lib.rs:42-178)
 // at the granularity a Rust FFI crate would bind.  No CPU fallback anywhere: every result comes from the kernels.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -8,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,23 +24,115 @@ constexpr int kSyncSlots = 2;
 
 thread_local std::string g_create_error;
 
+// driver entry points of the virtual-memory API, resolved through the runtime (no link-time dependency on libcuda)
+template <typename F>
+F drv_fn(const char *name) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<F>(p);
+}
+
+// Device memory with L2 compute-data compression (cuMemCreate + CU_MEM_ALLOCATION_COMP_GENERIC).  The mask and label
+// planes are almost entirely zero; compressed lines cost less DRAM time on their way out of the L2 (measured on the
+// headline batch: step 53.6 -> 49.2 us).  Returns false if the device or driver cannot do it (caller falls back to
+// cudaMalloc).
+struct VmmRec {
+    unsigned long long handle = 0;
+    size_t size = 0;
+    bool compressed = false;
+};
+bool vmm_alloc_compressible(int device, size_t bytes, void **out, VmmRec *rec) {
+    auto f_attr = drv_fn<decltype(&cuDeviceGetAttribute)>("cuDeviceGetAttribute");
+    auto f_gran = drv_fn<decltype(&cuMemGetAllocationGranularity)>("cuMemGetAllocationGranularity");
+    auto f_create = drv_fn<decltype(&cuMemCreate)>("cuMemCreate");
+    auto f_props = drv_fn<decltype(&cuMemGetAllocationPropertiesFromHandle)>("cuMemGetAllocationPropertiesFromHandle");
+    auto f_reserve = drv_fn<decltype(&cuMemAddressReserve)>("cuMemAddressReserve");
+    auto f_map = drv_fn<decltype(&cuMemMap)>("cuMemMap");
+    auto f_access = drv_fn<decltype(&cuMemSetAccess)>("cuMemSetAccess");
+    auto f_release = drv_fn<decltype(&cuMemRelease)>("cuMemRelease");
+    auto f_afree = drv_fn<decltype(&cuMemAddressFree)>("cuMemAddressFree");
+    auto f_unmap = drv_fn<decltype(&cuMemUnmap)>("cuMemUnmap");
+    int sup = 0;
+    if (!(f_attr && f_gran && f_create && f_props && f_reserve && f_map && f_access && f_release && f_afree && f_unmap)) return false;
+    if (getenv("HV_NO_COMPRESSION")) return false;
+    if (f_attr(&sup, CU_DEVICE_ATTRIBUTE_GENERIC_COMPRESSION_SUPPORTED, device) != CUDA_SUCCESS || !sup) return false;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.allocFlags.compressionType = CU_MEM_ALLOCATION_COMP_GENERIC;
+    size_t gran = 0;
+    if (f_gran(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) return false;
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    if (f_create(&h, size, &prop, 0) != CUDA_SUCCESS) return false;
+    CUdeviceptr d = 0;
+    const bool reserved = f_reserve(&d, size, 0, 0, 0) == CUDA_SUCCESS;
+    const bool mapped = reserved && f_map(d, size, 0, h, 0) == CUDA_SUCCESS;
+    CUmemAccessDesc a = {};
+    a.location = prop.location;
+    a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (mapped && f_access(d, size, &a, 1) == CUDA_SUCCESS) {
+        CUmemAllocationProp got = {};
+        f_props(&got, h);
+        rec->handle = (unsigned long long)h;
+        rec->size = size;
+        rec->compressed = got.allocFlags.compressionType == CU_MEM_ALLOCATION_COMP_GENERIC;
+        *out = reinterpret_cast<void *>(d);
+        return true;
+    }
+    if (mapped) f_unmap(d, size);
+    if (reserved) f_afree(d, size);
+    f_release(h);
+    return false;
+}
+void vmm_free(void *p, const VmmRec &rec) {
+    auto f_unmap = drv_fn<decltype(&cuMemUnmap)>("cuMemUnmap");
+    auto f_release = drv_fn<decltype(&cuMemRelease)>("cuMemRelease");
+    auto f_afree = drv_fn<decltype(&cuMemAddressFree)>("cuMemAddressFree");
+    if (!(f_unmap && f_release && f_afree)) return;
+    f_unmap((CUdeviceptr)p, rec.size);
+    f_afree((CUdeviceptr)p, rec.size);
+    f_release((CUmemGenericAllocationHandle)rec.handle);
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;  // elements
+    bool want_compressible = false;  // output planes (mask, labels): try compressible memory first
+    bool vmm = false;
+    VmmRec rec;
+    int device = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        release();
+        if (want_compressible) {
+            void *q = nullptr;
+            if (vmm_alloc_compressible(device, n * sizeof(T), &q, &rec)) {
+                p = static_cast<T *>(q);
+                cap = n;
+                vmm = true;
+                return cudaSuccess;
+            }
+        }
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T));
         if (e == cudaSuccess) cap = n;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (vmm) {
+                cudaDeviceSynchronize();
+                vmm_free(p, rec);
+            } else {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         cap = 0;
+        vmm = false;
     }
 };
 
@@ -137,6 +231,8 @@ struct hv_ctx {
     DevBuf<hv_center> u_centers;
     DevBuf<hv_contour> u_contours;
     DevBuf<uint32_t> u_count;
+    // buffers handed out by hv_device_alloc through the virtual-memory API (compressible memory)
+    std::map<void *, VmmRec> vmm;
 };
 
 namespace {
@@ -720,6 +816,9 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
     const int nslots = kSyncSlots + (ctx->cfg.num_slots > 0 ? ctx->cfg.num_slots : 3);
     ctx->slots.resize(nslots);
     for (auto &s : ctx->slots) {
+        // the slot's own output planes (used when the caller passes no device buffers) live in compressible memory
+        s.mask.want_compressible = s.labels.want_compressible = true;
+        s.mask.device = s.labels.device = device;
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
             g_create_error = "stream/event creation failed";
@@ -763,6 +862,7 @@ void hv_destroy(hv_ctx *ctx) {
     if (ctx->d_phase_ns) cudaFree(ctx->d_phase_ns);
     ctx->u_a.release(), ctx->u_b.release(), ctx->u_c.release();
     ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release();
+    while (!ctx->vmm.empty()) hv_device_free(ctx, ctx->vmm.begin()->first);  // buffers the caller did not return
     delete ctx;
 }
 
@@ -790,6 +890,58 @@ void *hv_host_alloc(hv_ctx *ctx, size_t bytes) {
 void hv_host_free(hv_ctx *ctx, void *p) {
     (void)ctx;
     if (p) cudaFreeHost(p);
+}
+
+hv_status hv_device_alloc(hv_ctx *ctx, size_t bytes, uint32_t flags, void **d_ptr, int32_t *compressed_out) {
+    if (!ctx || !d_ptr || bytes == 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    *d_ptr = nullptr;
+    if (compressed_out) *compressed_out = 0;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    HV_TRY_CUDA(ctx, cudaFree(nullptr));  // make sure the primary context exists before talking to the driver
+    if (flags & HV_ALLOC_COMPRESSIBLE) {
+        VmmRec rec;
+        if (vmm_alloc_compressible(ctx->device, bytes, d_ptr, &rec)) {
+            if (compressed_out) *compressed_out = rec.compressed ? 1 : 0;
+            ctx->vmm[*d_ptr] = rec;
+            return HV_OK;
+        }
+        // not supported / failed: ordinary memory below
+    }
+    HV_TRY_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    return HV_OK;
+}
+
+hv_status hv_device_free(hv_ctx *ctx, void *d_ptr) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    if (!d_ptr) return HV_OK;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
+    auto it = ctx->vmm.find(d_ptr);
+    if (it == ctx->vmm.end()) {
+        HV_TRY_CUDA(ctx, cudaFree(d_ptr));
+        return HV_OK;
+    }
+    vmm_free(d_ptr, it->second);
+    ctx->vmm.erase(it);
+    return HV_OK;
+}
+
+hv_status hv_device_read(hv_ctx *ctx, void *host_dst, const void *d_src, size_t bytes) {
+    if (!ctx || !host_dst || !d_src) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = sync_stream(ctx);
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
+hv_status hv_device_write(hv_ctx *ctx, void *d_dst, const void *host_src, size_t bytes) {
+    if (!ctx || !d_dst || !host_src) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = sync_stream(ctx);
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(d_dst, host_src, bytes, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
 }
 
 hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,

@@ -59,6 +59,9 @@ struct PreprocessParams {
     int static_sched;  // TMA kernel: static round-robin tile schedule instead of the atomic tile counter
     int gauss_ksize;   // > 0: the TMA kernel's Gaussian variant blurs with these taps (blur_radius is ignored), k <= 15
     uint16_t gk[16];   // OpenCV's 8.8 fixed-point kernel, sums to 256
+    int lookahead;      // TMA kernel: tiles the producer runs ahead of the consumers (1..stages), and the same once the
+    int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
+    int tail_tiles;
     int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which
                        // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)
 };

@@ -658,14 +658,20 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(
     if (tid >= kK1Consumers) {
         // ---- producer warp ---------------------------------------------------------------------------------------------
         if (tid != kK1Consumers) return;
-        // dynamic schedule: the number handed out now was requested one fetch earlier, so the round trip of the atomic
-        // overlaps the previous issue; static schedule (kernel launched alone, HV_K1_DYNAMIC unset): round robin
-        int pending = p.static_sched ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
+        // Tiles claimed ahead are tiles no other CTA can take.  A non-flat tile costs four times a flat one, so with every
+        // CTA holding kTmaStages claims (a third of the batch over the whole grid) the CTAs used to finish up to 17 us
+        // apart.  The producer therefore runs `look` tiles ahead of the consumers -- p.lookahead in the steady state,
+        // p.tail_lookahead once the tile numbers handed out are within p.tail_tiles of the end -- and claims a tile only
+        // when it is about to issue its load.  Tile it may be issued once tile it - look has been released; the stage's
+        // own barrier (tile it - kTmaStages) is implied because the consumers release in order.
+        const int tail_from = total - p.tail_tiles;
+        int look = p.lookahead, prev_t = 0;
         for (int it = 0;; it++) {
             const int st = it % kTmaStages;
-            if (it >= kTmaStages) mbar_wait(&empty[st], (uint32_t)(it / kTmaStages - 1) & 1u);
-            const int t = pending;
-            pending = p.static_sched ? pending + (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            if (prev_t >= tail_from) look = p.tail_lookahead;
+            if (it >= look) mbar_wait(&empty[(it - look) % kTmaStages], (uint32_t)((it - look) / kTmaStages) & 1u);
+            const int t = p.static_sched ? (int)blockIdx.x + it * (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            prev_t = t;
             const int f = t / per_frame, r = t - f * per_frame;
             const int ty = r / tiles_x, tx = r - ty * tiles_x;
             // bit 16 of .w: the whole staged box lies inside the image; bit 17: the whole tile lies inside the image
@@ -955,8 +961,15 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     *used = true;
-    if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, p, bits_out, sched);
-    return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, p, bits_out, sched);
+    PreprocessParams q = p;
+    static const int e_look = getenv("HV_K1_LOOKAHEAD") ? atoi(getenv("HV_K1_LOOKAHEAD")) : kTmaStages;
+    static const int e_tlook = getenv("HV_K1_TAIL_LOOKAHEAD") ? atoi(getenv("HV_K1_TAIL_LOOKAHEAD")) : 1;
+    static const int e_trounds = getenv("HV_K1_TAIL_ROUNDS") ? atoi(getenv("HV_K1_TAIL_ROUNDS")) : 4;
+    q.lookahead = e_look < 1 ? 1 : (e_look > kTmaStages ? kTmaStages : e_look);
+    q.tail_lookahead = e_tlook < 1 ? 1 : (e_tlook > q.lookahead ? q.lookahead : e_tlook);
+    q.tail_tiles = e_trounds * grid;
+    if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
+    return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
 
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s) {

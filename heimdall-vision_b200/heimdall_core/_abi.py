@@ -31,6 +31,7 @@ HV_FLAG_GLOBAL_CCL = 16
 HV_FLAG_PHASE_TIMING = 32
 
 HV_BLUR_BOX, HV_BLUR_GAUSSIAN, HV_BLUR_NONE = 0, 1, 2
+HV_ALLOC_COMPRESSIBLE = 1
 HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION = 0, 1
 HV_STATS_AREA_BINS = 16
 HV_K_COUNT = 9
@@ -132,6 +133,10 @@ PROTOTYPES = {
     "hv_set_stream": (_i32, [_vp, _vp, _i32]),
     "hv_host_alloc": (_vp, [_vp, _sz]),
     "hv_host_free": (None, [_vp, _vp]),
+    "hv_device_alloc": (_i32, [_vp, _sz, C.c_uint32, _P(_vp), _P(_i32)]),
+    "hv_device_free": (_i32, [_vp, _vp]),
+    "hv_device_read": (_i32, [_vp, _vp, _vp, _sz]),
+    "hv_device_write": (_i32, [_vp, _vp, _vp, _sz]),
     "hv_detect_batch": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _P(hv_frame_result),
                                _P(hv_defect), _sz, _P(_sz), _P(hv_debug_outputs)]),
     "hv_detect_batch_device": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _vp, _vp,

@@ -231,6 +231,11 @@ class Detector:
         _lib.hv_host_free(self._ctx, ptr)
 
     # ---- device-resident -----------------------------------------------------------------------------------------
+    def device_alloc(self, shape, dtype=np.uint8, compressible: bool = True) -> "DeviceArray":
+        """Device buffer for detect_device / enqueue_device outputs (hv_device_alloc).  compressible=True asks for L2
+        compute-data compression: the mostly-zero mask and label planes then cost less DRAM write time."""
+        return DeviceArray(self, shape, dtype, compressible)
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run on the caller's stream (0 = legacy default stream, e.g. torch's current stream); None = own stream."""
         st = _lib.hv_set_stream(self._ctx, cuda_stream or None, 0 if cuda_stream is None else 1)
@@ -364,6 +369,54 @@ class Detector:
         _lib.hv_profile_get(self._ctx, ms, cnt)
         return {_lib.hv_kernel_name(k).decode(): {"ms": float(ms[k]), "launches": int(cnt[k])}
                 for k in range(A.HV_K_COUNT)}
+
+
+class DeviceArray:
+    """A device buffer owned by a Detector's context: .ptr for the device-resident entry points, .get() / .set() copy."""
+
+    def __init__(self, det: Detector, shape, dtype, compressible: bool):
+        self._det = det
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p, got = C.c_void_p(), C.c_int32(0)
+        st = _lib.hv_device_alloc(det._ctx, self.nbytes, A.HV_ALLOC_COMPRESSIBLE if compressible else 0, C.byref(p), C.byref(got))
+        if st != A.HV_OK:
+            _raise(st, det._ctx)
+        self.ptr = int(p.value)
+        self.compressed = bool(got.value)
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def get(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Copy entries [first, first+count) along axis 0 (default: everything) to a new host array."""
+        count = self.shape[0] - first if count is None else count
+        out = np.empty((count,) + self.shape[1:], self.dtype)
+        row = int(np.prod(self.shape[1:])) * self.dtype.itemsize
+        st = _lib.hv_device_read(self._det._ctx, out.ctypes.data, self.ptr + first * row, out.nbytes)
+        if st != A.HV_OK:
+            _raise(st, self._det._ctx)
+        return out
+
+    def set(self, arr: np.ndarray) -> None:
+        arr = np.ascontiguousarray(arr, self.dtype)
+        if arr.nbytes != self.nbytes:
+            raise ValueError("size mismatch")
+        st = _lib.hv_device_write(self._det._ctx, self.ptr, arr.ctypes.data, arr.nbytes)
+        if st != A.HV_OK:
+            _raise(st, self._det._ctx)
+
+    def free(self) -> None:
+        if self.ptr and self._det._ctx:
+            _lib.hv_device_free(self._det._ctx, self.ptr)
+        self.ptr = 0
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 _default: Dict[int, Detector] = {}

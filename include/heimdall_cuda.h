@@ -182,6 +182,20 @@ HV_API hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream, int32_t enable);
 HV_API void *hv_host_alloc(hv_ctx *ctx, size_t bytes);
 HV_API void hv_host_free(hv_ctx *ctx, void *p);
 
+/* Device buffers for the device-resident entry points (hv_enqueue_device: d_mask / d_labels).  With
+ * HV_ALLOC_COMPRESSIBLE the buffer is created through the virtual-memory API with L2 compute-data compression
+ * (CU_MEM_ALLOCATION_COMP_GENERIC): the mask and label planes of inspection frames are almost entirely zero, the L2
+ * compresses such lines on their way to HBM and the write stream of the preprocess kernel -- 5 of the 6 algorithmic
+ * bytes per pixel -- takes less DRAM time.  Reads (kernels, cudaMemcpy) see ordinary memory.  If the device does not
+ * support compression the flag is ignored; *compressed_out (optional) reports what was obtained.  No counterpart in
+ * the reference (host-only code). */
+enum { HV_ALLOC_COMPRESSIBLE = 1 };
+HV_API hv_status hv_device_alloc(hv_ctx *ctx, size_t bytes, uint32_t flags, void **d_ptr, int32_t *compressed_out);
+HV_API hv_status hv_device_free(hv_ctx *ctx, void *d_ptr);
+/* Blocking copies from / to such a buffer (ordered after the work enqueued so far on the context's stream). */
+HV_API hv_status hv_device_read(hv_ctx *ctx, void *host_dst, const void *d_src, size_t bytes);
+HV_API hv_status hv_device_write(hv_ctx *ctx, void *d_dst, const void *host_src, size_t bytes);
+
 /* ---- the hot path --------------------------------------------------------------------------------------
  * Replaces heimdall_core.detect_contamination (rust/heimdall-core/src/lib.rs:95-143) ->
  * detection::detect_contamination (detection.rs:127-317), for a batch of n frames.

@@ -517,3 +517,52 @@ def test_idempotent_and_batch_invariant(detector):
     assert np.array_equal(a.debug["labels"][1], a.debug["labels"][3])
     assert np.array_equal(a.defects_of(1)[["y", "x", "size", "confidence"]],
                           a.defects_of(3)[["y", "x", "size", "confidence"]])
+
+
+def test_dense_frames_defect_order_across_score_chunks(oracle):
+    """Thousands of blobs per frame: the global-memory path scores them in chunks of 256 on different CTAs and stitches the
+    defect list together with a look-back over the chunk counts -- the list must still be the oracle's, in its order,
+    for every frame of the batch, twice in a row (the chunk counters clean up after themselves)."""
+    import heimdall_core as hc
+    frames = np.stack([synth.high_contamination_frame(1500, 2048, s) for s in (3, 4, 5)])
+    det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=50000)
+    try:
+        for rep in range(2):
+            res = det.detect_batch(frames[..., None], debug=["labels"])
+            for f in range(len(frames)):
+                ref = oracle.detect_contamination(frames[f][:, :, None])
+                assert int(res.frames["n_components"][f]) == ref.ncomp > 2000
+                assert np.array_equal(res.debug["labels"][f], ref.labels)
+                got = [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"]), int(d["label"]))
+                       for d in res.defects_of(f)]
+                exp = [(d["position"], d["size"], d["confidence"]) for d in ref.defects]
+                assert [g[:3] for g in got] == exp and len(got) > 256
+                assert [g[3] for g in got] == sorted(g[3] for g in got)
+    finally:
+        det.close()
+
+
+def test_compressible_device_buffers(oracle, detector):
+    """hv_device_alloc: output planes in L2-compressible memory give the same bytes as ordinary memory; write/read round
+    trip; the flag degrades to plain memory when compression is unavailable."""
+    n, h, w = 4, 256, 384
+    batch = synth.bottle_batch(n, h, w, start_index=900, contaminants=2)
+    d_in = detector.device_alloc((n, h, w), np.uint8, compressible=False)
+    d_in.set(batch)
+    assert np.array_equal(d_in.get(), batch) and not d_in.compressed
+    outs = {}
+    for comp in (False, True):
+        m = detector.device_alloc((n, h, w), np.uint8, compressible=comp)
+        l = detector.device_alloc((n, h, w), np.int32, compressible=comp)
+        l.set(np.full((n, h, w), -7, np.int32))  # stale contents must not survive
+        for rep in range(2):
+            res = detector.detect_device(d_in.ptr, n, h, w, 1, None, m.ptr, l.ptr)
+        outs[comp] = (m.get(), l.get(), res)
+        assert np.array_equal(l.get(1, 2), outs[comp][1][1:3])
+        m.free(), l.free()
+    assert np.array_equal(outs[False][0], outs[True][0]) and np.array_equal(outs[False][1], outs[True][1])
+    for f in range(n):
+        ref = oracle.detect_contamination(batch[f][:, :, None])
+        assert np.array_equal(outs[True][0][f], ref.mask) and np.array_equal(outs[True][1][f], ref.labels)
+        assert [(int(d["y"]), int(d["x"])) for d in outs[True][2].defects_of(f)] == [d["position"] for d in ref.defects]
+    d_in.free()
