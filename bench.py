@@ -267,10 +267,16 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     stats_buf = torch.zeros(hv_dist.STATS_WORDS, dtype=torch.int64, device=dev)
     side = torch.cuda.Stream(device=dev)
 
-    def reduce_stats():
+    def reduce_stats(final=False):
+        """Snapshot of the running line counters -> all-reduce, entirely on the side stream.  The counters are 64-bit
+        atomics that only grow, so a report may be a few microseconds stale but every counter in it is consistent; the
+        launching stream is never touched (an event between two kernels there would serialise K1 behind the per-frame
+        CCL kernel and undo the programmatic-dependent-launch overlap).  final=True orders the snapshot after everything
+        enqueued so far: the totals reported at the end."""
         if world == 1:
             return
-        side.wait_stream(stream)
+        if final:
+            side.wait_stream(stream)
         with torch.cuda.stream(side):
             stats_buf.copy_(stats_view)
             dist.all_reduce(stats_buf)
@@ -380,6 +386,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     if world > 1:
         torch.cuda.synchronize()
+        reduce_stats(final=True)
+        torch.cuda.synchronize()
         total_stats = hv_dist.stats_dict(stats_buf.cpu().numpy())
     else:
         total_stats = {k: v for k, v in det.stats().items() if k != "area_hist"}
@@ -429,7 +437,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "l2_policy": f"inputs rotate over a pool of {pool_n} distinct batches ({pool_n * batch_bytes / 1e6:.0f} MB "
                                 f"> 126 MB L2); each step also writes {5 * batch_bytes / 1e6:.0f} MB of mask+labels",
                    "output_memory": out_mem,
-                   "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B stats all-reduce per step)",
+                   "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B all-reduce of the running line statistics per step on a side stream)",
                    "timed": "K x hv_enqueue_device on one stream, CUDA events on that stream; K1 of step i+1 overlaps the "
                             "per-frame CCL kernel of step i (programmatic dependent launch, alternating output buffers); "
                             "results of every step stay on the device, the last step's are fetched and checked against "

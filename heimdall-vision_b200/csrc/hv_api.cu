@@ -528,7 +528,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
                          ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
-        gp.static_sched = pdl ? 0 : 1;
+        gp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
         HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, gp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &gauss_fused));
         if (gauss_fused) ctx->launches++;
         k1_tma = gauss_fused;
@@ -570,7 +570,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
-        pp.static_sched = (pdl || getenv("HV_K1_DYNAMIC")) ? 0 : 1;
+        pp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));

@@ -64,6 +64,11 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
         : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -606,7 +611,8 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
 // from an atomic counter and the TMA unit loads tile k+1 (zero-filling outside the image) while the threads test, compute
 // and store tile k; no thread ever issues a global load for pixels.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTmaStages = 4;  // tiles in flight per CTA: the load of tile k+3 is issued before tile k is processed
+constexpr int kTmaStages = 2;  // stages per CTA.  4 stages and 4 CTAs per SM ran the headline batch in 49.2 us, 2 stages and 5 CTAs per
+                               // SM (37.9 KB and 40 registers each) in 47.1 us: the kernel is latency-bound, residency wins
 
 template <int TW, int TH, int RB>
 struct TmaSmem {
@@ -624,7 +630,7 @@ constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler
 // the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
 // producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
 template <int TW, int TH, int RB>
-__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 3) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
                                                                             const __grid_constant__ BatchView b,
                                                                             const __grid_constant__ PreprocessParams p,
                                                                             uint32_t *bits_out, unsigned int *sched) {
@@ -685,6 +691,14 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 4 : 3) k_preprocess_tma(
             }
             mbar_expect_tx(&full[st], (uint32_t)T::G_BYTES);
             tma_load_3d(sm + st * STAGE, &tmap, &full[st], tx * TW - T::HX, ty * TH - T::HALO, f);
+            // Tiles are handed out in order, so tile t + prefetch_tiles will be claimed by some CTA a few microseconds
+            // from now: pull its box into the L2 (whoever loads it then finds it there; every tile is prefetched once).
+            if (p.prefetch_tiles > 0 && t + p.prefetch_tiles < total) {
+                const int tp = t + p.prefetch_tiles;
+                const int fp = tp / per_frame, rp = tp - fp * per_frame;
+                const int typ = rp / tiles_x, txp = rp - typ * tiles_x;
+                tma_prefetch_3d(&tmap, txp * TW - T::HX, typ * TH - T::HALO, fp);
+            }
         }
         // the last CTA to finish fetching rearms the scheduler for the next launch
         if (!p.static_sched) {
@@ -894,8 +908,8 @@ int k1_ctas_per_sm() {
     static int v = 0;
     if (!v) {
         const char *e = getenv("HV_K1_CTAS_PER_SM");
-        v = e ? atoi(e) : 4;
-        if (v < 1 || v > 6) v = 4;
+        v = e ? atoi(e) : 5;
+        if (v < 1 || v > 5) v = 5;
     }
     return v;
 }
@@ -968,6 +982,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.lookahead = e_look < 1 ? 1 : (e_look > kTmaStages ? kTmaStages : e_look);
     q.tail_lookahead = e_tlook < 1 ? 1 : (e_tlook > q.lookahead ? q.lookahead : e_tlook);
     q.tail_tiles = e_trounds * grid;
+    static const int e_pref = getenv("HV_K1_PREFETCH") ? atoi(getenv("HV_K1_PREFETCH")) : 0;
+    q.prefetch_tiles = e_pref;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
