@@ -159,7 +159,8 @@ struct PinBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf<uint8_t> in, gray, blur, mask, rowflags;
+    DevBuf<uint8_t> in, gray, blur, mask, rowflags, rowflags_tmp, tile_occ;
+    DevBuf<uint32_t> tile_list;
     DevBuf<uint16_t> gauss_tmp;
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
     PinBuf<uint32_t> h_flags;
@@ -182,6 +183,7 @@ struct Slot {
     int64_t ticket = -1;
     void release() {
         in.release(), gray.release(), blur.release(), mask.release(), gauss_tmp.release(), rowflags.release();
+        rowflags_tmp.release(), tile_occ.release(), tile_list.release();
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
         segbase.release(), score_state.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
@@ -392,8 +394,8 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
     HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
     if (!s.sched.p) {  // K1's tile scheduler: {next tile, CTAs done}; the kernel rearms it itself
-        HV_TRY_CUDA(ctx, s.sched.reserve(2));
-        HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 2 * sizeof(uint32_t)));
+        HV_TRY_CUDA(ctx, s.sched.reserve(8));  // [0..1] K1, [4..6] the fused morphology kernels
+        HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 8 * sizeof(uint32_t)));
     }
     HV_TRY_CUDA(ctx, s.h_flags.reserve(n));
     HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
@@ -513,8 +515,18 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
-    pp.write_mask = morph ? 0 : 1;
-    pp.init_labels = morph ? 0 : 1;
+    // Morphology in the fused kernel (k <= 15): K1 writes mask and labels as usual and the morphology kernel rewrites only
+    // the tiles in reach of foreground.  Multi-pass fallback: K1 writes the bit plane only, everything is expanded later.
+    const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
+    if (morph_fused_plan) {
+        const size_t ntiles = (size_t)n * ((h + 31) / 32) * b.tiles_x;
+        HV_TRY_CUDA(ctx, s.rowflags_tmp.reserve((size_t)n * b.rf_stride));
+        HV_TRY_CUDA(ctx, s.tile_occ.reserve(ntiles * 4));
+        HV_TRY_CUDA(ctx, s.tile_list.reserve(ntiles));
+        b.tile_occ = s.tile_occ.p;
+    }
+    pp.write_mask = (morph && !morph_fused_plan) ? 0 : 1;
+    pp.init_labels = (morph && !morph_fused_plan) ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
     // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
     bool gauss_fused = false, k1_tma = false;
@@ -577,27 +589,45 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         k1_tma = used_tma;
         ctx->launches++;
     }
+    bool morph_fused = false;
     if (morph) {
         ProfScope ps(ctx, HV_K_MORPH, st);
-        int nl = 0;
-        HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
-        HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
-        ctx->launches += nl + 1;
+        if (morph_fused_plan) {
+            // open + close + expansion in one kernel, launched ahead of K1's completion; its result goes to the other
+            // bit plane, which is the one the CCL reads from here on
+            const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !getenv("HV_NO_PDL");
+            HV_TRY_CUDA(ctx, launch_morph_expand(b, pr.morph_open_k, pr.morph_close_k, b.bits_tmp, s.rowflags_tmp.p,
+                                                 s.tile_list.p, s.sched.p + 4, pdl_mid, st));
+            std::swap(b.bits, b.bits_tmp);
+            b.rowflags = s.rowflags_tmp.p;
+            ctx->launches += 2;
+            morph_fused = true;
+        } else {
+            int nl = 0;
+            HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
+            HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
+            ctx->launches += nl + 1;
+        }
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
     if (fused) {
         ProfScope ps(ctx, HV_K_CCL_FRAME, st);
         // launched ahead of K1's completion when K1 (TMA kernel, which releases its dependents at once) is the kernel
         // right before it on the stream; the kernel waits for K1 itself (griddepcontrol.wait)
-        const bool pdl_tail = k1_tma && !morph && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") && !getenv("HV_NO_PDL_TAIL");
+        const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") &&
+                              !getenv("HV_NO_PDL_TAIL");
         HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, st));
         ctx->launches += 1;
     } else {
+        if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
+            HV_TRY_CUDA(ctx, launch_densify_bits(b, st));
+            ctx->launches++;
+        }
         hv_status rg = enqueue_global_ccl(ctx, b, sp, st);
         if (rg != HV_OK) return rg;
     }
     s.used_fused = fused;
-    s.sparse_bits = pp.sparse_aux != 0;
+    s.sparse_bits = pp.sparse_aux != 0 || (morph_fused && fused);  // (fused morphology: tiles out of reach of foreground have no bit words)
     s.score = sp;
     ctx->last_valid = true;
     ctx->last_stream = st;

@@ -26,6 +26,8 @@ struct BatchView {
                                // tile-major: byte (y & 31) of the 32-byte record of tile (y >> 5, tx), see rowflag_index()
     int tiles_x;               // ceil(w / 128)
     size_t rf_stride;          // bytes per frame in rowflags: ceil(h / 32) * tiles_x * 32
+    uint8_t *tile_occ;         // NULL or n * ceil(h/32) * tiles_x * 4: per 128 x 32 tile, byte g = which of the tile's 4 words are
+                               // non-zero in rows 8g..8g+7 (written by K1 when the fused morphology follows)
     int32_t *labels;           // n*h*w  union-find parents (+1) during CCL, canonical labels afterwards
     uint32_t *rootbits;        // n*h*ww
     uint32_t *rankbase;        // n*h*ww: number of roots in the words before this one inside its 256-word segment
@@ -67,6 +69,11 @@ struct PreprocessParams {
                        // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)
 };
 
+// index of tile (tx, ty) of frame f in tile_occ (4 bytes per tile)
+__host__ __device__ inline size_t tile_occ_index(const BatchView &b, size_t f, int tx, int ty) {
+    return (f * ((b.h + 31) / 32) + ty) * b.tiles_x + tx;
+}
+
 // byte offset of the occupancy record of (row y, tile tx) inside a frame's rowflags
 __host__ __device__ inline size_t rowflag_index(int y, int tx, int tiles_x) {
     return ((size_t)(y >> 5) * tiles_x + tx) * 32 + (y & 31);
@@ -107,6 +114,9 @@ cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s);
+bool morph_expand_supported(int open_k, int close_k);
+cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uint32_t *bits_out, uint8_t *rowflags_out,
+                                uint32_t *tile_list, unsigned int *ctrl, bool pdl, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
 cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);

@@ -19,6 +19,8 @@
 // plus halo, no pixel of the tile can satisfy blur < mean - c and the tile is written as zeros without computing
 // the sums.  On bottle frames most tiles are flat, which makes this kernel HBM-bound: 1 B/px read, 5.125 B/px written.
 #include <cuda.h>
+
+#include <algorithm>
 #include <cudaTypedefs.h>
 
 #include "hv_common.cuh"
@@ -433,6 +435,8 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         }
         if (b.rowflags && tid < TH && y0 + tid < H)
             b.rowflags[(size_t)f * b.rf_stride + rowflag_index(y0 + tid, tile_x, b.tiles_x)] = 0;
+        if (b.tile_occ && tid == 0)
+            *reinterpret_cast<uint32_t *>(b.tile_occ + 4 * tile_occ_index(b, f, tile_x, y0 / TH)) = 0u;
         return;
     }
     if (x0 + TW <= W && (W & 15) == 0) {
@@ -514,6 +518,13 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
         if (b.rowflags && wq == 0 && gy < H)
             b.rowflags[(size_t)f * b.rf_stride + rowflag_index(gy, tile_x, b.tiles_x)] =
                 (uint8_t)((bal >> (tid & 31)) & 0xfu);
+        // tile occupancy for the morphology scan: one byte per group of 8 rows (= this warp), bit k = word k non-zero
+        if (b.tile_occ && (tid & 31) == 0) {
+            uint32_t o = bal | (bal >> 16);
+            o |= o >> 8;
+            o |= o >> 4;
+            b.tile_occ[4 * tile_occ_index(b, f, tile_x, y0 / TH) + (tid >> 5)] = (uint8_t)(o & 0xfu);
+        }
     }
 }
 
@@ -630,7 +641,7 @@ constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler
 // the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
 // producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
 template <int TW, int TH, int RB>
-__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 3) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
                                                                             const __grid_constant__ BatchView b,
                                                                             const __grid_constant__ PreprocessParams p,
                                                                             uint32_t *bits_out, unsigned int *sched) {
@@ -831,6 +842,7 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 3) k_preprocess_tma(
             // only the fused per-frame CCL kernel reads this batch (it never looks at unflagged words).
             if (b.rowflags && tid < 2)
                 *reinterpret_cast<int4 *>(b.rowflags + (size_t)f * b.rf_stride + rowflag_index(y0, tx, tiles_x) + 16 * tid) = z;
+            if (b.tile_occ && tid == 2) *reinterpret_cast<uint32_t *>(b.tile_occ + 4 * tile_occ_index(b, f, tx, ty)) = 0u;
             if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
         } else {
             tile_compute_and_store<TW, TH, RB, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
@@ -962,7 +974,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
-    int grid = num_sms * (gauss ? 3 : k1_ctas_per_sm());
+    static const int gauss_ctas = getenv("HV_K1_GAUSS_CTAS") ? std::max(1, std::min(4, atoi(getenv("HV_K1_GAUSS_CTAS")))) : 4;
+    int grid = num_sms * (gauss ? gauss_ctas : k1_ctas_per_sm());
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -73,21 +73,71 @@ __global__ void __launch_bounds__(256) k_morph_v(const uint32_t *__restrict__ sr
     }
 }
 
-// Mask bytes, label-plane initialisation (p + 1 at the first pixel of every word-run, see k_preprocess.cu) and the
-// occupancy records from a bit-packed mask, one 128 x 32 tile per CTA-iteration with the store pattern of K1: all-zero
-// tiles (most of an inspection frame) are nothing but 128-bit zero stores.  Used after morphology.
+// Mask bytes and label-plane initialisation (p + 1 at the first pixel of every word-run, see k_preprocess.cu) of one
+// 128 x 32 tile from its bit-packed rows s_w[32][4], with the store pattern of K1: all-zero tiles (most of an
+// inspection frame) are nothing but 128-bit zero stores.
+__device__ __forceinline__ void expand_tile(const BatchView &b, size_t f, int tx, int ty, const uint32_t (*s_w)[4], bool any,
+                                            int tid) {
+    const int H = b.h, W = b.w;
+    const int x0 = tx * 128, y0 = ty * 32;
+    const size_t pix0 = (f * H + y0) * (size_t)W + x0;
+    if ((W & 15) == 0 && x0 + 128 <= W) {
+        // one thread per 16 pixels, 128-bit stores throughout
+        const int r = tid >> 3, c16 = (tid & 7) * 16;
+        if (y0 + r < H) {
+            const uint32_t m16 = any ? (s_w[r][c16 >> 5] >> (c16 & 31)) & 0xffffu : 0u;
+            const size_t o = pix0 + (size_t)r * W + c16;
+            uint4 mv;
+            uint32_t *mp = &mv.x;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 4 bits -> 4 bytes of 0x00 / 0xff
+                const uint32_t nib = (m16 >> (4 * q)) & 0xfu;
+                mp[q] = (((nib * 0x00204081u) & 0x01010101u) * 0xffu);
+            }
+            *reinterpret_cast<uint4 *>(b.mask + o) = mv;
+            int4 *dst = reinterpret_cast<int4 *>(b.labels + o);
+            if (!m16) {
+                const int4 z = make_int4(0, 0, 0, 0);
+                dst[0] = z, dst[1] = z, dst[2] = z, dst[3] = z;
+            } else {
+                const uint32_t prev = (c16 & 31) ? (s_w[r][c16 >> 5] >> ((c16 & 31) - 1)) & 1u : 0u;
+                const uint32_t starts = m16 & ~((m16 << 1) | prev);
+                const int base = (y0 + r) * W + x0 + c16 + 1;
+                int lab[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) lab[q] = ((starts >> q) & 1u) ? base + q : 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) dst[q] = make_int4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < 32 * 128; idx += 256) {
+            const int r = idx >> 7, c = idx & 127;
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy >= H || gx >= W) continue;
+            const uint32_t m = any ? s_w[r][c >> 5] : 0u;
+            const int bit = c & 31;
+            const bool fg = (m >> bit) & 1u;
+            const bool start = fg && (bit == 0 || !((m >> (bit - 1)) & 1u));
+            b.mask[pix0 + (size_t)r * W + c] = fg ? 255 : 0;
+            b.labels[pix0 + (size_t)r * W + c] = start ? (gy * W + gx + 1) : 0;
+        }
+    }
+}
+
+// Mask, labels and occupancy records from a bit-packed mask, one 128 x 32 tile per CTA-iteration.  Used after the
+// multi-pass morphology (kernel sizes above 15).
 __global__ void __launch_bounds__(256) k_expand_bits(BatchView b) {
     __shared__ uint32_t s_w[32][4];
     const int tid = threadIdx.x;
-    const int H = b.h, W = b.w;
+    const int H = b.h;
     const int tiles_y = (H + 31) / 32;
     const size_t per_frame = (size_t)tiles_y * b.tiles_x, total = per_frame * b.n;
-    const bool vec = (W & 15) == 0;
     for (size_t t = blockIdx.x; t < total; t += gridDim.x) {
         const size_t f = t / per_frame;
         const int j = (int)(t - f * per_frame);
         const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
-        const int x0 = tx * 128, y0 = ty * 32;
+        const int y0 = ty * 32;
         uint32_t word = 0;
         if (tid < 128) {
             const int r = tid >> 2, wq = tid & 3;
@@ -98,50 +148,240 @@ __global__ void __launch_bounds__(256) k_expand_bits(BatchView b) {
                 b.rowflags[f * b.rf_stride + rowflag_index(y0 + r, tx, b.tiles_x)] = (uint8_t)((bal >> (tid & 31)) & 0xfu);
         }
         const bool any = __syncthreads_or(word != 0);
-        const size_t pix0 = (f * H + y0) * (size_t)W + x0;
-        if (vec && x0 + 128 <= W) {
-            // one thread per 16 pixels, 128-bit stores throughout
-            const int r = tid >> 3, c16 = (tid & 7) * 16;
-            if (y0 + r < H) {
-                const uint32_t m16 = any ? (s_w[r][c16 >> 5] >> (c16 & 31)) & 0xffffu : 0u;
-                const size_t o = pix0 + (size_t)r * W + c16;
-                uint4 mv;
-                uint32_t *mp = &mv.x;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {  // 4 bits -> 4 bytes of 0x00 / 0xff
-                    const uint32_t nib = (m16 >> (4 * q)) & 0xfu;
-                    mp[q] = (((nib * 0x00204081u) & 0x01010101u) * 0xffu);
-                }
-                *reinterpret_cast<uint4 *>(b.mask + o) = mv;
-                int4 *dst = reinterpret_cast<int4 *>(b.labels + o);
-                if (!m16) {
-                    const int4 z = make_int4(0, 0, 0, 0);
-                    dst[0] = z, dst[1] = z, dst[2] = z, dst[3] = z;
-                } else {
-                    const uint32_t prev = (c16 & 31) ? (s_w[r][c16 >> 5] >> ((c16 & 31) - 1)) & 1u : 0u;
-                    const uint32_t starts = m16 & ~((m16 << 1) | prev);
-                    const int base = (y0 + r) * W + x0 + c16 + 1;
-                    int lab[16];
-#pragma unroll
-                    for (int q = 0; q < 16; q++) lab[q] = ((starts >> q) & 1u) ? base + q : 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) dst[q] = make_int4(lab[4 * q], lab[4 * q + 1], lab[4 * q + 2], lab[4 * q + 3]);
-                }
-            }
-        } else {
-            for (int idx = tid; idx < 32 * 128; idx += 256) {
-                const int r = idx >> 7, c = idx & 127;
-                const int gy = y0 + r, gx = x0 + c;
-                if (gy >= H || gx >= W) continue;
-                const uint32_t m = s_w[r][c >> 5];
-                const int bit = c & 31;
-                const bool fg = (m >> bit) & 1u;
-                const bool start = fg && (bit == 0 || !((m >> (bit - 1)) & 1u));
-                b.mask[pix0 + (size_t)r * W + c] = fg ? 255 : 0;
-                b.labels[pix0 + (size_t)r * W + c] = start ? (gy * W + gx + 1) : 0;
+        expand_tile(b, f, tx, ty, s_w, any, tid);
+        __syncthreads();  // s_w is rewritten by the next tile
+    }
+}
+
+// A8 in one pass (kernel sizes up to 15): K1 left the pre-morphology mask bit-packed; a CTA stages the words of a
+// 128 x 32 tile plus the reach of open followed by close (at most 28 pixels = 28 rows and one word on either side:
+// 88 x 6 words, 2 KB), runs the separable passes Eh Ev Dh Dv (open) Dh Dv Eh Ev (close) between two shared-memory
+// buffers and expands the centre into the mask bytes, the label plane, the final bit-mask (bits_out, a buffer other
+// than the input: neighbouring CTAs still read the original) and the occupancy records -- 5.1 B/px written once, where
+// the multi-pass version re-read and re-wrote the bit plane eight times and expanded it in a ninth kernel.  A staged
+// region without a set bit yields an empty tile (no pass can create foreground out of nothing), which is the common
+// case and costs one 2 KB read and the zero stores.  "Out of the image never wins" (OpenCV's default border) is applied
+// when a pass READS a word: bits outside the image count as 1 for erode and 0 for dilate, whatever the previous pass
+// left there.  Garbage entering from outside the staged region travels at most the reach and never gets to the centre.
+constexpr int kMorphReach = 28;
+constexpr int kMorphRows = 32 + 2 * kMorphReach;
+constexpr int kMorphCols = 6;
+
+// One separable pass over the staged rows [r_lo, r_hi): window [-lo, +hi] along the row (H) or the column (V).
+template <bool DILATE>
+__device__ __forceinline__ void morph_pass_h(const uint32_t (*src)[kMorphCols], uint32_t (*dst)[kMorphCols], int lo, int hi,
+                                             int r_lo, int r_hi, int tid, int y0, int wx0, int H, int ww, uint32_t tail_mask) {
+    const uint32_t ident = DILATE ? 0u : 0xffffffffu;
+    for (int idx = tid; idx < (r_hi - r_lo) * kMorphCols; idx += 256) {
+        const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
+        const int gy = y0 - kMorphReach + r;
+        const bool row_in = gy >= 0 && gy < H;
+        auto rd = [&](int cc) -> uint32_t {
+            if (cc < 0 || cc >= kMorphCols) return ident;
+            const int gwx = wx0 + cc;
+            const uint32_t inm = (!row_in || gwx < 0 || gwx >= ww) ? 0u : (gwx == ww - 1 ? tail_mask : 0xffffffffu);
+            const uint32_t v = src[r][cc];
+            return DILATE ? (v & inm) : (v | ~inm);
+        };
+        const uint32_t L = rd(c - 1), M = rd(c), R = rd(c + 1);
+        uint32_t acc = M;
+        for (int dx = 1; dx <= hi; dx++) {
+            const uint32_t t = __funnelshift_r(M, R, dx);
+            acc = DILATE ? (acc | t) : (acc & t);
+        }
+        for (int dx = 1; dx <= lo; dx++) {
+            const uint32_t t = __funnelshift_l(L, M, dx);
+            acc = DILATE ? (acc | t) : (acc & t);
+        }
+        dst[r][c] = acc;
+    }
+}
+
+template <bool DILATE>
+__device__ __forceinline__ void morph_pass_v(const uint32_t (*src)[kMorphCols], uint32_t (*dst)[kMorphCols], int lo, int hi,
+                                             int r_lo, int r_hi, int tid, int y0, int wx0, int H, int ww, uint32_t tail_mask) {
+    for (int idx = tid; idx < (r_hi - r_lo) * kMorphCols; idx += 256) {
+        const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
+        const int gwx = wx0 + c;
+        const uint32_t colm = (gwx < 0 || gwx >= ww) ? 0u : (gwx == ww - 1 ? tail_mask : 0xffffffffu);
+        uint32_t acc = DILATE ? 0u : 0xffffffffu;
+        // rows outside [r_lo, r_hi) were not staged: whatever they hold cannot reach the centre
+        const int a_lo = max(r - lo, r_lo), a_hi = min(r + hi, r_hi - 1);
+        for (int rr = a_lo; rr <= a_hi; rr++) {
+            const int gy = y0 - kMorphReach + rr;
+            const uint32_t inm = (gy >= 0 && gy < H) ? colm : 0u;
+            const uint32_t v = src[rr][c];
+            acc = DILATE ? (acc | (v & inm)) : (acc & (v | ~inm));
+        }
+        dst[r][c] = acc;
+    }
+}
+
+// Which tiles can open + close change at all?  Only those with foreground within reach.  K1 left 4 bytes per tile (byte g:
+// which of the tile's 4 words are non-zero in rows 8g..8g+7); one thread per tile looks at its 3 x 3 neighbourhood --
+// of the tiles to the left only the last word matters (reach < 32 px), of those to the right the first, of the tiles above
+// and below the row groups within reach -- and appends the tile to a work list (warp-aggregated).  A tile that is not
+// listed keeps what K1 wrote for it (zeros: its own mask is empty); its occupancy record for the CCL is zeroed here.
+__global__ void __launch_bounds__(256) k_morph_scan(BatchView b, int reach, uint8_t *rowflags_out, uint32_t *tile_list,
+                                                    unsigned int *ctrl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // K1 may still be running (programmatic dependent launch)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tiles_y = (b.h + 31) / 32;
+    const size_t per_frame = (size_t)tiles_y * b.tiles_x, total = per_frame * b.n;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool busy = false;
+    if (t < total) {
+        const size_t f = t / per_frame;
+        const int j = (int)(t - f * per_frame);
+        const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
+        const uint32_t *occ = reinterpret_cast<const uint32_t *>(b.tile_occ) + f * per_frame;
+        // row groups of the neighbours above / below that lie within reach: group g of the tile above is 25 - 8g rows
+        // away (its last row), group g of the tile below 8g + 1
+        uint32_t up_rows = 0, down_rows = 0;
+        for (int g = 0; g < 4; g++) {
+            if (25 - 8 * g <= reach) up_rows |= 0xffu << (8 * g);
+            if (8 * g + 1 <= reach) down_rows |= 0xffu << (8 * g);
+        }
+        uint32_t acc = 0;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int ny = ty + dy;
+            if (ny < 0 || ny >= tiles_y) continue;
+            const uint32_t rows = dy < 0 ? up_rows : (dy > 0 ? down_rows : 0xffffffffu);
+            for (int dx = -1; dx <= 1; dx++) {
+                const int nx = tx + dx;
+                if (nx < 0 || nx >= b.tiles_x) continue;
+                const uint32_t cols = dx < 0 ? 0x08080808u : (dx > 0 ? 0x01010101u : 0x0f0f0f0fu);
+                acc |= __ldg(occ + (size_t)ny * b.tiles_x + nx) & rows & cols;
             }
         }
-        __syncthreads();  // s_w is rewritten by the next tile
+        busy = acc != 0;
+        if (!busy) {
+            int4 *rec = reinterpret_cast<int4 *>(rowflags_out + f * b.rf_stride + rowflag_index(ty * 32, tx, b.tiles_x));
+            rec[0] = make_int4(0, 0, 0, 0);
+            rec[1] = make_int4(0, 0, 0, 0);
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, busy);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(ctrl, (unsigned int)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (busy) tile_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)t;
+    }
+}
+
+// A8 for the listed tiles: persistent CTAs take entries of the work list through an atomic cursor (requested one
+// iteration ahead, so its round trip is never waited for).  ctrl = {list length, cursor, CTAs done}; the last CTA to
+// finish rearms all three for the next launch.
+__global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, int close_k, uint32_t *bits_out,
+                                                     uint8_t *rowflags_out, const uint32_t *tile_list, unsigned int *ctrl) {
+    __shared__ uint32_t s_a[kMorphRows][kMorphCols], s_b[kMorphRows][kMorphCols];
+    __shared__ uint32_t s_w[32][4];
+    __shared__ unsigned int s_next[2];
+    const int tid = threadIdx.x;
+    const int H = b.h, W = b.w, WW = b.ww;
+    const int tiles_y = (H + 31) / 32;
+    const size_t per_frame = (size_t)tiles_y * b.tiles_x;
+    const uint32_t tail_mask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xffffffffu;
+    // window [-lo, +hi] of the two kernel sizes (anchor k/2, as cv2), and the staged rows: the tile plus what open + close
+    // can reach (4 rows for two 3 x 3 kernels, 28 for two 15 x 15 ones)
+    const int lo_o = open_k > 0 ? open_k / 2 : 0, hi_o = open_k > 0 ? open_k - 1 - open_k / 2 : 0;
+    const int lo_c = close_k > 0 ? close_k / 2 : 0, hi_c = close_k > 0 ? close_k - 1 - close_k / 2 : 0;
+    const int reach = min(kMorphReach, 2 * max(lo_o, hi_o) + 2 * max(lo_c, hi_c));
+    const int r_lo = kMorphReach - reach, r_hi = kMorphReach + 32 + reach;
+    const int n_staged = (r_hi - r_lo) * kMorphCols;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the scan (and K1 before it) have completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const unsigned int count = *reinterpret_cast<volatile unsigned int *>(ctrl);
+    unsigned int pending = 0;
+    if (tid == 0) {
+        s_next[0] = atomicAdd(ctrl + 1, 1u);
+        pending = atomicAdd(ctrl + 1, 1u);
+    }
+    __syncthreads();
+    unsigned int cur = s_next[0];
+    for (int it = 1; cur < count; it++) {
+        if (tid == 0) {
+            s_next[it & 1] = pending;
+            if (pending < count) pending = atomicAdd(ctrl + 1, 1u);
+        }
+        const size_t t = tile_list[cur];
+        const size_t f = t / per_frame;
+        const int j = (int)(t - f * per_frame);
+        const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
+        const int y0 = ty * 32, wx0 = tx * 4 - 1;
+        const uint32_t *fb = b.bits + f * (size_t)H * WW;
+        // all loads of the thread first, then the shared-memory stores: one global-memory latency per tile
+        uint32_t v[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int idx = tid + 256 * q;
+            const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
+            const int gy = y0 - kMorphReach + r, gwx = wx0 + c;
+            v[q] = 0;
+            if (idx < n_staged && gy >= 0 && gy < H && gwx >= 0 && gwx < WW) {
+                v[q] = __ldg(fb + (size_t)gy * WW + gwx);
+                if (gwx == WW - 1) v[q] &= tail_mask;
+            }
+        }
+        __syncthreads();  // the previous tile's readers of s_a / s_b / s_w are done; s_next[it & 1] is published
+        const unsigned int nxt = s_next[it & 1];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int idx = tid + 256 * q;
+            if (idx < n_staged) s_a[r_lo + idx / kMorphCols][idx % kMorphCols] = v[q];
+        }
+        const bool any = __syncthreads_or((v[0] | v[1] | v[2]) != 0);  // also: s_a complete
+        if (any) {
+            const uint32_t(*src)[kMorphCols] = s_a;
+            uint32_t(*dst)[kMorphCols] = s_b;
+            auto flip = [&]() {
+                __syncthreads();
+                const uint32_t(*tsrc)[kMorphCols] = dst;
+                dst = const_cast<uint32_t(*)[kMorphCols]>(src);
+                src = tsrc;
+            };
+            // open = erode, dilate; close = dilate, erode.  The two dilations in the middle are one dilation with the
+            // summed window (a maximum over in-image pixels of a maximum over in-image pixels, and the image is convex).
+            if (open_k > 0) {
+                morph_pass_h<false>(src, dst, lo_o, hi_o, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+                morph_pass_v<false>(src, dst, lo_o, hi_o, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+            }
+            morph_pass_h<true>(src, dst, lo_o + lo_c, hi_o + hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+            morph_pass_v<true>(src, dst, lo_o + lo_c, hi_o + hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+            if (close_k > 0) {
+                morph_pass_h<false>(src, dst, lo_c, hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+                morph_pass_v<false>(src, dst, lo_c, hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+            }
+            if (tid < 128) {
+                const int r = tid >> 2, wq = tid & 3;
+                const int gwx = 4 * tx + wq;
+                uint32_t w = src[kMorphReach + r][1 + wq];
+                if (y0 + r >= H || gwx >= WW) w = 0;
+                else if (gwx == WW - 1) w &= tail_mask;
+                s_w[r][wq] = w;
+            }
+            __syncthreads();
+        }
+        // final bit-mask words + occupancy records (a second set of records and a second bit plane: other CTAs still
+        // read K1's), then the mask bytes and the label plane of the tile
+        uint32_t word = 0;
+        if (tid < 128) {
+            const int r = tid >> 2, wq = tid & 3;
+            if (any) word = s_w[r][wq];
+            if (y0 + r < H && 4 * tx + wq < WW) bits_out[(f * H + y0 + r) * (size_t)WW + 4 * tx + wq] = word;
+            const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+            if (wq == 0 && y0 + r < H)
+                rowflags_out[f * b.rf_stride + rowflag_index(y0 + r, tx, b.tiles_x)] = (uint8_t)((bal >> (tid & 31)) & 0xfu);
+        }
+        const bool any_out = __syncthreads_or(word != 0);
+        expand_tile(b, f, tx, ty, s_w, any_out, tid);
+        cur = nxt;
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ctrl + 2, 1u) == gridDim.x - 1) ctrl[0] = 0, ctrl[1] = 0, ctrl[2] = 0;
     }
 }
 
@@ -309,9 +549,48 @@ cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_lau
     return cudaGetLastError();
 }
 
+// open followed by close in one kernel; the final bit-mask goes to bits_out (must not be b.bits)
+bool morph_expand_supported(int open_k, int close_k) {
+    auto reach = [](int k) { return k > 0 ? 2 * std::max(k / 2, k - 1 - k / 2) : 0; };
+    return reach(open_k) + reach(close_k) <= kMorphReach;
+}
+
+// persistent grids: exactly one wave (a second, partial wave would run at a fraction of the occupancy for as long again)
+template <typename K>
+int one_wave_grid(K kernel, int block) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uint32_t *bits_out, uint8_t *rowflags_out,
+                                uint32_t *tile_list, unsigned int *ctrl, bool pdl, cudaStream_t s) {
+    const size_t tiles = (size_t)b.n * ((b.h + 31) / 32) * b.tiles_x;
+    auto reach1 = [](int k) { return k > 0 ? 2 * std::max(k / 2, k - 1 - k / 2) : 0; };
+    const int reach = std::min(kMorphReach, reach1(open_k) + reach1(close_k));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((tiles + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_morph_scan, b, reach, rowflags_out, tile_list, ctrl);
+    if (e != cudaSuccess) return e;
+    static const int wave = one_wave_grid(k_morph_tiles, 256);
+    cfg.gridDim = dim3((unsigned)std::min<size_t>(tiles, (size_t)wave));
+    cfg.numAttrs = 1;  // behind the scan, whatever preceded that
+    return cudaLaunchKernelEx(&cfg, k_morph_tiles, b, open_k, close_k, bits_out, rowflags_out, (const uint32_t *)tile_list, ctrl);
+}
+
 cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s) {
     const size_t tiles = (size_t)b.n * ((b.h + 31) / 32) * b.tiles_x;
-    k_expand_bits<<<(int)std::min<size_t>(tiles, 148 * 8), 256, 0, s>>>(b);
+    static const int wave = one_wave_grid(k_expand_bits, 256);
+    k_expand_bits<<<(int)std::min<size_t>(tiles, (size_t)wave), 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 

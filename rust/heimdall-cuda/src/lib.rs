@@ -79,6 +79,12 @@ extern "C" {
     pub fn hv_last_error(ctx: *const hv_ctx) -> *const c_char;
     pub fn hv_host_alloc(ctx: *mut hv_ctx, bytes: usize) -> *mut c_void;
     pub fn hv_host_free(ctx: *mut hv_ctx, p: *mut c_void);
+    /// Device buffers for the device-resident entry points; flags = HV_ALLOC_COMPRESSIBLE (1) asks for L2
+    /// compute-data compression (the mostly-zero mask / label planes then cost less DRAM write time).
+    pub fn hv_device_alloc(ctx: *mut hv_ctx, bytes: usize, flags: u32, d_ptr: *mut *mut c_void, compressed_out: *mut i32) -> hv_status;
+    pub fn hv_device_free(ctx: *mut hv_ctx, d_ptr: *mut c_void) -> hv_status;
+    pub fn hv_device_read(ctx: *mut hv_ctx, host_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> hv_status;
+    pub fn hv_device_write(ctx: *mut hv_ctx, d_dst: *mut c_void, host_src: *const c_void, bytes: usize) -> hv_status;
     pub fn hv_detect_batch(
         ctx: *mut hv_ctx,
         frames: *const u8,

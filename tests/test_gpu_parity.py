@@ -290,6 +290,31 @@ def test_morphology_open_close(oracle, detector, k_open, k_close):
                 morph_close_k=k_close)
 
 
+@pytest.mark.parametrize("k_open,k_close,shape", [(3, 3, (1024, 1280)), (7, 5, (1024, 1280)), (15, 13, (200, 256)),
+                                                   (17, 0, (150, 192)), (0, 21, (150, 200)), (4, 6, (97, 128)),
+                                                   (15, 15, (33, 31))])
+def test_morphology_fused_kernel_and_fallback(oracle, detector, k_open, k_close, shape):
+    """One-kernel open+close+expansion (kernel sizes up to 15, reach <= 28 px) against the oracle on tile-aligned and
+    ragged shapes, frames smaller than the reach, and the multi-pass fallback for larger kernels; a batch of two frames
+    so that neighbouring frames must not leak into each other's halo."""
+    import heimdall_core as hc
+    h, w = shape
+    rng = np.random.default_rng(k_open * 100 + k_close)
+    a = synth.bottle_frame(h, w, 77, contaminants=3) if min(h, w) >= 150 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+    bimg = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    bimg[: h // 2] = 128  # half flat, half texture: empty and busy tiles side by side
+    batch = np.stack([a, bimg])[..., None]
+    p = hc.make_params(1.0, 1e9, 2.0 if min(h, w) < 150 else 25.0, morph_open_k=k_open, morph_close_k=k_close)
+    res = detector.detect_batch(batch, p, debug=["mask", "labels"])
+    for f in range(2):
+        ref = oracle.detect_contamination(batch[f], 1.0, 1e9, 2.0 if min(h, w) < 150 else 25.0, morph_open_k=k_open,
+                                          morph_close_k=k_close)
+        assert np.array_equal(res.debug["mask"][f], ref.mask)
+        assert np.array_equal(res.debug["labels"][f], ref.labels)
+        assert [(int(d["y"]), int(d["x"]), float(d["size"]), float(d["confidence"])) for d in res.defects_of(f)] == \
+            [(d["position"][0], d["position"][1], d["size"], d["confidence"]) for d in ref.defects]
+
+
 def test_morphology_matches_opencv_golden(detector, golden_dir):
     """Mask-level check against committed cv2 outputs: run open/close via detect on an image whose mask is known."""
     import heimdall_core as hc

@@ -116,6 +116,9 @@ del twelve
 # ---- configs[4] on one GPU: 8 camera streams x 5 MP, one batch per stream round (bench.py --gpus N shards streams) ----
 streams = tile_batch([synth.bottle_frame(2048, 2448, 900 + i, contaminants=i % 3) for i in range(8)], 8)
 run("C5 8 streams x 5 MP, 1 frame per stream per step (1 GPU)", streams, hc.make_params(), {}, 10 if quick else 40)
+streams4 = tile_batch([synth.bottle_frame(2048, 2448, 900 + i, contaminants=i % 3) for i in range(8)], 32)
+run("C5 8 streams x 5 MP, 4 frame sets per step (FrameSet batcher, sets_per_batch=4; 1 GPU)", streams4, hc.make_params(), {},
+    10 if quick else 40)
 
 hdr = ("config", "batch", "oracle parity", "ms/step", "frames/s", "alg GB/s", "frac of measured HBM", "launches/step",
        "components/frame", "defects/frame")
