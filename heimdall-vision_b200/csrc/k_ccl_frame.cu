@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     unsigned long long t_start = 0;
     if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     auto stamp = [&]() {
-        if (b.phase_ns && f == b.phase_frame && lane == 0 && stamp_i < 12) {
+        if (b.phase_ns && f == b.phase_frame && lane == 0 && stamp_i < 12 && wid < 16) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             b.phase_ns[stamp_i * 16 + wid] = t;

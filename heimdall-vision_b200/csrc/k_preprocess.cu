@@ -767,17 +767,33 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
             // reach of the filters (RB + 5 <= 12 px) take the value of their mirror image, which is inside the box.
             uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
             if (!box_inside) {
-                for (int idx = tid; idx < T::GH * T::GW; idx += kK1Consumers) {
-                    const int r = idx / T::GW, c = idx - r * T::GW;
-                    const int gy = y0 - T::HALO + r, gx = x0 - T::HX + c;
-                    if ((gy < 0 || gy >= H || gx < 0 || gx >= W) && gy >= -T::HALO && gy < H + T::HALO && gx >= -T::HALO &&
-                        gx < W + T::HALO) {
-                        const int sy = gy < 0 ? -gy : (gy >= H ? 2 * (H - 1) - gy : gy);
-                        const int sx = gx < 0 ? -gx : (gx >= W ? 2 * (W - 1) - gx : gx);
-                        s_g[r][c] = s_g[sy - (y0 - T::HALO)][sx - (x0 - T::HX)];
-                    }
+                // rows above / below the image first (whole rows, 16-byte items, from their mirror rows), then the columns
+                // left / right of it in every row (from their mirror columns, which lie inside the image).  The whole halo
+                // is filled, 16 columns and 12 rows, so that a border tile can pass the flat test like any other.
+                // (below the image only the HALO rows the filters can reach: the mirror of anything further lies outside
+                // the box; such rows exist only in a frame's last, partial tile row)
+                const int r_top = max(0, T::HALO - y0), r_bot = min(T::GH, H - y0 + T::HALO);
+                const int n_rows = r_top + min(T::GH - r_bot, T::HALO);
+                constexpr int IPR = T::GW / 16;
+                for (int idx = tid; idx < n_rows * IPR; idx += kK1Consumers) {
+                    const int k = idx / IPR, j = idx - k * IPR;
+                    const int r = k < r_top ? k : r_bot + (k - r_top);
+                    const int gy = y0 - T::HALO + r;
+                    const int sy = gy < 0 ? -gy : 2 * (H - 1) - gy;
+                    *reinterpret_cast<uint4 *>(&s_g[r][16 * j]) = *reinterpret_cast<const uint4 *>(&s_g[sy - (y0 - T::HALO)][16 * j]);
                 }
-                tile_sync<true>();
+                if (n_rows) tile_sync<true>();  // block-uniform
+                const int c_r = W - x0 + T::HX;  // first box column right of the image
+                const int n_left = x0 == 0 ? T::HX : 0, n_right = c_r < T::GW ? min(T::HX, T::GW - c_r) : 0;
+                const int n_cols = n_left + n_right;
+                for (int idx = tid; idx < T::GH * n_cols; idx += kK1Consumers) {
+                    const int r = idx / n_cols, k = idx - r * n_cols;
+                    const int c = k < n_left ? k : c_r + (k - n_left);
+                    const int gx = x0 - T::HX + c;
+                    const int sx = gx < 0 ? -gx : 2 * (W - 1) - gx;
+                    s_g[r][c] = s_g[r][sx - (x0 - T::HX)];
+                }
+                if (n_cols) tile_sync<true>();
             }
             if (try_flat) {  // every row of the box, all its 16-byte items (4 px more than needed on either side)
                 const uint32_t ref4 = 0x01010101u * s_g[T::HALO + TH / 2][T::HX + TW / 2];
@@ -842,7 +858,7 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
             // only the fused per-frame CCL kernel reads this batch (it never looks at unflagged words).
             if (b.rowflags && tid < 2)
                 *reinterpret_cast<int4 *>(b.rowflags + (size_t)f * b.rf_stride + rowflag_index(y0, tx, tiles_x) + 16 * tid) = z;
-            if (b.tile_occ && tid == 2) *reinterpret_cast<uint32_t *>(b.tile_occ + 4 * tile_occ_index(b, f, tx, ty)) = 0u;
+            if (b.tile_occ && tid == 2) reinterpret_cast<uint32_t *>(b.tile_occ)[cur.x] = 0u;  // (the tile number is its index)
             if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
         } else {
             tile_compute_and_store<TW, TH, RB, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,

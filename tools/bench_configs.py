@@ -120,12 +120,36 @@ streams4 = tile_batch([synth.bottle_frame(2048, 2448, 900 + i, contaminants=i % 
 run("C5 8 streams x 5 MP, 4 frame sets per step (FrameSet batcher, sets_per_batch=4; 1 GPU)", streams4, hc.make_params(), {},
     10 if quick else 40)
 
+# ---- configs[0]: one 1280x1024 frame through the drop-in module call (host array in, Python dict out) -------------------
+lat_note = ""
+if not only or any("C1" in o for o in only):
+    one = synth.bottle_frame(1024, 1280, 1234, contaminants=2)[:, :, None]
+    ref1 = O.detect_contamination(one)
+    out = hc.detect_contamination(one)
+    ok1 = [(d["position"], d["size"], d["confidence"]) for d in out["defects"]] == \
+        [(d["position"], d["size"], d["confidence"]) for d in ref1.defects]
+    for _ in range(20):
+        hc.detect_contamination(one)
+    reps = 200
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        hc.detect_contamination(one)
+    lat_us = (time.perf_counter() - t1) / reps * 1e6
+    t1 = time.perf_counter()
+    for _ in range(3):
+        O.detect_contamination(one, want_intermediates=False)
+    cpu_us = (time.perf_counter() - t1) / 3 * 1e6
+    lat_note = (f"\nC1 (configs[0]): one 1280x1024 frame through `heimdall_core.detect_contamination` (pageable numpy array in, "
+                f"list of dicts out, synchronous): {lat_us:.0f} us per call, parity {'yes' if ok1 else 'NO'}; the oracle port of "
+                f"the reference's CPU path on one host core: {cpu_us / 1e3:.1f} ms per frame.\n")
+    print(lat_note, flush=True)
+
 hdr = ("config", "batch", "oracle parity", "ms/step", "frames/s", "alg GB/s", "frac of measured HBM", "launches/step",
        "components/frame", "defects/frame")
 text = "| " + " | ".join(hdr) + " |\n|" + "---|" * len(hdr) + "\n" + "\n".join("| " + " | ".join(r) + " |" for r in rows)
 text = (f"BASELINE.json configs[2..4] on one B200 (device-resident inputs, CUDA events, outputs alternate between two "
         f"buffer sets; algorithmic bytes = 6 B/px; measured HBM peak {PEAK:.1f} GB/s).  Generated by tools/bench_configs.py"
-        f"{' --quick' if quick else ''} in {time.time() - t0:.0f} s.\n\n" + text + "\n")
+        f"{' --quick' if quick else ''} in {time.time() - t0:.0f} s.\n\n" + text + "\n" + lat_note)
 print(text)
 if out_md:
     open(out_md, "w").write(text)

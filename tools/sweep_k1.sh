@@ -1,6 +1,4 @@
-HV_K1_CTAS_PER_SM=5 python tools/sweep_k1.py
-HV_K1_CTAS_PER_SM=4 python tools/sweep_k1.py
-HV_K1_CTAS_PER_SM=5 python tools/sweep_k1.py
-HV_K1_CTAS_PER_SM=4 python tools/sweep_k1.py
-HV_K1_CTAS_PER_SM=5 HV_K1_STATIC=1 python tools/sweep_k1.py
-HV_K1_CTAS_PER_SM=3 python tools/sweep_k1.py
+python tools/sweep_k1.py
+HV_CCL_THREADS=1024 python tools/sweep_k1.py
+python tools/sweep_k1.py
+HV_CCL_THREADS=1024 python tools/sweep_k1.py
