@@ -64,6 +64,7 @@ struct PreprocessParams {
     int lookahead;      // TMA kernel: tiles the producer runs ahead of the consumers (1..stages), and the same once the
     int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
     int tail_tiles;
+    int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)
     int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which
                        // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)

@@ -681,13 +681,24 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
         // p.tail_lookahead once the tile numbers handed out are within p.tail_tiles of the end -- and claims a tile only
         // when it is about to issue its load.  Tile it may be issued once tile it - look has been released; the stage's
         // own barrier (tile it - kTmaStages) is implied because the consumers release in order.
+        // p.claim_ahead (off): request the next tile number one tile early, so that the round trip of the atomic overlaps
+        // the wait below.  Measured: the TMA wait per tile drops from 0.71 to 0.52 us, but one more tile per CTA is spoken
+        // for and the step gets 0.9 us longer (49.7 -> 50.6 us): balance is worth more than the hidden latency.
         const int tail_from = total - p.tail_tiles;
         int look = p.lookahead, prev_t = 0;
+        int pending = 0;
+        if (p.claim_ahead) pending = p.static_sched ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
         for (int it = 0;; it++) {
             const int st = it % kTmaStages;
             if (prev_t >= tail_from) look = p.tail_lookahead;
             if (it >= look) mbar_wait(&empty[(it - look) % kTmaStages], (uint32_t)((it - look) / kTmaStages) & 1u);
-            const int t = p.static_sched ? (int)blockIdx.x + it * (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            int t;
+            if (p.claim_ahead) {
+                t = pending;
+                if (t < total) pending = p.static_sched ? t + (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            } else {
+                t = p.static_sched ? (int)blockIdx.x + it * (int)gridDim.x : (int)atomicAdd(sched, 1u);
+            }
             prev_t = t;
             const int f = t / per_frame, r = t - f * per_frame;
             const int ty = r / tiles_x, tx = r - ty * tiles_x;
@@ -1013,6 +1024,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.tail_tiles = e_trounds * grid;
     static const int e_pref = getenv("HV_K1_PREFETCH") ? atoi(getenv("HV_K1_PREFETCH")) : 0;
     q.prefetch_tiles = e_pref;
+    static const int e_claim = getenv("HV_K1_CLAIM_AHEAD") ? atoi(getenv("HV_K1_CLAIM_AHEAD")) : 0;
+    q.claim_ahead = e_claim;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
