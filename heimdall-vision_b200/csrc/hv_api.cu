@@ -163,6 +163,7 @@ struct Slot {
     DevBuf<uint32_t> tile_list;
     DevBuf<uint16_t> gauss_tmp;
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
+    uint32_t ccl_expected = 0;  // frames handed to the per-frame CCL kernel on this slot so far (sched[7] counts them done)
     PinBuf<uint32_t> h_flags;
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
@@ -495,6 +496,8 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.stats = ctx->d_stats;
     b.frame_flags = s.frame_flags.p;
     b.frame_select = nullptr;
+    b.ccl_done = getenv("HV_NO_EARLY_K1") ? nullptr : s.sched.p + 7;
+    b.ccl_wait_value = s.ccl_expected;
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
     if (b.phase_ns) {
         cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
@@ -617,6 +620,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") &&
                               !getenv("HV_NO_PDL_TAIL");
         HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, st));
+        s.ccl_expected += (uint32_t)n;
         ctx->launches += 1;
     } else {
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words

@@ -47,6 +47,9 @@ struct BatchView {
     uint32_t *frame_flags;     // n: written by the fused per-frame kernel, 1 = frame needs the global-memory CCL path
     unsigned long long *phase_ns;  // 256 or NULL: per-phase timestamps of frame `phase_frame` in the fused kernel (debug)
     int phase_frame;               // which frame's CTA records the stamps (HV_PHASE_FRAME, default 0)
+    unsigned int *ccl_done;        // NULL or the slot's completion counter: +1 per frame when the per-frame CCL kernel is
+                                   // through with it (K1 of the batch that reuses the slot waits for ccl_wait_value)
+    unsigned int ccl_wait_value;   // K1: counter value that means "every earlier per-frame kernel on this slot is done"
     const uint32_t *frame_select;  // n or NULL: when set, the global-path kernels only touch frames with a non-zero entry
 };
 
@@ -64,6 +67,7 @@ struct PreprocessParams {
     int lookahead;      // TMA kernel: tiles the producer runs ahead of the consumers (1..stages), and the same once the
     int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
     int tail_tiles;
+    int wait_hint_ns;   // TMA kernel: suspend-time hint of mbarrier.try_wait
     int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)
     int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which

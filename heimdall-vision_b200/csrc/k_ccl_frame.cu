@@ -126,14 +126,20 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
 }
 
 __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams sp) {
-    // Programmatic dependent launch, both ways.  (1) This kernel may have been launched while K1 of its own batch was
-    // still running (its CTAs become resident as K1's CTAs retire): wait until that grid has completed and its stores
-    // are visible.  (2) Then let K1 of the next batch start (it shares no buffers with this batch).  Order matters: a K1
-    // that has started implies every CTA here is past the wait, i.e. K1 of this batch has completed, and that K1 does not
-    // complete before the per-frame kernel of the batch before it has (it waits at its end) -- so the slot the new K1
-    // overwrites is no longer in use.  Without the launch attribute both instructions are no-ops.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch, both ways.  (1) Let K1 of the next batch start as soon as every CTA of this kernel is
+    // resident, which is when K1 of this batch is retiring its last CTAs: the tail of one K1 overlaps the head of the next.
+    // That K1 works on the other slot, whose last user is the per-frame kernel of the batch before this one; it checks
+    // that kernel's completion counter itself before it touches anything (see k_preprocess_tma), because nothing in the
+    // launch order guarantees it any more.  (2) This kernel may have been launched while K1 of its own batch was still
+    // running: wait until that grid has completed and its stores are visible.  Without the launch attribute both
+    // instructions are no-ops.
+    if (b.ccl_done) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    } else {  // no completion counter: the next K1 may only start once K1 of this batch has completed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -209,7 +215,10 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         }
     }
     if (too_big) {  // block-uniform
-        if (tid == 0) b.frame_flags[f] = 1u;
+        if (tid == 0) {
+            b.frame_flags[f] = 1u;
+            if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
+        }
         return;
     }
     stamp();  // 1
@@ -234,7 +243,10 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     uint32_t nn = 0;
     uint32_t off = block_exclusive_scan(local, S.warp_tmp, &nn);
     if (nn > (uint32_t)kCapN) {  // block-uniform
-        if (tid == 0) b.frame_flags[f] = 1u;
+        if (tid == 0) {
+            b.frame_flags[f] = 1u;
+            if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
+        }
         return;
     }
     for (int e = e0; e < e1; e++) {
@@ -327,7 +339,10 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     __syncthreads();
     const uint32_t ne = S.n_edges;
     if (ne > (uint32_t)kCapE) {  // block-uniform
-        if (tid == 0) b.frame_flags[f] = 1u;
+        if (tid == 0) {
+            b.frame_flags[f] = 1u;
+            if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
+        }
         return;
     }
     pointer_jump(S.parent, nn, tid);
@@ -357,7 +372,10 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     uint32_t ncomp = 0;
     uint32_t rk = block_exclusive_scan(nroots, S.warp_tmp, &ncomp);
     if (ncomp > (uint32_t)kCapB || ncomp > (uint32_t)b.blob_cap) {  // block-uniform
-        if (tid == 0) b.frame_flags[f] = 1u;
+        if (tid == 0) {
+            b.frame_flags[f] = 1u;
+            if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
+        }
         return;
     }
     for (uint32_t v = v0; v < v1; v++)
@@ -456,6 +474,14 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     }
     if (tid < HV_STATS_AREA_BINS && S.hist[tid])
         atomicAdd(reinterpret_cast<unsigned long long *>(b.stats) + 6 + tid, (unsigned long long)S.hist[tid]);
+    // completion counter of the slot: the K1 that reuses the slot (two batches later) waits for it
+    if (b.ccl_done) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(b.ccl_done, 1u);
+        }
+    }
     if (b.phase_ns && tid == 0 && f < 40) {  // debug: duration of this frame's CTA and its problem size
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

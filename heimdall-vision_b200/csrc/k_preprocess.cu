@@ -46,17 +46,20 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread is parked until the phase completes (or the hint expires) instead of
+// re-issuing the test -- in the r03c capture 28 % of all executed warp instructions were this spin loop (the producer
+// warp of every CTA waits nearly all the time), competing for issue slots with the warps that have work.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(hint_ns)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2) {
@@ -663,6 +666,14 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     // resident as ours retire and wait there for this grid to complete, which takes its launch latency off the step
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
+        // Launched while the kernels of the previous batch are still running (programmatic dependent launch): the slot this
+        // batch writes was last used by the per-frame CCL kernel two batches back, which is normally long done -- make sure
+        // (its completion counter; wrap-safe comparison) before anything of the slot, the tile counter included, is touched.
+        if (b.ccl_done) {
+            const volatile unsigned int *flag = b.ccl_done;
+            while ((int)(*flag - b.ccl_wait_value) < 0) __nanosleep(100);
+            __threadfence();
+        }
 #pragma unroll
         for (int k = 0; k < kTmaStages; k++) {
             mbar_init(&full[k], 1);
@@ -691,7 +702,7 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
         for (int it = 0;; it++) {
             const int st = it % kTmaStages;
             if (prev_t >= tail_from) look = p.tail_lookahead;
-            if (it >= look) mbar_wait(&empty[(it - look) % kTmaStages], (uint32_t)((it - look) / kTmaStages) & 1u);
+            if (it >= look) mbar_wait(&empty[(it - look) % kTmaStages], (uint32_t)((it - look) / kTmaStages) & 1u, (uint32_t)p.wait_hint_ns);
             int t;
             if (p.claim_ahead) {
                 t = pending;
@@ -762,7 +773,7 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
         const int st = it % kTmaStages;
         unsigned long long t_a = 0, t_b = 0;
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
-        mbar_wait(&full[st], (uint32_t)(it / kTmaStages) & 1u);
+        mbar_wait(&full[st], (uint32_t)(it / kTmaStages) & 1u, (uint32_t)p.wait_hint_ns);
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
         const int4 cur = s_tile[st];
         if (cur.x >= total) break;
@@ -886,7 +897,10 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     // Launched ahead of the previous batch's per-frame CCL kernel's completion (programmatic dependent launch): this grid
     // must not complete before that one has, because the kernel after us relies on "K1 complete => everything before it
     // complete" when it lets the next K1 overwrite that batch's buffers (see k_ccl_frame).  A no-op otherwise.
-    if (tid == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // With the slots' completion counters (b.ccl_done) that inference is not needed -- every K1 checks the counter of the
+    // slot it is about to overwrite -- and the wait would only serialise the per-frame kernels of consecutive batches
+    // (measured: step = duration of that kernel + 7 us, whatever K1 did).
+    if (tid == 0 && !b.ccl_done) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (b.phase_ns && tid == 0) {  // debug: CTA lifetimes
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -1026,6 +1040,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.prefetch_tiles = e_pref;
     static const int e_claim = getenv("HV_K1_CLAIM_AHEAD") ? atoi(getenv("HV_K1_CLAIM_AHEAD")) : 0;
     q.claim_ahead = e_claim;
+    static const int e_hint = getenv("HV_K1_WAIT_HINT_NS") ? atoi(getenv("HV_K1_WAIT_HINT_NS")) : 10000000;
+    q.wait_hint_ns = e_hint;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
