@@ -20,7 +20,7 @@ using namespace hv;
 
 namespace {
 
-constexpr int kSyncSlots = 2;
+constexpr int kSyncSlots = 5;  // scratch sets rotated by the synchronous / device-resident entry points (see enqueue_pipeline)
 
 thread_local std::string g_create_error;
 
@@ -164,9 +164,11 @@ struct Slot {
     DevBuf<uint16_t> gauss_tmp;
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
     uint32_t ccl_expected = 0;  // frames handed to the per-frame CCL kernel on this slot so far (sched[7] counts them done)
+    uint32_t k1_expected = 0;   // K1 launches with a launch counter on this slot so far (sched[9] counts them done)
     PinBuf<uint32_t> h_flags;
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
+    bool used_small = false;  // ... its small build
     bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
     DevBuf<int32_t> labels;
@@ -216,11 +218,25 @@ struct hv_ctx {
     // fallback the next batches use the global path directly and the fused kernel is re-tried every 8th batch
     bool dense_hint = false;
     uint32_t dense_batches = 0;
-    int sync_cur = 0;  // which of the two synchronous slots holds the most recent batch
+    int sync_cur = 0;  // which of the synchronous slots holds the most recent batch
     // last batch enqueued through the device-resident path (for the programmatic-dependent-launch overlap decision)
     cudaStream_t last_stream = nullptr;
     bool last_valid = false, last_fused_tail = false;
     const void *last_mask = nullptr, *last_labels = nullptr;
+    // The batches before that one whose per-frame CCL kernels may still be running when K1 of the batch being enqueued
+    // starts (most recent first, at most kSyncSlots - 2 of them; the one that used the same slot is covered by the slot's
+    // own counter): output planes, completion counter of their slot and the value that means "through".
+    struct InFlight {
+        const void *mask, *labels;
+        unsigned int *done;
+        uint32_t expected;
+    };
+    std::vector<InFlight> in_flight;
+    unsigned int *last_done = nullptr;
+    uint32_t last_expected = 0;
+    // which build of the per-frame CCL kernel: the small one (co-resident with K1) until a frame did not fit in it
+    bool ccl_small_ok = true;
+    uint32_t ccl_small_retry = 0;
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -395,8 +411,10 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
     HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
     if (!s.sched.p) {  // K1's tile scheduler: {next tile, CTAs done}; the kernel rearms it itself
-        HV_TRY_CUDA(ctx, s.sched.reserve(8));  // [0..1] K1, [4..6] the fused morphology kernels
-        HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 8 * sizeof(uint32_t)));
+        // [0..1] K1's tile counter, [4..6] the fused morphology kernels, [7] frames the per-frame CCL kernel is through
+        // with, [8] K1 CTAs done in the running launch, [9] K1 launches done
+        HV_TRY_CUDA(ctx, s.sched.reserve(16));
+        HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 16 * sizeof(uint32_t)));
     }
     HV_TRY_CUDA(ctx, s.h_flags.reserve(n));
     HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
@@ -496,8 +514,18 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.stats = ctx->d_stats;
     b.frame_flags = s.frame_flags.p;
     b.frame_select = nullptr;
-    b.ccl_done = getenv("HV_NO_EARLY_K1") ? nullptr : s.sched.p + 7;
+    b.ccl_done = (getenv("HV_NO_EARLY_K1") || getenv("HV_EXP_K1_ONLY")) ? nullptr : s.sched.p + 7;
     b.ccl_wait_value = s.ccl_expected;
+    // The caller's output planes are not tied to our slots: if this batch writes planes that one of the batches still in
+    // flight wrote (a caller rotating fewer sets than we have slots), K1 also waits for that batch's per-frame kernel.
+    b.ccl_wait_n = 0;
+    if (b.ccl_done && ctx->last_valid && ctx->last_stream == st)
+        for (const auto &q : ctx->in_flight)
+            if (q.done && (q.mask == (const void *)b.mask || q.labels == (const void *)b.labels) && b.ccl_wait_n < 4) {
+                b.ccl_wait_flag[b.ccl_wait_n] = q.done;
+                b.ccl_wait_val[b.ccl_wait_n] = q.expected;
+                b.ccl_wait_n++;
+            }
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
     if (b.phase_ns) {
         cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
@@ -513,7 +541,17 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ctx->dense_batches++;
         if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
     }
+    // Small build of the per-frame kernel (co-resident with four K1 CTAs per SM): plain box path only.  After a frame did
+    // not fit, the big build serves the next 64 batches before the small one is tried again.
+    bool ccl_small = fused && !morph && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
+    if (ccl_small && !ctx->ccl_small_ok) {
+        if (++ctx->ccl_small_retry < 64)
+            ccl_small = false;
+        else
+            ctx->ccl_small_ok = true, ctx->ccl_small_retry = 0;
+    }
     PreprocessParams pp{};
+    pp.ctas_per_sm = ccl_small ? 4 : 0;  // 0 = the kernel's default
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
@@ -531,6 +569,9 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.write_mask = (morph && !morph_fused_plan) ? 0 : 1;
     pp.init_labels = (morph && !morph_fused_plan) ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
+    // K1 (TMA kernel) publishes a launch counter for the per-frame CCL kernel that follows it directly
+    unsigned int *k1_flag = (b.ccl_done && fused && !morph && !getenv("HV_NO_K1_FLAG")) ? s.sched.p + 9 : nullptr;
+    kb.k1_done = k1_flag;
     // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
     bool gauss_fused = false, k1_tma = false;
     if (gauss && pr.blur_ksize <= 15 && !(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) && !getenv("HV_NO_FUSED_GAUSS")) {
@@ -612,15 +653,23 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
             ctx->launches += nl + 1;
         }
     }
+    if (k1_flag && k1_tma) {
+        s.k1_expected++;
+        b.k1_done = k1_flag;
+        b.k1_wait_value = s.k1_expected;
+    }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
-    if (fused) {
+    if (fused && getenv("HV_EXP_K1_ONLY")) {
+        // experiment: K1 chain alone (results are NOT computed)
+    } else if (fused) {
         ProfScope ps(ctx, HV_K_CCL_FRAME, st);
         // launched ahead of K1's completion when K1 (TMA kernel, which releases its dependents at once) is the kernel
         // right before it on the stream; the kernel waits for K1 itself (griddepcontrol.wait)
         const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") &&
                               !getenv("HV_NO_PDL_TAIL");
-        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, st));
+        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, ccl_small, st));
         s.ccl_expected += (uint32_t)n;
+        s.used_small = ccl_small;
         ctx->launches += 1;
     } else {
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
@@ -633,11 +682,18 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     s.used_fused = fused;
     s.sparse_bits = pp.sparse_aux != 0 || (morph_fused && fused);  // (fused morphology: tiles out of reach of foreground have no bit words)
     s.score = sp;
+    if (!(ctx->last_valid && ctx->last_stream == st)) ctx->in_flight.clear();  // everything before this batch has completed
+    else if (ctx->last_fused_tail && ctx->last_done) {
+        ctx->in_flight.insert(ctx->in_flight.begin(), hv_ctx::InFlight{ctx->last_mask, ctx->last_labels, ctx->last_done, ctx->last_expected});
+        if (ctx->in_flight.size() > (size_t)(kSyncSlots - 2)) ctx->in_flight.resize(kSyncSlots - 2);
+    }
     ctx->last_valid = true;
     ctx->last_stream = st;
     ctx->last_fused_tail = fused;
     ctx->last_mask = b.mask;
     ctx->last_labels = b.labels;
+    ctx->last_done = fused ? b.ccl_done : nullptr;
+    ctx->last_expected = s.ccl_expected;
     s.view = b;
     s.has_batch = true;
     s.have_blur = (separate_blur && !gauss_fused) || want_blur;
@@ -666,6 +722,10 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
         ctx->dense_hint = false;
         return HV_OK;
     }
+    if (s.used_small) {  // too much foreground for the small build: the big one takes over (the global path below
+        ctx->ccl_small_ok = false;  // finishes the flagged frames of this batch)
+        ctx->ccl_small_retry = 0;
+    }
     BatchView b = s.view;
     b.frame_select = b.frame_flags;
     if (s.sparse_bits) {
@@ -679,8 +739,11 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->dense_hint = true;
-    ctx->dense_batches = 0;
+    if (!s.used_small) {  // (after the small build the big one is tried before the global path becomes the default)
+        ctx->dense_hint = true;
+        ctx->dense_batches = 0;
+    }
+    s.used_small = false;
     return HV_OK;
 }
 
@@ -926,6 +989,8 @@ void hv_host_free(hv_ctx *ctx, void *p) {
     if (p) cudaFreeHost(p);
 }
 
+int32_t hv_pipeline_depth(void) { return kSyncSlots; }
+
 hv_status hv_device_alloc(hv_ctx *ctx, size_t bytes, uint32_t flags, void **d_ptr, int32_t *compressed_out) {
     if (!ctx || !d_ptr || bytes == 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
     *d_ptr = nullptr;
@@ -990,7 +1055,7 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
         pr = *params;
     else
         hv_params_default(&pr);
-    ctx->sync_cur ^= 1;
+    ctx->sync_cur = (ctx->sync_cur + 1) % kSyncSlots;
     return enqueue_pipeline(ctx, cur_sync_slot(ctx), sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr,
                             d_mask, d_labels, (ctx->cfg.flags & 4u) != 0);
 }
@@ -1050,7 +1115,7 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
         pr = *params;
     else
         hv_params_default(&pr);
-    ctx->sync_cur ^= 1;
+    ctx->sync_cur = (ctx->sync_cur + 1) % kSyncSlots;
     ctx->last_valid = false;
     Slot &s = cur_sync_slot(ctx);
     cudaStream_t st = sync_stream(ctx);

@@ -50,6 +50,12 @@ struct BatchView {
     unsigned int *ccl_done;        // NULL or the slot's completion counter: +1 per frame when the per-frame CCL kernel is
                                    // through with it (K1 of the batch that reuses the slot waits for ccl_wait_value)
     unsigned int ccl_wait_value;   // K1: counter value that means "every earlier per-frame kernel on this slot is done"
+    unsigned int *k1_done;         // NULL or the slot's K1 launch counter (+1 when the last CTA of a K1 launch has stored its last
+                                   // tile), k1_done[-1] counts the CTAs of the running launch; the per-frame kernel waits for
+    unsigned int k1_wait_value;    // this value instead of griddepcontrol.wait
+    int ccl_wait_n;                // K1: further counters to wait for (batches on other slots that wrote the same output planes)
+    unsigned int *ccl_wait_flag[4];
+    unsigned int ccl_wait_val[4];
     const uint32_t *frame_select;  // n or NULL: when set, the global-path kernels only touch frames with a non-zero entry
 };
 
@@ -67,6 +73,8 @@ struct PreprocessParams {
     int lookahead;      // TMA kernel: tiles the producer runs ahead of the consumers (1..stages), and the same once the
     int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
     int tail_tiles;
+    int ctas_per_sm;    // TMA kernel: resident CTAs per SM to launch (0 = default); 4 leaves room for the small CCL build
+    int reserve_from_smid; // experiment: K1 CTAs on SMs with this id or above exit at once (0 = off)
     int wait_hint_ns;   // TMA kernel: suspend-time hint of mbarrier.try_wait
     int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)
@@ -128,7 +136,7 @@ cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s);
 cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s);
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, cudaStream_t s);
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, bool small, cudaStream_t s);
 bool ccl_frame_supported(const BatchView &b);
 cudaError_t configure_ccl_frame();
 cudaError_t configure_preprocess_tma();

@@ -29,34 +29,55 @@ namespace hv {
 
 namespace {
 
-constexpr int kFT = 512;       // threads per CTA
-constexpr int kNW = kFT / 32;  // warps per CTA
-constexpr int kCapW = 4096;    // non-zero words per frame
-constexpr int kCapN = 8192;    // word-runs (nodes) per frame
-constexpr int kCapB = 2048;    // components per frame
-constexpr int kMaxEPT = kCapW / kFT;  // compacted words per thread (blocked partition)
-constexpr int kCapE = 4096;    // residual union edges per frame
+// Two builds of the kernel.  Big: 512 threads, 4096 non-zero words / 8192 runs / 2048 components per frame, 170 KB of
+// shared memory -- a CTA needs an SM to itself.  Small: 256 threads (64 registers), 2048 / 4096 / 512, 68 KB -- fits next to
+// four resident CTAs of K1 (155 KB), so its CTAs become resident the moment the kernel is launched, release the next K1
+// at once (see the top of the kernel) and simply wait there for their own K1 to finish: the chain of K1 launches has no
+// gap and no SM is set aside.  hv_api.cu picks the build per batch (small first; a frame that does not fit is flagged).
+template <int FT, int CW, int CN, int CB, int CE>
+struct CclCfg {
+    static constexpr int kFT = FT;         // threads per CTA
+    static constexpr int kNW = FT / 32;    // warps per CTA
+    static constexpr int kCapW = CW;       // non-zero words per frame
+    static constexpr int kCapN = CN;       // word-runs (nodes) per frame
+    static constexpr int kCapB = CB;       // components per frame
+    static constexpr int kCapE = CE;       // residual union edges per frame
+    static constexpr int kMaxEPT = CW / FT;  // compacted words per thread (blocked partition)
+};
+using CclBig = CclCfg<512, 4096, 8192, 2048, 4096>;
+using CclSmall = CclCfg<256, 2048, 4096, 512, 1024>;
 
+template <typename C>
 struct FrameSmem {
-    uint32_t widx[kCapW];      // word index (y * ww + wx) of the compacted non-zero words, raster order
-    uint32_t wbits[kCapW];
-    uint32_t parent[kCapN];    // union-find parents (node ids)
-    uint32_t node_px[kCapN];   // pixel index (y * w + x) of the first pixel of the run
-    uint16_t woff[kCapW + 8];  // first node of every compacted word
-    uint32_t edges[kCapE];     // residual union edges (u << 16 | v), see phase 2
+    union {  // the compacted words are dead after phase 2, the blob table is born in phase 3
+        struct {
+            uint32_t widx[C::kCapW];   // word index (y * ww + wx) of the compacted non-zero words, raster order
+            uint32_t wbits[C::kCapW];
+        };
+        struct {
+            uint32_t b_area[C::kCapB], b_sy[C::kCapB], b_sx[C::kCapB], b_ymin[C::kCapB], b_ymax[C::kCapB], b_xmin[C::kCapB],
+                b_xmax[C::kCapB];
+        };
+    };
+    uint32_t parent[C::kCapN];    // union-find parents (node ids)
+    uint32_t node_px[C::kCapN];   // pixel index (y * w + x) of the first pixel of the run
+    uint16_t woff[C::kCapW + 8];  // first node of every compacted word
+    uint32_t edges[C::kCapE];     // residual union edges (u << 16 | v), see phase 2
     uint32_t n_edges;
-    uint16_t rnk[kCapN];       // rank of the component among the roots (valid at root nodes)
-    uint8_t node_len[kCapN];
-    uint32_t b_area[kCapB], b_sy[kCapB], b_sx[kCapB], b_ymin[kCapB], b_ymax[kCapB], b_xmin[kCapB], b_xmax[kCapB];
+    uint16_t rnk[C::kCapN];       // rank of the component among the roots (valid at root nodes)
+    uint8_t node_len[C::kCapN];
     uint32_t warp_tmp[32];
     uint32_t warp_fg[32];
     uint32_t area_sum;
     uint32_t hist[HV_STATS_AREA_BINS];
 };
-static_assert(sizeof(FrameSmem) <= 227 * 1024, "FrameSmem must fit the 227 KB per-CTA shared memory of sm_100");
+static_assert(sizeof(FrameSmem<CclBig>) <= 227 * 1024, "FrameSmem must fit the 227 KB per-CTA shared memory of sm_100");
+static_assert(sizeof(FrameSmem<CclSmall>) <= 71 * 1024, "the small build must fit next to four K1 CTAs");
+static_assert(CclBig::kCapN <= 65536 && CclBig::kCapE <= 65536, "16-bit node ids in rnk / edges");
 
 // exclusive scan of one value per thread across the CTA; returns the exclusive prefix, *total_out gets the block sum.
 // Contains two __syncthreads().  One copy in the binary (see the header: code size is latency here).
+template <int kNW>
 __device__ __noinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *tmp, uint32_t *total_out) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = v;
@@ -107,6 +128,7 @@ __device__ __forceinline__ void s_union(uint32_t *parent, uint32_t a, uint32_t b
 
 // pointer jumping: every node shortens its own path (parent <- grandparent until the parent is a root); all nodes
 // concurrently, so a chain of length n collapses in O(log n) rounds
+template <int kFT>
 __device__ __forceinline__ void pointer_jump(uint32_t *parent, uint32_t nn, int tid) {
     volatile uint32_t *vp = parent;
     for (uint32_t v = tid; v < nn; v += kFT) {
@@ -125,7 +147,11 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
     return __popc(starts & ((2u << bit) - 1u)) - 1u;  // (2u << 31) - 1 wraps to all ones, as intended
 }
 
-__global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams sp) {
+template <typename C>
+__global__ void __launch_bounds__(C::kFT, C::kFT == 256 ? 4 : 1) k_ccl_frame(BatchView b, ScoreParams sp) {
+    constexpr int kFT = C::kFT, kNW = C::kNW, kCapW = C::kCapW, kCapN = C::kCapN, kCapB = C::kCapB, kCapE = C::kCapE;
+    constexpr int kMaxEPT = C::kMaxEPT;
+    using FrameSmem = hv::FrameSmem<C>;
     // Programmatic dependent launch, both ways.  (1) Let K1 of the next batch start as soon as every CTA of this kernel is
     // resident, which is when K1 of this batch is retiring its last CTAs: the tail of one K1 overlaps the head of the next.
     // That K1 works on the other slot, whose last user is the per-frame kernel of the batch before this one; it checks
@@ -135,7 +161,23 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     // instructions are no-ops.
     if (b.ccl_done) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (b.k1_done) {
+            // K1 of this batch publishes a launch counter when its last CTA has stored its last tile.  Waiting for that
+            // instead of griddepcontrol.wait matters: K1 was itself launched ahead of the previous batch's per-frame
+            // kernel, and a grid does not count as complete before the grids ahead of it in the stream have completed,
+            // so the hardware wait made the per-frame kernels of consecutive batches run strictly one after the other
+            // (measured: step = duration of this kernel + 5..8 us in every configuration).  What K1 wrote is read
+            // through the L2 below (ld.cg): a CTA that has been resident since before K1 finished has no guarantee
+            // about its L1.
+            if (threadIdx.x == 0) {
+                const volatile unsigned int *flag = b.k1_done;
+                while ((int)(*flag - b.k1_wait_value) < 0) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        } else {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
     } else {  // no completion counter: the next K1 may only start once K1 of this batch has completed
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -167,6 +209,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     // parent + node_px arrays), then thread t takes the contiguous rows [t*rpt, (t+1)*rpt) of the chunk and a block scan
     // of the popcounts gives its first output slot.  Frames with more bands than fit are staged in several chunks.
     static_assert(offsetof(FrameSmem, node_px) == offsetof(FrameSmem, parent) + sizeof(uint32_t) * kCapN, "staging area");
+    static_assert(kNW <= 16, "phase stamps");
     const int TX = b.tiles_x;
     const int nbands = (H + 31) / 32;
     const int band_bytes = TX * 32;
@@ -183,7 +226,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         if (b0) __syncthreads();            // the previous chunk has been consumed
         for (int i = tid * 16; i < bytes; i += kFT * 16)
             *reinterpret_cast<uint4 *>(stage + i) =
-                __ldg(reinterpret_cast<const uint4 *>(rf + (size_t)b0 * band_bytes + i));
+                __ldcg(reinterpret_cast<const uint4 *>(rf + (size_t)b0 * band_bytes + i));  // (L2: see the wait above)
         __syncthreads();
         const int rows = min(nb * 32, H - b0 * 32);
         const int rpt = (rows + kFT - 1) / kFT;
@@ -194,7 +237,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
             for (int tx = 0; tx < TX; tx++) cnt += __popc(rec[tx * 32] & 0xfu);
         }
         uint32_t tot = 0;
-        uint32_t pos = nw + block_exclusive_scan(cnt, S.warp_tmp, &tot);
+        uint32_t pos = nw + block_exclusive_scan<kNW>(cnt, S.warp_tmp, &tot);
         nw += tot;
         if (nw > (uint32_t)kCapW) {  // block-uniform
             too_big = true;
@@ -232,7 +275,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     {
         uint32_t wv[kMaxEPT];
 #pragma unroll
-        for (int k = 0; k < kMaxEPT; k++) wv[k] = (e0 + k < e1) ? __ldg(bits + S.widx[e0 + k]) : 0u;  // one round trip
+        for (int k = 0; k < kMaxEPT; k++) wv[k] = (e0 + k < e1) ? __ldcg(bits + S.widx[e0 + k]) : 0u;  // one round trip
 #pragma unroll
         for (int k = 0; k < kMaxEPT; k++) {
             if (e0 + k < e1) S.wbits[e0 + k] = wv[k];
@@ -241,7 +284,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         }
     }
     uint32_t nn = 0;
-    uint32_t off = block_exclusive_scan(local, S.warp_tmp, &nn);
+    uint32_t off = block_exclusive_scan<kNW>(local, S.warp_tmp, &nn);
     if (nn > (uint32_t)kCapN) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
@@ -345,7 +388,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
         }
         return;
     }
-    pointer_jump(S.parent, nn, tid);
+    pointer_jump<kFT>(S.parent, nn, tid);
     stamp();  // 4
     __syncthreads();
     for (uint32_t k = tid; k < ne; k += kFT) {
@@ -370,7 +413,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
     uint32_t nroots = 0;
     for (uint32_t v = v0; v < v1; v++) nroots += S.parent[v] == v ? 1u : 0u;
     uint32_t ncomp = 0;
-    uint32_t rk = block_exclusive_scan(nroots, S.warp_tmp, &ncomp);
+    uint32_t rk = block_exclusive_scan<kNW>(nroots, S.warp_tmp, &ncomp);
     if (ncomp > (uint32_t)kCapB || ncomp > (uint32_t)b.blob_cap) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
@@ -434,7 +477,7 @@ __global__ void __launch_bounds__(kFT, 1) k_ccl_frame(BatchView b, ScoreParams s
             sc = score_blob(b, sp, f, k, q);
         }
         uint32_t total = 0;
-        const uint32_t dpos = nd_base + block_exclusive_scan(sc.keep ? 1u : 0u, S.warp_tmp, &total);
+        const uint32_t dpos = nd_base + block_exclusive_scan<kNW>(sc.keep ? 1u : 0u, S.warp_tmp, &total);
         uint32_t a = sc.keep ? (uint32_t)sc.d.size : 0u;
         if (sc.keep) {
             if (dpos < (uint32_t)b.defect_cap) out[dpos] = sc.d;
@@ -495,21 +538,26 @@ bool ccl_frame_supported(const BatchView &b) { return b.h <= 8192 && b.w <= 8192
 
 // per device, once (hv_create): opt in to the large dynamic shared-memory carve-out
 cudaError_t configure_ccl_frame() {
-    return cudaFuncSetAttribute(k_ccl_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_ccl_frame<CclBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem<CclBig>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ccl_frame<CclSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem<CclSmall>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ccl_frame<CclSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, cudaStream_t s) {
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, bool small, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(b.n);
-    cfg.blockDim = dim3(kFT);
-    cfg.dynamicSmemBytes = sizeof(FrameSmem);
+    cfg.blockDim = dim3(small ? CclSmall::kFT : CclBig::kFT);
+    cfg.dynamicSmemBytes = small ? sizeof(FrameSmem<CclSmall>) : sizeof(FrameSmem<CclBig>);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_ccl_frame, b, p);
+    if (small) return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclSmall>, b, p);
+    return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclBig>, b, p);
 }
 
 }  // namespace hv

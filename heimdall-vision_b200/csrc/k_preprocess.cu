@@ -662,6 +662,11 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     unsigned long long t_cta0 = 0;
     if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
 
+    if (p.reserve_from_smid > 0) {  // experiment: leave the SMs from this id on to other kernels
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((int)smid >= p.reserve_from_smid) return;
+    }
     // the per-frame CCL kernel of this batch may be launched now (programmatic dependent launch): its CTAs become
     // resident as ours retire and wait there for this grid to complete, which takes its launch latency off the step
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -672,6 +677,10 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
         if (b.ccl_done) {
             const volatile unsigned int *flag = b.ccl_done;
             while ((int)(*flag - b.ccl_wait_value) < 0) __nanosleep(100);
+            for (int k = 0; k < b.ccl_wait_n; k++) {
+                const volatile unsigned int *flag2 = b.ccl_wait_flag[k];
+                while ((int)(*flag2 - b.ccl_wait_val[k]) < 0) __nanosleep(100);
+            }
             __threadfence();
         }
 #pragma unroll
@@ -901,6 +910,19 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     // slot it is about to overwrite -- and the wait would only serialise the per-frame kernels of consecutive batches
     // (measured: step = duration of that kernel + 7 us, whatever K1 did).
     if (tid == 0 && !b.ccl_done) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // launch counter for the per-frame kernel of this batch: the last CTA whose consumers have stored their last tile
+    // publishes it (and rearms the CTA count)
+    if (b.k1_done) {
+        tile_sync<true>();  // all 256 consumers of this CTA are past their stores
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(b.k1_done - 1, 1u) == gridDim.x - 1) {
+                b.k1_done[-1] = 0;
+                __threadfence();
+                atomicAdd(b.k1_done, 1u);
+            }
+        }
+    }
     if (b.phase_ns && tid == 0) {  // debug: CTA lifetimes
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -1016,7 +1038,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
     static const int gauss_ctas = getenv("HV_K1_GAUSS_CTAS") ? std::max(1, std::min(4, atoi(getenv("HV_K1_GAUSS_CTAS")))) : 4;
-    int grid = num_sms * (gauss ? gauss_ctas : k1_ctas_per_sm());
+    int grid = num_sms * (gauss ? gauss_ctas : (p.ctas_per_sm > 0 ? std::min(p.ctas_per_sm, k1_ctas_per_sm()) : k1_ctas_per_sm()));
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1042,6 +1064,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.claim_ahead = e_claim;
     static const int e_hint = getenv("HV_K1_WAIT_HINT_NS") ? atoi(getenv("HV_K1_WAIT_HINT_NS")) : 10000000;
     q.wait_hint_ns = e_hint;
+    static const int e_res = getenv("HV_EXP_RESERVE_SMS") ? atoi(getenv("HV_EXP_RESERVE_SMS")) : 0;
+    q.reserve_from_smid = e_res > 0 ? num_sms - e_res : 0;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }

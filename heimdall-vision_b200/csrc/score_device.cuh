@@ -31,7 +31,7 @@ __device__ __forceinline__ Scored score_blob(const BatchView &b, const ScorePara
     for (int k = 0; k < 25; k++) {
         const int y = min(max(icy - 2 + k / 5, 0), H - 1), x = min(max(icx - 2 + k % 5, 0), W - 1);
         gv[k] = gray[(size_t)y * b.gray_row_stride + x];
-        mv[k] = mask[(size_t)y * W + x];
+        mv[k] = __ldcg(mask + (size_t)y * W + x);  // written by K1 while this CTA may already have been resident: L2
     }
 #pragma unroll
     for (int k = 0; k < 25; k++) {

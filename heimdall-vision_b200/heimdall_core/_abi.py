@@ -133,6 +133,7 @@ PROTOTYPES = {
     "hv_set_stream": (_i32, [_vp, _vp, _i32]),
     "hv_host_alloc": (_vp, [_vp, _sz]),
     "hv_host_free": (None, [_vp, _vp]),
+    "hv_pipeline_depth": (_i32, []),
     "hv_device_alloc": (_i32, [_vp, _sz, C.c_uint32, _P(_vp), _P(_i32)]),
     "hv_device_free": (_i32, [_vp, _vp]),
     "hv_device_read": (_i32, [_vp, _vp, _vp, _sz]),

@@ -231,6 +231,11 @@ class Detector:
         _lib.hv_host_free(self._ctx, ptr)
 
     # ---- device-resident -----------------------------------------------------------------------------------------
+    @staticmethod
+    def pipeline_depth() -> int:
+        """How many sets of output planes to rotate through enqueue_device for full overlap (hv_pipeline_depth)."""
+        return int(_lib.hv_pipeline_depth())
+
     def device_alloc(self, shape, dtype=np.uint8, compressible: bool = True) -> "DeviceArray":
         """Device buffer for detect_device / enqueue_device outputs (hv_device_alloc).  compressible=True asks for L2
         compute-data compression: the mostly-zero mask and label planes then cost less DRAM write time."""

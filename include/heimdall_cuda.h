@@ -189,6 +189,12 @@ HV_API void hv_host_free(hv_ctx *ctx, void *p);
  * bytes per pixel -- takes less DRAM time.  Reads (kernels, cudaMemcpy) see ordinary memory.  If the device does not
  * support compression the flag is ignored; *compressed_out (optional) reports what was obtained.  No counterpart in
  * the reference (host-only code). */
+/* Number of scratch sets the device-resident entry point rotates through = how many batches may be in flight on the
+ * device at once.  A caller that passes its own d_mask / d_labels planes to hv_enqueue_device should rotate this many
+ * sets of them: a set that is reused earlier is still correct (the preprocess kernel of the new batch waits on the
+ * device for the batch that last wrote it), it only costs overlap. */
+HV_API int32_t hv_pipeline_depth(void);
+
 enum { HV_ALLOC_COMPRESSIBLE = 1 };
 HV_API hv_status hv_device_alloc(hv_ctx *ctx, size_t bytes, uint32_t flags, void **d_ptr, int32_t *compressed_out);
 HV_API hv_status hv_device_free(hv_ctx *ctx, void *d_ptr);

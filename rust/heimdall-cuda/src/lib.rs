@@ -81,6 +81,7 @@ extern "C" {
     pub fn hv_host_free(ctx: *mut hv_ctx, p: *mut c_void);
     /// Device buffers for the device-resident entry points; flags = HV_ALLOC_COMPRESSIBLE (1) asks for L2
     /// compute-data compression (the mostly-zero mask / label planes then cost less DRAM write time).
+    pub fn hv_pipeline_depth() -> i32;
     pub fn hv_device_alloc(ctx: *mut hv_ctx, bytes: usize, flags: u32, d_ptr: *mut *mut c_void, compressed_out: *mut i32) -> hv_status;
     pub fn hv_device_free(ctx: *mut hv_ctx, d_ptr: *mut c_void) -> hv_status;
     pub fn hv_device_read(ctx: *mut hv_ctx, host_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> hv_status;

@@ -591,3 +591,61 @@ def test_compressible_device_buffers(oracle, detector):
         assert np.array_equal(outs[True][0][f], ref.mask) and np.array_equal(outs[True][1][f], ref.labels)
         assert [(int(d["y"]), int(d["x"])) for d in outs[True][2].defects_of(f)] == [d["position"] for d in ref.defects]
     d_in.free()
+
+
+@pytest.mark.parametrize("n_sets", [1, 2, 3, 5])
+def test_batches_in_flight_with_rotating_output_sets(oracle, n_sets):
+    """Streaming use of enqueue_device: many batches enqueued back to back, the kernels of several of them in flight at
+    once (K1 of a batch starts while the per-frame CCL kernels of the previous ones still run), output planes rotated
+    over n_sets sets -- fewer than the library's pipeline depth means K1 has to wait on the device for the batch that
+    last wrote the set.  Every set must end up holding exactly the oracle's planes of the last batch written into it,
+    and the last batch's defect list must be the oracle's."""
+    import heimdall_core as hc
+    n, h, w = 4, 256, 384
+    n_batches = 13
+    batches = [synth.bottle_batch(n, h, w, start_index=7000 + 10 * i, contaminants=(i % 4)) for i in range(n_batches)]
+    det = hc.Detector(0)
+    try:
+        assert det.pipeline_depth() >= 3
+        d_in = [det.device_alloc((n, h, w), np.uint8, compressible=False) for _ in range(n_batches)]
+        for a, bt in zip(d_in, batches):
+            a.set(bt)
+        masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(n_sets)]
+        labels = [det.device_alloc((n, h, w), np.int32) for _ in range(n_sets)]
+        for rep in range(2):
+            for i in range(n_batches):
+                det.enqueue_device(d_in[i].ptr, n, h, w, 1, None, masks[i % n_sets].ptr, labels[i % n_sets].ptr)
+            last = det.fetch_results(n)
+            for k in range(n_sets):
+                i = max(j for j in range(n_batches) if j % n_sets == k)
+                got_m, got_l = masks[k].get(), labels[k].get()
+                for f in range(n):
+                    ref = oracle.detect_contamination(batches[i][f][:, :, None])
+                    assert np.array_equal(got_m[f], ref.mask), (n_sets, rep, k, f)
+                    assert np.array_equal(got_l[f], ref.labels), (n_sets, rep, k, f)
+            for f in range(n):
+                ref = oracle.detect_contamination(batches[n_batches - 1][f][:, :, None])
+                assert [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in last.defects_of(f)] == \
+                    [(d["position"], d["size"], d["confidence"]) for d in ref.defects]
+    finally:
+        det.close()
+
+
+def test_small_ccl_build_overflow_escalates(oracle):
+    """A frame with more foreground than the small per-frame CCL build holds (2048 non-zero words) is flagged, finished by
+    the global path, and the next batches go through the big build -- results identical throughout."""
+    import heimdall_core as hc
+    busy = synth.high_contamination_frame(512, 640, 3)  # 2333 non-zero words, 402 components: fits the big build only
+    calm = synth.bottle_frame(512, 640, 4, contaminants=1)
+    batch = np.stack([calm, busy])[..., None]
+    det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=20000)
+    try:
+        for rep in range(3):
+            res = det.detect_batch(batch, debug=["mask", "labels"])
+            for f in range(2):
+                ref = oracle.detect_contamination(batch[f])
+                assert np.array_equal(res.debug["mask"][f], ref.mask) and np.array_equal(res.debug["labels"][f], ref.labels)
+                assert [((int(d["y"]), int(d["x"])), float(d["size"])) for d in res.defects_of(f)] == \
+                    [(d["position"], d["size"]) for d in ref.defects]
+    finally:
+        det.close()

@@ -10,7 +10,7 @@ st = torch.cuda.current_stream().cuda_stream
 pool = [torch.from_numpy(synth.bottle_batch(n, h, w, start_index=100 * i)).cuda() for i in range(8)]
 det = hc.Detector(0); det.set_stream(st)
 comp = os.environ.get('SWEEP_COMPRESS', '1') == '1'
-nout = int(os.environ.get('SWEEP_OUTS', '2'))
+nout = int(os.environ.get('SWEEP_OUTS', str(det.pipeline_depth())))
 outs = [(det.device_alloc((n, h, w), np.uint8, comp), det.device_alloc((n, h, w), np.int32, comp)) for _ in range(nout)]
 print('outputs compressed:', outs[0][0].compressed, outs[0][1].compressed)
 def step(i): det.enqueue_device(pool[i % 8].data_ptr(), n, h, w, 1, None, outs[i % nout][0].data_ptr(), outs[i % nout][1].data_ptr())

@@ -1,4 +1,3 @@
-python tools/sweep_k1.py
-HV_NO_EARLY_K1=1 python tools/sweep_k1.py
-python tools/sweep_k1.py
-HV_NO_EARLY_K1=1 python tools/sweep_k1.py
+SWEEP_OUTS=5 python tools/sweep_k1.py
+SWEEP_OUTS=5 HV_CCL_BIG=1 python tools/sweep_k1.py
+SWEEP_OUTS=5 python tools/sweep_k1.py
