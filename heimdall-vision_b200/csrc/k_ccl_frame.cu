@@ -147,8 +147,10 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
     return __popc(starts & ((2u << bit) - 1u)) - 1u;  // (2u << 31) - 1 wraps to all ones, as intended
 }
 
+// Registers: the small build shares an SM with four K1 CTAs (4 x 288 threads x 40 registers = 46080 of 65536), which
+// leaves 256 threads x 72 registers.
 template <typename C>
-__global__ void __launch_bounds__(C::kFT, C::kFT == 256 ? 4 : 1) k_ccl_frame(BatchView b, ScoreParams sp) {
+__global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) k_ccl_frame(BatchView b, ScoreParams sp) {
     constexpr int kFT = C::kFT, kNW = C::kNW, kCapW = C::kCapW, kCapN = C::kCapN, kCapB = C::kCapB, kCapE = C::kCapE;
     constexpr int kMaxEPT = C::kMaxEPT;
     using FrameSmem = hv::FrameSmem<C>;
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(C::kFT, C::kFT == 256 ? 4 : 1) k_ccl_frame(Bat
             q.sum_y = S.b_sy[k];
             q.sum_x = S.b_sx[k];
             blobs[k] = q;
-            sc = score_blob(b, sp, f, k, q);
+            sc = score_blob<(kFT < 512)>(b, sp, f, k, q);
         }
         uint32_t total = 0;
         const uint32_t dpos = nd_base + block_exclusive_scan<kNW>(sc.keep ? 1u : 0u, S.warp_tmp, &total);

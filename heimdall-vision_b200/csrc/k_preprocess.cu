@@ -1054,7 +1054,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     PreprocessParams q = p;
     static const int e_look = getenv("HV_K1_LOOKAHEAD") ? atoi(getenv("HV_K1_LOOKAHEAD")) : kTmaStages;
     static const int e_tlook = getenv("HV_K1_TAIL_LOOKAHEAD") ? atoi(getenv("HV_K1_TAIL_LOOKAHEAD")) : 1;
-    static const int e_trounds = getenv("HV_K1_TAIL_ROUNDS") ? atoi(getenv("HV_K1_TAIL_ROUNDS")) : 4;
+    static const int e_trounds = getenv("HV_K1_TAIL_ROUNDS") ? atoi(getenv("HV_K1_TAIL_ROUNDS")) : 0;
     q.lookahead = e_look < 1 ? 1 : (e_look > kTmaStages ? kTmaStages : e_look);
     q.tail_lookahead = e_tlook < 1 ? 1 : (e_tlook > q.lookahead ? q.lookahead : e_tlook);
     q.tail_tiles = e_trounds * grid;

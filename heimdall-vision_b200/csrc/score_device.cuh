@@ -11,6 +11,10 @@ struct Scored {
     hv_defect d;
 };
 
+// LOW_REG = false: all 50 probe loads in flight together (50 registers).  LOW_REG = true (the 64-register build of the
+// per-frame kernel): the 25 mask bytes first, folded into a bit mask, then the 25 gray bytes -- two round trips, half the
+// registers; with everything in flight that build spilled and its scoring phase took 20 us instead of 6.
+template <bool LOW_REG = false>
 __device__ __forceinline__ Scored score_blob(const BatchView &b, const ScoreParams &p, int f, uint32_t k,
                                              const hv_blob &q) {
     Scored out;
@@ -25,24 +29,55 @@ __device__ __forceinline__ Scored score_blob(const BatchView &b, const ScorePara
     const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
     const uint8_t *mask = b.mask + (size_t)f * H * W;
     uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
-    // 5x5 probe, fully unrolled with clamped coordinates so that all 50 loads are in flight together
-    uint32_t gv[25], mv[25];
+    if (LOW_REG) {
+        // one probe row per round trip (10 loads in flight), accumulated at once
+#pragma unroll 1
+        for (int dy = -2; dy <= 2; dy++) {
+            const int y = icy + dy;
+            if (y < y_lo || y > y_hi) continue;
+            const uint8_t *grow = gray + (size_t)y * b.gray_row_stride;
+            const uint8_t *mrow = mask + (size_t)y * W;
+            uint32_t g[5], m[5];
 #pragma unroll
-    for (int k = 0; k < 25; k++) {
-        const int y = min(max(icy - 2 + k / 5, 0), H - 1), x = min(max(icx - 2 + k % 5, 0), W - 1);
-        gv[k] = gray[(size_t)y * b.gray_row_stride + x];
-        mv[k] = __ldcg(mask + (size_t)y * W + x);  // written by K1 while this CTA may already have been resident: L2
-    }
+            for (int dx = 0; dx < 5; dx++) {
+                const int xc = min(max(icx - 2 + dx, 0), W - 1);
+                g[dx] = grow[xc];
+                m[dx] = __ldcg(mrow + xc);
+            }
 #pragma unroll
-    for (int k = 0; k < 25; k++) {
-        const int y = icy - 2 + k / 5, x = icx - 2 + k % 5;
-        if (y >= y_lo && y <= y_hi && x >= x_lo && x <= x_hi) {
-            if (mv[k] == 255) {
-                fg_sum += gv[k];
-                fg_cnt++;
-            } else {
-                bg_sum += gv[k];
-                bg_cnt++;
+            for (int dx = 0; dx < 5; dx++) {
+                const int x = icx - 2 + dx;
+                if (x >= x_lo && x <= x_hi) {
+                    if (m[dx] == 255) {
+                        fg_sum += g[dx];
+                        fg_cnt++;
+                    } else {
+                        bg_sum += g[dx];
+                        bg_cnt++;
+                    }
+                }
+            }
+        }
+    } else {
+        // 5x5 probe, fully unrolled with clamped coordinates so that all 50 loads are in flight together
+        uint32_t gv[25], mv[25];
+#pragma unroll
+        for (int k = 0; k < 25; k++) {
+            const int y = min(max(icy - 2 + k / 5, 0), H - 1), x = min(max(icx - 2 + k % 5, 0), W - 1);
+            gv[k] = gray[(size_t)y * b.gray_row_stride + x];
+            mv[k] = __ldcg(mask + (size_t)y * W + x);  // written by K1 while this CTA may already have been resident: L2
+        }
+#pragma unroll
+        for (int k = 0; k < 25; k++) {
+            const int y = icy - 2 + k / 5, x = icx - 2 + k % 5;
+            if (y >= y_lo && y <= y_hi && x >= x_lo && x <= x_hi) {
+                if (mv[k] == 255) {
+                    fg_sum += gv[k];
+                    fg_cnt++;
+                } else {
+                    bg_sum += gv[k];
+                    bg_cnt++;
+                }
             }
         }
     }
