@@ -542,14 +542,9 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
     }
     // Small build of the per-frame kernel (co-resident with four K1 CTAs per SM): plain box path only.  After a frame did
-    // not fit, the big build serves the next 64 batches before the small one is tried again.
+    // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
     bool ccl_small = fused && !morph && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
-    if (ccl_small && !ctx->ccl_small_ok) {
-        if (++ctx->ccl_small_retry < 64)
-            ccl_small = false;
-        else
-            ctx->ccl_small_ok = true, ctx->ccl_small_retry = 0;
-    }
+    if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
     PreprocessParams pp{};
     pp.ctas_per_sm = ccl_small ? 4 : 0;  // 0 = the kernel's default
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
@@ -717,9 +712,14 @@ hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
 hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     if (!s.used_fused) return HV_OK;
     bool any = false;
-    for (int f = 0; f < s.view.n; f++) any |= s.h_flags.p[f] != 0;
+    bool all_fit_small = true;
+    for (int f = 0; f < s.view.n; f++) {
+        any |= (s.h_flags.p[f] & 1u) != 0;
+        all_fit_small &= s.h_flags.p[f] == 0;
+    }
     if (!any) {
         ctx->dense_hint = false;
+        if (!s.used_small && all_fit_small) ctx->ccl_small_ok = true;  // the big build reports that the small one would do
         return HV_OK;
     }
     if (s.used_small) {  // too much foreground for the small build: the big one takes over (the global path below

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
         const uint32_t m = b.bits[i];
         if (!m) continue;
         const size_t f = i / words_per_frame;
-        if (b.frame_select && !b.frame_select[f]) continue;
+        if (b.frame_select && !(b.frame_select[f] & 1u)) continue;
         const int wi = (int)(i - f * words_per_frame);
         const int y = wi / b.ww, wx = wi - y * b.ww;
         int32_t *L = b.labels + f * (size_t)b.h * b.w;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_ccl_flatten(BatchView b) {
     for (size_t si = blockIdx.x; si < total; si += gridDim.x) {
         const size_t f = si / b.nseg;
         const int seg = (int)(si - f * b.nseg);
-        if (b.frame_select && !b.frame_select[f]) continue;  // block-uniform
+        if (b.frame_select && !(b.frame_select[f] & 1u)) continue;  // block-uniform
         const int wi = seg * 256 + tid;
         const size_t i = f * (size_t)words_per_frame + wi;
         const uint32_t m = wi < words_per_frame ? b.bits[i] : 0u;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(1024) k_ccl_scan(BatchView b) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const int f = blockIdx.x;
-    if (b.frame_select && !b.frame_select[f]) return;
+    if (b.frame_select && !(b.frame_select[f] & 1u)) return;
     // counts in the first half of segbase, prefixes in the second: the other CTAs of the frame read the counts too
     const uint32_t *cnt = b.segbase + (size_t)f * b.nseg;
     uint32_t *pre = b.segbase + ((size_t)b.n + f) * b.nseg;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) k_ccl_label(BatchView b) {
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t pi = warp0; pi < total; pi += nwarps) {
         const size_t f = pi / patches_per_frame;
-        if (b.frame_select && !b.frame_select[f]) continue;
+        if (b.frame_select && !(b.frame_select[f] & 1u)) continue;
         const int pj = (int)(pi - f * patches_per_frame);
         const int py = pj / pw, px = pj - py * pw;
         const int y = py * 8 + (lane >> 2), wx = px * 4 + (lane & 3);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) k_densify_bits(BatchView b) {
     const int lane = threadIdx.x & 31;
     for (size_t t = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; t < total; t += ((size_t)gridDim.x * blockDim.x) >> 5) {
         const size_t f = t / per_frame;
-        if (b.frame_select && !b.frame_select[f]) continue;
+        if (b.frame_select && !(b.frame_select[f] & 1u)) continue;
         const int j = (int)(t - f * per_frame);
         const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
         const int y = ty * 32 + lane;

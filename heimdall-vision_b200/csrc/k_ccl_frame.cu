@@ -507,7 +507,12 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
         b.results[f] = r;
         b.ncomp[f] = ncomp;
         b.fgcount[f] = fg;
-        b.frame_flags[f] = 0u;
+        // bit 0 = "not done, needs the global path" (set on the early exits); bit 1 = done, but would not have fitted the
+        // small build: the host uses it to decide when to go back to that build
+        b.frame_flags[f] = (nw <= (uint32_t)CclSmall::kCapW && nn <= (uint32_t)CclSmall::kCapN && ne <= (uint32_t)CclSmall::kCapE &&
+                            ncomp <= (uint32_t)CclSmall::kCapB)
+                               ? 0u
+                               : 2u;
         unsigned long long *st = reinterpret_cast<unsigned long long *>(b.stats);
         atomicAdd(st + 0, 1ull);
         atomicAdd(st + 1, (unsigned long long)r.rejected);

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_score(BatchView b, ScoreParams p) {
     __shared__ uint32_t s_hist[HV_STATS_AREA_BINS];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t chunk = blockIdx.x;
-    if (b.frame_select && !b.frame_select[f]) return;
+    if (b.frame_select && !(b.frame_select[f] & 1u)) return;
     const uint32_t ncomp = b.ncomp[f];
     const uint32_t nb = min(ncomp, (uint32_t)b.blob_cap);
     const uint32_t nchunks = max((nb + 255u) / 256u, 1u);
