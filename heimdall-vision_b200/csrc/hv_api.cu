@@ -20,7 +20,17 @@ using namespace hv;
 
 namespace {
 
-constexpr int kSyncSlots = 5;  // scratch sets rotated by the synchronous / device-resident entry points (see enqueue_pipeline)
+// scratch sets rotated by the synchronous / device-resident entry points = batches in flight on the device (see
+// enqueue_pipeline); HV_PIPELINE_DEPTH overrides the default for experiments
+int sync_slots() {
+    static const int v = [] {
+        const char *e = getenv("HV_PIPELINE_DEPTH");
+        const int d = e ? atoi(e) : 5;
+        return d < 2 ? 2 : (d > 8 ? 8 : d);
+    }();
+    return v;
+}
+#define kSyncSlots (sync_slots())
 
 thread_local std::string g_create_error;
 
@@ -519,9 +529,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // The caller's output planes are not tied to our slots: if this batch writes planes that one of the batches still in
     // flight wrote (a caller rotating fewer sets than we have slots), K1 also waits for that batch's per-frame kernel.
     b.ccl_wait_n = 0;
+    bool conflict_overflow = false;
     if (b.ccl_done && ctx->last_valid && ctx->last_stream == st)
         for (const auto &q : ctx->in_flight)
-            if (q.done && (q.mask == (const void *)b.mask || q.labels == (const void *)b.labels) && b.ccl_wait_n < 4) {
+            if (q.done && (q.mask == (const void *)b.mask || q.labels == (const void *)b.labels)) {
+                if (b.ccl_wait_n == 4) {  // more conflicts than K1 can wait for: this batch is launched in plain stream order
+                    conflict_overflow = true;
+                    break;
+                }
                 b.ccl_wait_flag[b.ccl_wait_n] = q.done;
                 b.ccl_wait_val[b.ccl_wait_n] = q.expected;
                 b.ccl_wait_n++;
@@ -576,7 +591,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         gp.blur_radius = 0;
         gp.write_blur = want_blur ? 1 : 0;
         ProfScope ps(ctx, HV_K_PREPROCESS, st);
-        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
+        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 && !conflict_overflow &&
                          ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
         gp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
@@ -618,7 +633,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         // Programmatic dependent launch: if the kernel right before this one on the stream is the previous batch's fused
         // per-frame CCL kernel (25 CTAs, latency-bound) and the two batches share no buffers, K1 may start while it is
         // still running.  Anything else in between (copies, events, other kernels) means plain stream order.
-        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 &&
+        const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 && !conflict_overflow &&
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
                          !getenv("HV_NO_PDL");
         pp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
