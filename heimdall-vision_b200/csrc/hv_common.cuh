@@ -74,7 +74,6 @@ struct PreprocessParams {
     int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
     int tail_tiles;
     int ctas_per_sm;    // TMA kernel: resident CTAs per SM to launch (0 = default); 4 leaves room for the small CCL build
-    int reserve_from_smid; // experiment: K1 CTAs on SMs with this id or above exit at once (0 = off)
     int wait_hint_ns;   // TMA kernel: suspend-time hint of mbarrier.try_wait
     int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)

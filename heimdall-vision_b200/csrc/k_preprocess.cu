@@ -662,11 +662,6 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     unsigned long long t_cta0 = 0;
     if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
 
-    if (p.reserve_from_smid > 0) {  // experiment: leave the SMs from this id on to other kernels
-        unsigned int smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if ((int)smid >= p.reserve_from_smid) return;
-    }
     // the per-frame CCL kernel of this batch may be launched now (programmatic dependent launch): its CTAs become
     // resident as ours retire and wait there for this grid to complete, which takes its launch latency off the step
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1064,8 +1059,6 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.claim_ahead = e_claim;
     static const int e_hint = getenv("HV_K1_WAIT_HINT_NS") ? atoi(getenv("HV_K1_WAIT_HINT_NS")) : 10000000;
     q.wait_hint_ns = e_hint;
-    static const int e_res = getenv("HV_EXP_RESERVE_SMS") ? atoi(getenv("HV_EXP_RESERVE_SMS")) : 0;
-    q.reserve_from_smid = e_res > 0 ? num_sms - e_res : 0;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
