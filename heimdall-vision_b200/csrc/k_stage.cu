@@ -167,23 +167,32 @@ constexpr int kMorphReach = 28;
 constexpr int kMorphRows = 32 + 2 * kMorphReach;
 constexpr int kMorphCols = 6;
 
-// One separable pass over the staged rows [r_lo, r_hi): window [-lo, +hi] along the row (H) or the column (V).
+// One separable pass over the staged rows [r_lo, r_hi): window [-lo, +hi] along the row (H) or the column (V).  What
+// depends only on the thread's words -- their position and the in-image masks of the word and its neighbours -- is
+// computed once per tile (MorphItem), not once per pass: the passes themselves are a few loads, shifts and stores.
+// packed: staged row | column << 8 | flags << 16, flags: 1 row inside the image, 2 / 4 / 8 word c-1 / c / c+1 inside the
+// image (and the staged region), 16 / 32 / 64 that word is the row's last one (tail mask); 0xffffffff = no word
+__device__ __forceinline__ uint32_t morph_word_mask(uint32_t item, uint32_t in_bit, uint32_t tail_bit, uint32_t tail_mask,
+                                                    bool need_row) {
+    const uint32_t fl = item >> 16;
+    if (!(fl & in_bit) || (need_row && !(fl & 1u))) return 0u;
+    return (fl & tail_bit) ? tail_mask : 0xffffffffu;
+}
+
 template <bool DILATE>
 __device__ __forceinline__ void morph_pass_h(const uint32_t (*src)[kMorphCols], uint32_t (*dst)[kMorphCols], int lo, int hi,
-                                             int r_lo, int r_hi, int tid, int y0, int wx0, int H, int ww, uint32_t tail_mask) {
-    const uint32_t ident = DILATE ? 0u : 0xffffffffu;
-    for (int idx = tid; idx < (r_hi - r_lo) * kMorphCols; idx += 256) {
-        const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
-        const int gy = y0 - kMorphReach + r;
-        const bool row_in = gy >= 0 && gy < H;
-        auto rd = [&](int cc) -> uint32_t {
-            if (cc < 0 || cc >= kMorphCols) return ident;
-            const int gwx = wx0 + cc;
-            const uint32_t inm = (!row_in || gwx < 0 || gwx >= ww) ? 0u : (gwx == ww - 1 ? tail_mask : 0xffffffffu);
-            const uint32_t v = src[r][cc];
-            return DILATE ? (v & inm) : (v | ~inm);
-        };
-        const uint32_t L = rd(c - 1), M = rd(c), R = rd(c + 1);
+                                             const uint32_t (&it)[3], uint32_t tail_mask) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (it[q] == 0xffffffffu) continue;
+        const int r = it[q] & 0xff, c = (it[q] >> 8) & 0xff;
+        // outside the image (or the staged region) a word reads as the identity: 0 for dilate, all ones for erode
+        const uint32_t ml = morph_word_mask(it[q], 2u, 16u, tail_mask, true), mc = morph_word_mask(it[q], 4u, 32u, tail_mask, true),
+                       mr = morph_word_mask(it[q], 8u, 64u, tail_mask, true);
+        uint32_t L = c > 0 ? src[r][c - 1] : 0u, M = src[r][c], R = c < kMorphCols - 1 ? src[r][c + 1] : 0u;
+        L = DILATE ? (L & ml) : (L | ~ml);
+        M = DILATE ? (M & mc) : (M | ~mc);
+        R = DILATE ? (R & mr) : (R | ~mr);
         uint32_t acc = M;
         for (int dx = 1; dx <= hi; dx++) {
             const uint32_t t = __funnelshift_r(M, R, dx);
@@ -197,23 +206,23 @@ __device__ __forceinline__ void morph_pass_h(const uint32_t (*src)[kMorphCols], 
     }
 }
 
+// rows [v_lo, v_hi] are the staged rows that lie inside the image (and inside the staged region)
 template <bool DILATE>
 __device__ __forceinline__ void morph_pass_v(const uint32_t (*src)[kMorphCols], uint32_t (*dst)[kMorphCols], int lo, int hi,
-                                             int r_lo, int r_hi, int tid, int y0, int wx0, int H, int ww, uint32_t tail_mask) {
-    for (int idx = tid; idx < (r_hi - r_lo) * kMorphCols; idx += 256) {
-        const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
-        const int gwx = wx0 + c;
-        const uint32_t colm = (gwx < 0 || gwx >= ww) ? 0u : (gwx == ww - 1 ? tail_mask : 0xffffffffu);
+                                             const uint32_t (&it)[3], uint32_t tail_mask, int v_lo, int v_hi) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        if (it[q] == 0xffffffffu) continue;
+        const int r = it[q] & 0xff, c = (it[q] >> 8) & 0xff;
         uint32_t acc = DILATE ? 0u : 0xffffffffu;
-        // rows outside [r_lo, r_hi) were not staged: whatever they hold cannot reach the centre
-        const int a_lo = max(r - lo, r_lo), a_hi = min(r + hi, r_hi - 1);
+        const int a_lo = max(r - lo, v_lo), a_hi = min(r + hi, v_hi);
         for (int rr = a_lo; rr <= a_hi; rr++) {
-            const int gy = y0 - kMorphReach + rr;
-            const uint32_t inm = (gy >= 0 && gy < H) ? colm : 0u;
             const uint32_t v = src[rr][c];
-            acc = DILATE ? (acc | (v & inm)) : (acc & (v | ~inm));
+            acc = DILATE ? (acc | v) : (acc & v);
         }
-        dst[r][c] = acc;
+        // the column mask of the word is the same in every row: apply it once
+        const uint32_t colm = morph_word_mask(it[q], 4u, 32u, tail_mask, false);
+        dst[r][c] = DILATE ? (acc & colm) : (acc | ~colm);
     }
 }
 
@@ -306,25 +315,40 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
             s_next[it & 1] = pending;
             if (pending < count) pending = atomicAdd(ctrl + 1, 1u);
         }
-        const size_t t = tile_list[cur];
-        const size_t f = t / per_frame;
-        const int j = (int)(t - f * per_frame);
+        const uint32_t t = tile_list[cur];  // 32-bit arithmetic: the 64-bit divisions were a quarter of the kernel's instructions
+        const uint32_t f32 = t / (uint32_t)per_frame;
+        const size_t f = f32;
+        const int j = (int)(t - f32 * (uint32_t)per_frame);
         const int ty = j / b.tiles_x, tx = j - ty * b.tiles_x;
         const int y0 = ty * 32, wx0 = tx * 4 - 1;
         const uint32_t *fb = b.bits + f * (size_t)H * WW;
         // all loads of the thread first, then the shared-memory stores: one global-memory latency per tile
         uint32_t v[3];
+        uint32_t item[3];
+        auto col_flags = [&](int cc, uint32_t in_bit, uint32_t tail_bit) -> uint32_t {
+            const int gwx = wx0 + cc;
+            if (cc < 0 || cc >= kMorphCols || gwx < 0 || gwx >= WW) return 0u;
+            return in_bit | (gwx == WW - 1 ? tail_bit : 0u);
+        };
 #pragma unroll
         for (int q = 0; q < 3; q++) {
             const int idx = tid + 256 * q;
+            v[q] = 0;
+            item[q] = 0xffffffffu;
+            if (idx >= n_staged) continue;  // (two 3 x 3 kernels stage 240 words: one per thread)
             const int r = r_lo + idx / kMorphCols, c = idx % kMorphCols;
             const int gy = y0 - kMorphReach + r, gwx = wx0 + c;
-            v[q] = 0;
-            if (idx < n_staged && gy >= 0 && gy < H && gwx >= 0 && gwx < WW) {
+            const bool row_in = gy >= 0 && gy < H;
+            item[q] = idx < n_staged ? ((uint32_t)r | ((uint32_t)c << 8) |
+                                        (((row_in ? 1u : 0u) | col_flags(c - 1, 2u, 16u) | col_flags(c, 4u, 32u) | col_flags(c + 1, 8u, 64u)) << 16))
+                                     : 0xffffffffu;
+            if (idx < n_staged && row_in && gwx >= 0 && gwx < WW) {
                 v[q] = __ldg(fb + (size_t)gy * WW + gwx);
                 if (gwx == WW - 1) v[q] &= tail_mask;
             }
         }
+        // staged rows inside the image and the staged region (for the vertical passes)
+        const int v_lo = max(r_lo, kMorphReach - y0), v_hi = min(r_hi - 1, kMorphReach + (H - 1 - y0));
         __syncthreads();  // the previous tile's readers of s_a / s_b / s_w are done; s_next[it & 1] is published
         const unsigned int nxt = s_next[it & 1];
 #pragma unroll
@@ -345,14 +369,14 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
             // open = erode, dilate; close = dilate, erode.  The two dilations in the middle are one dilation with the
             // summed window (a maximum over in-image pixels of a maximum over in-image pixels, and the image is convex).
             if (open_k > 0) {
-                morph_pass_h<false>(src, dst, lo_o, hi_o, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
-                morph_pass_v<false>(src, dst, lo_o, hi_o, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+                morph_pass_h<false>(src, dst, lo_o, hi_o, item, tail_mask), flip();
+                morph_pass_v<false>(src, dst, lo_o, hi_o, item, tail_mask, v_lo, v_hi), flip();
             }
-            morph_pass_h<true>(src, dst, lo_o + lo_c, hi_o + hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
-            morph_pass_v<true>(src, dst, lo_o + lo_c, hi_o + hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+            morph_pass_h<true>(src, dst, lo_o + lo_c, hi_o + hi_c, item, tail_mask), flip();
+            morph_pass_v<true>(src, dst, lo_o + lo_c, hi_o + hi_c, item, tail_mask, v_lo, v_hi), flip();
             if (close_k > 0) {
-                morph_pass_h<false>(src, dst, lo_c, hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
-                morph_pass_v<false>(src, dst, lo_c, hi_c, r_lo, r_hi, tid, y0, wx0, H, WW, tail_mask), flip();
+                morph_pass_h<false>(src, dst, lo_c, hi_c, item, tail_mask), flip();
+                morph_pass_v<false>(src, dst, lo_c, hi_c, item, tail_mask, v_lo, v_hi), flip();
             }
             if (tid < 128) {
                 const int r = tid >> 2, wq = tid & 3;

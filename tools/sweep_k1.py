@@ -13,7 +13,9 @@ comp = os.environ.get('SWEEP_COMPRESS', '1') == '1'
 nout = int(os.environ.get('SWEEP_OUTS', str(det.pipeline_depth())))
 outs = [(det.device_alloc((n, h, w), np.uint8, comp), det.device_alloc((n, h, w), np.int32, comp)) for _ in range(nout)]
 print('outputs compressed:', outs[0][0].compressed, outs[0][1].compressed)
-def step(i): det.enqueue_device(pool[i % 8].data_ptr(), n, h, w, 1, None, outs[i % nout][0].data_ptr(), outs[i % nout][1].data_ptr())
+mk = int(os.environ.get('SWEEP_MORPH', '0'))
+params = hc.make_params(morph_open_k=mk, morph_close_k=mk) if mk else None
+def step(i): det.enqueue_device(pool[i % 8].data_ptr(), n, h, w, 1, params, outs[i % nout][0].data_ptr(), outs[i % nout][1].data_ptr())
 for i in range(10): step(i)
 torch.cuda.synchronize()
 best = 1e9; tot = 0
