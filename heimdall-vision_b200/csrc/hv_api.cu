@@ -175,6 +175,7 @@ struct Slot {
     DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
     uint32_t ccl_expected = 0;  // frames handed to the per-frame CCL kernel on this slot so far (sched[7] counts them done)
     uint32_t k1_expected = 0;   // K1 launches with a launch counter on this slot so far (sched[9] counts them done)
+    uint32_t scan_expected = 0, tiles_expected = 0;  // likewise for the morphology kernels (sched[11], sched[12])
     PinBuf<uint32_t> h_flags;
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
@@ -422,7 +423,8 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
     if (!s.sched.p) {  // K1's tile scheduler: {next tile, CTAs done}; the kernel rearms it itself
         // [0..1] K1's tile counter, [4..6] the fused morphology kernels, [7] frames the per-frame CCL kernel is through
-        // with, [8] K1 CTAs done in the running launch, [9] K1 launches done
+        // with, [8] K1 CTAs done in the running launch, [9] K1 launches done, [10..12] morphology: scan CTAs done, scan
+        // launches done, tiles launches done
         HV_TRY_CUDA(ctx, s.sched.reserve(16));
         HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 16 * sizeof(uint32_t)));
     }
@@ -558,17 +560,21 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     }
     // Small build of the per-frame kernel (co-resident with four K1 CTAs per SM): plain box path only.  After a frame did
     // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
-    bool ccl_small = fused && !morph && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
+    const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
+    // counter chain through the morphology kernels too (K1 -> scan -> tiles -> CCL), HV_NO_MORPH_CHAIN: griddepcontrol.wait
+    const bool morph_chain = morph_fused_plan && !getenv("HV_NO_MORPH_CHAIN");
+    bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
     PreprocessParams pp{};
-    pp.ctas_per_sm = ccl_small ? 4 : 0;  // 0 = the kernel's default
+    // resident K1 CTAs per SM (0 = the kernel's default): 4 leave room for a CTA of the small CCL build, 3 for one of the
+    // morphology tiles kernel as well
+    pp.ctas_per_sm = ccl_small ? (morph ? 3 : 4) : 0;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
     // Morphology in the fused kernel (k <= 15): K1 writes mask and labels as usual and the morphology kernel rewrites only
     // the tiles in reach of foreground.  Multi-pass fallback: K1 writes the bit plane only, everything is expanded later.
-    const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
     if (morph_fused_plan) {
         const size_t ntiles = (size_t)n * ((h + 31) / 32) * b.tiles_x;
         HV_TRY_CUDA(ctx, s.rowflags_tmp.reserve((size_t)n * b.rf_stride));
@@ -580,7 +586,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.init_labels = (morph && !morph_fused_plan) ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
     // K1 (TMA kernel) publishes a launch counter for the per-frame CCL kernel that follows it directly
-    unsigned int *k1_flag = (b.ccl_done && fused && !morph && !getenv("HV_NO_K1_FLAG")) ? s.sched.p + 9 : nullptr;
+    unsigned int *k1_flag = (b.ccl_done && fused && (!morph || (morph_chain && ccl_small)) && !getenv("HV_NO_K1_FLAG")) ? s.sched.p + 9 : nullptr;
     kb.k1_done = k1_flag;
     // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
     bool gauss_fused = false, k1_tma = false;
@@ -643,6 +649,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         k1_tma = used_tma;
         ctx->launches++;
     }
+    if (k1_flag && k1_tma) {
+        s.k1_expected++;
+        b.k1_done = k1_flag;
+        b.k1_wait_value = s.k1_expected;
+    }
     bool morph_fused = false;
     if (morph) {
         ProfScope ps(ctx, HV_K_MORPH, st);
@@ -650,10 +661,21 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
             // open + close + expansion in one kernel, launched ahead of K1's completion; its result goes to the other
             // bit plane, which is the one the CCL reads from here on
             const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !getenv("HV_NO_PDL");
+            // counter chain: the scan waits for K1's launch counter (b.k1_done), the tiles kernel for the scan's, and the
+            // per-frame CCL kernel for the tiles kernel's (handed to it in the k1_done fields)
+            unsigned int *chain = (b.k1_done && morph_chain) ? s.sched.p + 10 : nullptr;
+            if (chain) s.scan_expected++;
             HV_TRY_CUDA(ctx, launch_morph_expand(b, pr.morph_open_k, pr.morph_close_k, b.bits_tmp, s.rowflags_tmp.p,
-                                                 s.tile_list.p, s.sched.p + 4, pdl_mid, st));
+                                                 s.tile_list.p, s.sched.p + 4, chain, s.scan_expected, ctx->num_sms, pdl_mid, st));
             std::swap(b.bits, b.bits_tmp);
             b.rowflags = s.rowflags_tmp.p;
+            if (chain) {
+                s.tiles_expected++;
+                b.k1_done = chain + 2;
+                b.k1_wait_value = s.tiles_expected;
+            } else {
+                b.k1_done = nullptr;  // the per-frame kernel waits with griddepcontrol.wait
+            }
             ctx->launches += 2;
             morph_fused = true;
         } else {
@@ -662,11 +684,6 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
             HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
             ctx->launches += nl + 1;
         }
-    }
-    if (k1_flag && k1_tma) {
-        s.k1_expected++;
-        b.k1_done = k1_flag;
-        b.k1_wait_value = s.k1_expected;
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
     if (fused && getenv("HV_EXP_K1_ONLY")) {

@@ -128,7 +128,8 @@ cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s);
 bool morph_expand_supported(int open_k, int close_k);
 cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uint32_t *bits_out, uint8_t *rowflags_out,
-                                uint32_t *tile_list, unsigned int *ctrl, bool pdl, cudaStream_t s);
+                                uint32_t *tile_list, unsigned int *ctrl, unsigned int *chain, unsigned int scan_expected,
+                                int num_sms, bool pdl, cudaStream_t s);
 cudaError_t launch_morph(const BatchView &b, int open_k, int close_k, int *n_launches, cudaStream_t s);
 cudaError_t launch_ccl_merge(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);

@@ -231,10 +231,23 @@ __device__ __forceinline__ void morph_pass_v(const uint32_t (*src)[kMorphCols], 
 // of the tiles to the left only the last word matters (reach < 32 px), of those to the right the first, of the tiles above
 // and below the row groups within reach -- and appends the tile to a work list (warp-aggregated).  A tile that is not
 // listed keeps what K1 wrote for it (zeros: its own mask is empty); its occupancy record for the CCL is zeroed here.
+// chain (optional): {scan CTAs done, scan launches done, tiles launches done} -- with it, and with K1's launch counter in
+// b.k1_done, the kernels of the morphology variant hand over through counters like the plain path does (see
+// k_ccl_frame.cu: griddepcontrol.wait would make every kernel wait for the whole previous batch).
 __global__ void __launch_bounds__(256) k_morph_scan(BatchView b, int reach, uint8_t *rowflags_out, uint32_t *tile_list,
-                                                    unsigned int *ctrl) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // K1 may still be running (programmatic dependent launch)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                                                    unsigned int *ctrl, unsigned int *chain) {
+    if (chain && b.k1_done) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (threadIdx.x == 0) {
+            const volatile unsigned int *flag = b.k1_done;
+            while ((int)(*flag - b.k1_wait_value) < 0) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // K1 may still be running (programmatic dependent launch)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     const int tiles_y = (b.h + 31) / 32;
     const size_t per_frame = (size_t)tiles_y * b.tiles_x, total = per_frame * b.n;
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(256) k_morph_scan(BatchView b, int reach, uint
                 const int nx = tx + dx;
                 if (nx < 0 || nx >= b.tiles_x) continue;
                 const uint32_t cols = dx < 0 ? 0x08080808u : (dx > 0 ? 0x01010101u : 0x0f0f0f0fu);
-                acc |= __ldg(occ + (size_t)ny * b.tiles_x + nx) & rows & cols;
+                acc |= __ldcg(occ + (size_t)ny * b.tiles_x + nx) & rows & cols;  // (L2: written by a K1 this CTA may have waited for)
             }
         }
         busy = acc != 0;
@@ -278,13 +291,25 @@ __global__ void __launch_bounds__(256) k_morph_scan(BatchView b, int reach, uint
         base = __shfl_sync(0xffffffffu, base, 0);
         if (busy) tile_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)t;
     }
+    if (chain) {  // the last CTA of the launch publishes "scan done"
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(chain, 1u) == gridDim.x - 1) {
+                chain[0] = 0;
+                __threadfence();
+                atomicAdd(chain + 1, 1u);
+            }
+        }
+    }
 }
 
 // A8 for the listed tiles: persistent CTAs take entries of the work list through an atomic cursor (requested one
 // iteration ahead, so its round trip is never waited for).  ctrl = {list length, cursor, CTAs done}; the last CTA to
 // finish rearms all three for the next launch.
 __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, int close_k, uint32_t *bits_out,
-                                                     uint8_t *rowflags_out, const uint32_t *tile_list, unsigned int *ctrl) {
+                                                     uint8_t *rowflags_out, const uint32_t *tile_list, unsigned int *ctrl,
+                                                     unsigned int *chain, unsigned int scan_expected) {
     __shared__ uint32_t s_a[kMorphRows][kMorphCols], s_b[kMorphRows][kMorphCols];
     __shared__ uint32_t s_w[32][4];
     __shared__ unsigned int s_next[2];
@@ -300,8 +325,18 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
     const int reach = min(kMorphReach, 2 * max(lo_o, hi_o) + 2 * max(lo_c, hi_c));
     const int r_lo = kMorphReach - reach, r_hi = kMorphReach + 32 + reach;
     const int n_staged = (r_hi - r_lo) * kMorphCols;
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // the scan (and K1 before it) have completed
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (chain) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (tid == 0) {
+            const volatile unsigned int *flag = chain + 1;
+            while ((int)(*flag - scan_expected) < 0) __nanosleep(200);
+            __threadfence();
+        }
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the scan (and K1 before it) have completed
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     const unsigned int count = *reinterpret_cast<volatile unsigned int *>(ctrl);
     unsigned int pending = 0;
     if (tid == 0) {
@@ -315,7 +350,7 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
             s_next[it & 1] = pending;
             if (pending < count) pending = atomicAdd(ctrl + 1, 1u);
         }
-        const uint32_t t = tile_list[cur];  // 32-bit arithmetic: the 64-bit divisions were a quarter of the kernel's instructions
+        const uint32_t t = __ldcg(tile_list + cur);  // 32-bit arithmetic: the 64-bit divisions were a quarter of the kernel's instructions
         const uint32_t f32 = t / (uint32_t)per_frame;
         const size_t f = f32;
         const int j = (int)(t - f32 * (uint32_t)per_frame);
@@ -343,7 +378,7 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
                                         (((row_in ? 1u : 0u) | col_flags(c - 1, 2u, 16u) | col_flags(c, 4u, 32u) | col_flags(c + 1, 8u, 64u)) << 16))
                                      : 0xffffffffu;
             if (idx < n_staged && row_in && gwx >= 0 && gwx < WW) {
-                v[q] = __ldg(fb + (size_t)gy * WW + gwx);
+                v[q] = __ldcg(fb + (size_t)gy * WW + gwx);
                 if (gwx == WW - 1) v[q] &= tail_mask;
             }
         }
@@ -403,9 +438,16 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
         expand_tile(b, f, tx, ty, s_w, any_out, tid);
         cur = nxt;
     }
+    __syncthreads();  // every thread of the CTA is past its stores
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(ctrl + 2, 1u) == gridDim.x - 1) ctrl[0] = 0, ctrl[1] = 0, ctrl[2] = 0;
+        if (atomicAdd(ctrl + 2, 1u) == gridDim.x - 1) {
+            ctrl[0] = 0, ctrl[1] = 0, ctrl[2] = 0;
+            if (chain) {  // "tiles done": the per-frame CCL kernel of the batch may read the planes
+                __threadfence();
+                atomicAdd(chain + 2, 1u);
+            }
+        }
     }
 }
 
@@ -590,7 +632,8 @@ int one_wave_grid(K kernel, int block) {
 }
 
 cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uint32_t *bits_out, uint8_t *rowflags_out,
-                                uint32_t *tile_list, unsigned int *ctrl, bool pdl, cudaStream_t s) {
+                                uint32_t *tile_list, unsigned int *ctrl, unsigned int *chain, unsigned int scan_expected,
+                                int num_sms, bool pdl, cudaStream_t s) {
     const size_t tiles = (size_t)b.n * ((b.h + 31) / 32) * b.tiles_x;
     auto reach1 = [](int k) { return k > 0 ? 2 * std::max(k / 2, k - 1 - k / 2) : 0; };
     const int reach = std::min(kMorphReach, reach1(open_k) + reach1(close_k));
@@ -603,12 +646,15 @@ cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uin
     cfg.stream = s;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_morph_scan, b, reach, rowflags_out, tile_list, ctrl);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_morph_scan, b, reach, rowflags_out, tile_list, ctrl, chain);
     if (e != cudaSuccess) return e;
+    // counter chain: one CTA per SM, so that the whole grid is resident next to K1 and the CCL kernels at once (it has to
+    // be, to release the kernel behind it); otherwise one full wave
     static const int wave = one_wave_grid(k_morph_tiles, 256);
-    cfg.gridDim = dim3((unsigned)std::min<size_t>(tiles, (size_t)wave));
+    cfg.gridDim = dim3((unsigned)std::min<size_t>(tiles, (size_t)(chain ? num_sms : wave)));
     cfg.numAttrs = 1;  // behind the scan, whatever preceded that
-    return cudaLaunchKernelEx(&cfg, k_morph_tiles, b, open_k, close_k, bits_out, rowflags_out, (const uint32_t *)tile_list, ctrl);
+    return cudaLaunchKernelEx(&cfg, k_morph_tiles, b, open_k, close_k, bits_out, rowflags_out, (const uint32_t *)tile_list, ctrl,
+                              chain, scan_expected);
 }
 
 cudaError_t launch_expand_bits(const BatchView &b, cudaStream_t s) {

@@ -593,8 +593,8 @@ def test_compressible_device_buffers(oracle, detector):
     d_in.free()
 
 
-@pytest.mark.parametrize("n_sets", [1, 2, 3, 5])
-def test_batches_in_flight_with_rotating_output_sets(oracle, n_sets):
+@pytest.mark.parametrize("n_sets,morph_k", [(1, 0), (2, 0), (3, 0), (5, 0), (2, 3), (5, 3), (5, 7)])
+def test_batches_in_flight_with_rotating_output_sets(oracle, n_sets, morph_k):
     """Streaming use of enqueue_device: many batches enqueued back to back, the kernels of several of them in flight at
     once (K1 of a batch starts while the per-frame CCL kernels of the previous ones still run), output planes rotated
     over n_sets sets -- fewer than the library's pipeline depth means K1 has to wait on the device for the batch that
@@ -612,19 +612,21 @@ def test_batches_in_flight_with_rotating_output_sets(oracle, n_sets):
             a.set(bt)
         masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(n_sets)]
         labels = [det.device_alloc((n, h, w), np.int32) for _ in range(n_sets)]
+        params = hc.make_params(morph_open_k=morph_k, morph_close_k=morph_k) if morph_k else None
+        okw = dict(morph_open_k=morph_k, morph_close_k=morph_k) if morph_k else {}
         for rep in range(2):
             for i in range(n_batches):
-                det.enqueue_device(d_in[i].ptr, n, h, w, 1, None, masks[i % n_sets].ptr, labels[i % n_sets].ptr)
+                det.enqueue_device(d_in[i].ptr, n, h, w, 1, params, masks[i % n_sets].ptr, labels[i % n_sets].ptr)
             last = det.fetch_results(n)
             for k in range(n_sets):
                 i = max(j for j in range(n_batches) if j % n_sets == k)
                 got_m, got_l = masks[k].get(), labels[k].get()
                 for f in range(n):
-                    ref = oracle.detect_contamination(batches[i][f][:, :, None])
+                    ref = oracle.detect_contamination(batches[i][f][:, :, None], **okw)
                     assert np.array_equal(got_m[f], ref.mask), (n_sets, rep, k, f)
                     assert np.array_equal(got_l[f], ref.labels), (n_sets, rep, k, f)
             for f in range(n):
-                ref = oracle.detect_contamination(batches[n_batches - 1][f][:, :, None])
+                ref = oracle.detect_contamination(batches[n_batches - 1][f][:, :, None], **okw)
                 assert [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in last.defects_of(f)] == \
                     [(d["position"], d["size"], d["confidence"]) for d in ref.defects]
     finally:

@@ -1,3 +1,4 @@
-python tools/sweep_k1.py
 SWEEP_MORPH=3 python tools/sweep_k1.py
+SWEEP_MORPH=3 HV_NO_MORPH_CHAIN=1 python tools/sweep_k1.py
 SWEEP_MORPH=7 python tools/sweep_k1.py
+python tools/sweep_k1.py
