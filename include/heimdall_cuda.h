@@ -192,7 +192,8 @@ HV_API void hv_host_free(hv_ctx *ctx, void *p);
 /* Number of scratch sets the device-resident entry point rotates through = how many batches may be in flight on the
  * device at once.  A caller that passes its own d_mask / d_labels planes to hv_enqueue_device should rotate this many
  * sets of them: a set that is reused earlier is still correct (the preprocess kernel of the new batch waits on the
- * device for the batch that last wrote it), it only costs overlap. */
+ * device for the batch that last wrote it), it only costs overlap.  The input frames of a batch must stay untouched
+ * until the batch has completed (stream-ordered work on the same stream is ordered behind it as usual). */
 HV_API int32_t hv_pipeline_depth(void);
 
 enum { HV_ALLOC_COMPRESSIBLE = 1 };
