@@ -544,6 +544,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                 b.ccl_wait_n++;
             }
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
+    if (getenv("HV_EXP_CCL_NOOP")) b.phase_frame = -12345;
     if (b.phase_ns) {
         cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
         cudaMemsetAsync(ctx->d_phase_ns + 248, 0xff, sizeof(unsigned long long), st);
