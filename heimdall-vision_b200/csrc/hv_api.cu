@@ -559,7 +559,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ctx->dense_batches++;
         if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
     }
-    // Small build of the per-frame kernel (co-resident with four K1 CTAs per SM): plain box path only.  After a frame did
+    // Small build of the per-frame kernel (co-resident with K1 CTAs): box-blur path, with or without the fused morphology.  After a frame did
     // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
     const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
     // counter chain through the morphology kernels too (K1 -> scan -> tiles -> CCL), HV_NO_MORPH_CHAIN: griddepcontrol.wait

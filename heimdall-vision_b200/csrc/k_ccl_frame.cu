@@ -30,7 +30,7 @@ namespace hv {
 namespace {
 
 // Two builds of the kernel.  Big: 512 threads, 4096 non-zero words / 8192 runs / 2048 components per frame, 170 KB of
-// shared memory -- a CTA needs an SM to itself.  Small: 256 threads (64 registers), 2048 / 4096 / 512, 68 KB -- fits next to
+// shared memory -- a CTA needs an SM to itself.  Small: 256 threads (72 registers), 2048 / 4096 / 512, 68 KB -- fits next to
 // four resident CTAs of K1 (155 KB), so its CTAs become resident the moment the kernel is launched, release the next K1
 // at once (see the top of the kernel) and simply wait there for their own K1 to finish: the chain of K1 launches has no
 // gap and no SM is set aside.  hv_api.cu picks the build per batch (small first; a frame that does not fit is flagged).
