@@ -1,4 +1,4 @@
-SWEEP_MORPH=3 python tools/sweep_k1.py
-SWEEP_MORPH=3 HV_MORPH_TILES_PER_SM=2 python tools/sweep_k1.py
-SWEEP_MORPH=3 HV_MORPH_TILES_PER_SM=3 python tools/sweep_k1.py
-SWEEP_MORPH=7 HV_MORPH_TILES_PER_SM=2 python tools/sweep_k1.py
+python tools/sweep_k1.py
+HV_NO_CCL_QUEUE=1 python tools/sweep_k1.py
+python tools/sweep_k1.py
+HV_NO_CCL_QUEUE=1 python tools/sweep_k1.py
