@@ -563,7 +563,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
     const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
     // counter chain through the morphology kernels too (K1 -> scan -> tiles -> CCL), HV_NO_MORPH_CHAIN: griddepcontrol.wait
-    const bool morph_chain = morph_fused_plan && !getenv("HV_NO_MORPH_CHAIN");
+    // (only for small batches: the chain needs the tiles kernel resident as a whole, two CTAs per SM, which pays when launch
+    // gaps and serialisation dominate -- 8000 tiles: 78 -> 66 us -- and costs when the kernels are long -- 256 x 5 MP: 2.0 ->
+    // 2.6 ms)
+    const bool morph_chain = morph_fused_plan && !getenv("HV_NO_MORPH_CHAIN") &&
+                             (size_t)n * ((h + 31) / 32) * ((w + 127) / 128) <= 16384;
     bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
     PreprocessParams pp{};
