@@ -339,19 +339,31 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
     const unsigned int count = *reinterpret_cast<volatile unsigned int *>(ctrl);
+    // thread 0 requests the next list entry AND loads its tile number one iteration ahead (two dependent round trips, 16 %
+    // of the warp samples of this kernel when they sat at the top of the iteration)
+    __shared__ uint32_t s_tile[2];
     unsigned int pending = 0;
+    uint32_t pending_tile = 0;
     if (tid == 0) {
-        s_next[0] = atomicAdd(ctrl + 1, 1u);
+        const unsigned int first = atomicAdd(ctrl + 1, 1u);
+        s_next[0] = first;
+        s_tile[0] = first < count ? __ldcg(tile_list + first) : 0u;
         pending = atomicAdd(ctrl + 1, 1u);
+        pending_tile = pending < count ? __ldcg(tile_list + pending) : 0u;
     }
     __syncthreads();
     unsigned int cur = s_next[0];
+    uint32_t t = s_tile[0];
     for (int it = 1; cur < count; it++) {
         if (tid == 0) {
             s_next[it & 1] = pending;
-            if (pending < count) pending = atomicAdd(ctrl + 1, 1u);
+            s_tile[it & 1] = pending_tile;
+            if (pending < count) {
+                pending = atomicAdd(ctrl + 1, 1u);
+                pending_tile = pending < count ? __ldcg(tile_list + pending) : 0u;
+            }
         }
-        const uint32_t t = __ldcg(tile_list + cur);  // 32-bit arithmetic: the 64-bit divisions were a quarter of the kernel's instructions
+        // 32-bit arithmetic: the 64-bit divisions were a quarter of the kernel's instructions
         const uint32_t f32 = t / (uint32_t)per_frame;
         const size_t f = f32;
         const int j = (int)(t - f32 * (uint32_t)per_frame);
@@ -387,6 +399,7 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
         const int v_lo = max(r_lo, kMorphReach - y0), v_hi = min(r_hi - 1, kMorphReach + (H - 1 - y0));
         __syncthreads();  // the previous tile's readers of s_a / s_b / s_w are done; s_next[it & 1] is published
         const unsigned int nxt = s_next[it & 1];
+        const uint32_t t_nxt = s_tile[it & 1];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
             const int idx = tid + 256 * q;
@@ -438,6 +451,7 @@ __global__ void __launch_bounds__(256) k_morph_tiles(BatchView b, int open_k, in
         const bool any_out = __syncthreads_or(word != 0);
         expand_tile(b, f, tx, ty, s_w, any_out, tid);
         cur = nxt;
+        t = t_nxt;
     }
     __syncthreads();  // every thread of the CTA is past its stores
     if (tid == 0) {
