@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Throughput of the BASELINE.json configs other than the headline one (configs[2..4]); the headline config is
 bench.py's.  Device-resident inputs, CUDA events on the launching stream, steady state (buffers alternate).
-Every case is checked against the oracle on one frame before it is timed.  Writes a markdown table.
+Every case is checked against the oracle on one frame before it is timed (measurement infrastructure like bench.py: the
+oracle is the checker here, never the thing measured).  Writes a markdown table.
 
 usage: bench_configs.py [out.md] [--quick]
 """
