@@ -29,7 +29,45 @@ __device__ __forceinline__ Scored score_blob(const BatchView &b, const ScorePara
     const uint8_t *gray = b.gray + (size_t)f * b.gray_frame_stride;
     const uint8_t *mask = b.mask + (size_t)f * H * W;
     uint32_t fg_sum = 0, bg_sum = 0, fg_cnt = 0, bg_cnt = 0;
-    if (LOW_REG) {
+    const bool words_ok = W >= 8 && (W & 3) == 0 && (b.gray_row_stride & 3) == 0 && (b.gray_frame_stride & 3) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(b.gray) | reinterpret_cast<uintptr_t>(b.mask)) & 3) == 0;
+    if (LOW_REG && words_ok) {
+        // The five bytes of a probe row lie inside the eight bytes that start at the 4-byte boundary at or below their first
+        // one: two 32-bit loads per row and plane, 20 loads for the whole probe, all in flight together -- one round trip
+        // with 20 registers instead of five round trips (one row each) or 50 registers.  Rows / columns outside the clamped
+        // window are loaded from clamped addresses and ignored.
+        const int xa = min(max(icx - 2, 0) & ~3, W - 8);  // first byte of the 8-byte window, inside the row
+        uint32_t gw[5][2], mw[5][2];
+#pragma unroll
+        for (int dy = 0; dy < 5; dy++) {
+            const int yc = min(max(icy - 2 + dy, 0), H - 1);
+            const uint32_t *grow = reinterpret_cast<const uint32_t *>(gray + (size_t)yc * b.gray_row_stride + xa);
+            const uint32_t *mrow = reinterpret_cast<const uint32_t *>(mask + (size_t)yc * W + xa);
+            gw[dy][0] = grow[0], gw[dy][1] = grow[1];
+            mw[dy][0] = __ldcg(mrow), mw[dy][1] = __ldcg(mrow + 1);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 5; dy++) {
+            const int y = icy - 2 + dy;
+            if (y < y_lo || y > y_hi) continue;
+            const uint64_t g8 = (uint64_t)gw[dy][0] | ((uint64_t)gw[dy][1] << 32), m8 = (uint64_t)mw[dy][0] | ((uint64_t)mw[dy][1] << 32);
+#pragma unroll
+            for (int dx = 0; dx < 5; dx++) {
+                const int x = icx - 2 + dx;
+                if (x >= x_lo && x <= x_hi) {
+                    const int sh = 8 * (x - xa);
+                    const uint32_t g = (uint32_t)(g8 >> sh) & 0xffu, m = (uint32_t)(m8 >> sh) & 0xffu;
+                    if (m == 255) {
+                        fg_sum += g;
+                        fg_cnt++;
+                    } else {
+                        bg_sum += g;
+                        bg_cnt++;
+                    }
+                }
+            }
+        }
+    } else if (LOW_REG) {
         // one probe row per round trip (10 loads in flight), accumulated at once
 #pragma unroll 1
         for (int dy = -2; dy <= 2; dy++) {
