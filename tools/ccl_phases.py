@@ -15,4 +15,4 @@ pt = np.array(det.phase_times()[:192], dtype=np.int64).reshape(12, 16); t0 = pt[
 names = ['start', 'p0 compaction', 'p1 fetch+nodes', 'p2a hook', 'p2b jump', 'p2c edges', 'p3 rank', 'p4 labels+stats', 'p5 score']
 for i in range(9):
     v = pt[i][pt[i] > 0]
-    if len(v): print('  %-16s warps reach it at %.1f .. %.1f us' % (names[i], (v.min() - t0) / 1e3, (v.max() - t0) / 1e3))
+    if len(v): print('  %-16s warps reach it at %.1f .. %.1f us' % (names[i], (v.min() - t0) / 1e3, (v.max() - t0) / 1e3), ' per warp:', ' '.join('%.1f' % ((x - t0) / 1e3) for x in pt[i] if x > 0))
