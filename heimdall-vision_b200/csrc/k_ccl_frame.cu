@@ -64,6 +64,7 @@ struct FrameSmem {
     uint16_t woff[C::kCapW + 8];  // first node of every compacted word
     uint32_t edges[C::kCapE];     // residual union edges (u << 16 | v), see phase 2
     uint32_t n_edges;
+    uint32_t cursor;              // phase 2: next word to hand out
     uint16_t rnk[C::kCapN];       // rank of the component among the roots (valid at root nodes)
     uint8_t node_len[C::kCapN];
     uint32_t warp_tmp[32];
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     uint8_t *stage = reinterpret_cast<uint8_t *>(S.parent);
     const int bands_per_chunk = min(nbands, (int)(2 * sizeof(uint32_t) * kCapN) / band_bytes);
     if (tid < HV_STATS_AREA_BINS) S.hist[tid] = 0;
-    if (tid == 0) S.area_sum = 0, S.n_edges = 0;
+    if (tid == 0) S.area_sum = 0, S.n_edges = 0, S.cursor = 0;
     uint32_t nw = 0;
     bool too_big = H > 8192 || W > 8192 || bands_per_chunk < 1;
     for (int b0 = 0; b0 < nbands && !too_big; b0 += bands_per_chunk) {
@@ -330,7 +331,16 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     //   (c) the listed edges are ordinary unions by minimum between the now depth-1 trees, ONE edge per thread: inside
     //       the per-word loops a union (a few hundred cycles of dependent shared-memory accesses and an atomic per
     //       retry) was serialised by the SIMT execution of the nested loops of all 32 lanes -- 8 us for 76 unions.
-    for (uint32_t e = tid; e < nw; e += kFT) {
+    // The words are handed out to the warps 32 at a time through a shared-memory cursor: words with many runs cluster (the
+    // ragged fringe of a thresholded edge: 116 runs in the first 32 words of a bottle frame, 35 in any other 32), and with
+    // a fixed assignment the warp that owned such a cluster took 12 us for this loop where the others took 5.
+    while (true) {
+        uint32_t e = 0;
+        if (lane == 0) e = atomicAdd(&S.cursor, 32u);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= nw) break;
+        e += lane;
+        if (e >= nw) continue;
         const uint32_t i = S.widx[e], m = S.wbits[e];
         const uint32_t base = S.woff[e];
         uint32_t up = 0, ustarts = 0, ubase = 0;
