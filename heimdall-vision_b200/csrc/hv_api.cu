@@ -571,9 +571,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
     PreprocessParams pp{};
-    // resident K1 CTAs per SM (0 = the kernel's default): 4 leave room for a CTA of the small CCL build, 3 for one of the
-    // morphology tiles kernel as well
-    pp.ctas_per_sm = ccl_small ? (morph ? 3 : 4) : 0;
+    // resident K1 CTAs per SM (0 = the kernel's default, 5).  Next to the small CCL build: 3.  Four would fit beside one CTA
+    // of it, but those CTAs often land two to an SM, and two of them leave room for two K1 CTAs whatever K1 asked for --
+    // with three the loss is one CTA instead of two (measured in one call: 41.9 us per step with 4, 41.1 with 3, although
+    // K1 alone is slower with 3: 53.5 vs 50.4 us).  The morphology tiles kernel needs the room as well.
+    pp.ctas_per_sm = ccl_small ? 3 : 0;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
     pp.c_thresh = clamp_threshold(pr.threshold);
     pp.inverse = 1;
