@@ -284,9 +284,12 @@ hv_status fail_cuda(hv_ctx *ctx, cudaError_t e, const char *what) {
         if (_e != cudaSuccess) return fail_cuda((ctx), _e, #expr);     \
     } while (0)
 
-int clamp_threshold(double thr) {
-    // `threshold as i32` (detection.rs:186): truncating, saturating, NaN -> 0; then clamped to [-256, 256], beyond
-    // which the comparison `px < mean - c` is constant for u8 data anyway.
+// `c = threshold as i32` (detection.rs:186): truncating, saturating, NaN -> 0.  The comparison `px < mean - c` is i32
+// arithmetic that WRAPS in the reference's release build (rust/Cargo.toml [profile.release]: no overflow-checks):
+//   c > 255 - 2^31: no wrap for any u8 mean; beyond [-256, 256] the comparison is constant, so c is clamped there;
+//   c <= 255 - 2^31 (threshold <= -2147483393.0): pixels whose window mean is >= T = c + 2^31 wrap to "never
+//   foreground", the others are "always foreground": mask = mean < T.  *wrap_t1 = T + 1 (0 = no wrap).
+int threshold_plan(double thr, int *wrap_t1) {
     long long c;
     if (!(thr == thr))
         c = 0;
@@ -296,6 +299,11 @@ int clamp_threshold(double thr) {
         c = -2147483648LL;
     else
         c = (long long)thr;
+    *wrap_t1 = 0;
+    if (c <= 255LL - 2147483648LL) {
+        *wrap_t1 = (int)(c + 2147483648LL) + 1;
+        return -256;  // negative: no flat-tile skip, no packed fast path
+    }
     if (c > 256) c = 256;
     if (c < -256) c = -256;
     return (int)c;
@@ -577,7 +585,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // K1 alone is slower with 3: 53.5 vs 50.4 us).  The morphology tiles kernel needs the room as well.
     pp.ctas_per_sm = ccl_small ? 3 : 0;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
-    pp.c_thresh = clamp_threshold(pr.threshold);
+    pp.c_thresh = threshold_plan(pr.threshold, &pp.wrap_t1);
     pp.inverse = 1;
     pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
     // Morphology in the fused kernel (k <= 15): K1 writes mask and labels as usual and the morphology kernel rewrites only

@@ -61,6 +61,8 @@ struct BatchView {
 
 struct PreprocessParams {
     int c_thresh;      // clamp(threshold as i32, -256, 256)
+    int wrap_t1;       // 0 = off.  T + 1 when `mean - c` wraps in i32 for pixels with mean >= T = c + 2^31 (c <= 255 - 2^31,
+                       // detection.rs:211 in a release build): the test becomes mean < T (c_thresh is then -256: generic path)
     int blur_radius;   // 0 = input is already blurred / no blur, 2 = fused 5x5 box
     int write_blur;    // also materialise the blurred image (debug)
     int write_mask;    // write the u8 mask (0 when morphology follows and rewrites it)

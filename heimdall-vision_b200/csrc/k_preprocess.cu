@@ -407,7 +407,10 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
                     const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
                     const int cnt = rows * cols;
                     const int px = s_bl[r + kAdaptHalf][c + 8];
-                    const bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
+                    bool t = p.inverse ? ((px + cth + 1) * cnt <= s) : !((px + cth) * cnt <= s);
+                    // i32 wrap of `mean - c` (see PreprocessParams::wrap_t1): where mean >= T the right-hand side wrapped to
+                    // a large negative number, elsewhere it is a large positive one
+                    if (p.wrap_t1) t = (s < (p.wrap_t1 - 1) * cnt) == (p.inverse != 0);
                     fg = t ? 255 : 0;
                 }
                 s_f[r][c] = fg;

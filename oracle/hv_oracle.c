@@ -104,14 +104,17 @@ void hvo_adaptive_threshold(const uint8_t *src, int h, int w, int32_t c, int inv
                 }
             int32_t mean = (int32_t)(sum / count);
             int32_t px = src[(size_t)i * w + j];
-            /* `mean - c` in i32: rustc release wraps on overflow (debug would panic); do it in 64 bits and
-             * compare there -- identical whenever the i32 expression does not overflow, and well-defined in C. */
-            int64_t rhs = (int64_t)mean - (int64_t)c;
+            /* `mean - c` in i32 (detection.rs:211).  The reference's release profile (rust/Cargo.toml [profile.release])
+             * does not enable overflow-checks, so the subtraction WRAPS: for c <= mean - 2^31 (only reachable with
+             * threshold <= -2147483393.0, since `threshold as i32` saturates at i32::MIN) the right-hand side becomes a
+             * large negative number and the inverse test is false.  Unsigned arithmetic is the well-defined C spelling of
+             * that wrap. */
+            int32_t rhs = (int32_t)((uint32_t)mean - (uint32_t)c);
             uint8_t v;
             if (inverse)
-                v = ((int64_t)px < rhs) ? 255 : 0;
+                v = (px < rhs) ? 255 : 0;
             else
-                v = ((int64_t)px > rhs) ? 255 : 0;
+                v = (px > rhs) ? 255 : 0;
             mask[(size_t)i * w + j] = v;
         }
 }

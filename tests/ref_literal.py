@@ -64,7 +64,8 @@ def detect_contamination(image, min_size=10.0, max_size=3000.0, threshold=25.0):
                     s += blurred[y][x]
                     count += 1
             mean = s // count
-            binary[i][j] = 255 if blurred[i][j] < mean - c else 0
+            rhs = (mean - c + 2 ** 31) % 2 ** 32 - 2 ** 31  # i32 arithmetic of a release build wraps (no overflow-checks)
+            binary[i][j] = 255 if blurred[i][j] < rhs else 0
 
     defects = []
     labels = [[0] * width for _ in range(height)]

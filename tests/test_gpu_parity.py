@@ -139,11 +139,24 @@ def test_fast_path_extreme_values(oracle, detector):
     check_frame(oracle, detector, np.full((160, 520, 1), 255, np.uint8), threshold=0.0)
 
 
-@pytest.mark.parametrize("thr", [-1.0, -40.0, -300.0, 0.0, 0.9, 1e12, -1e12, float("nan"), 254.0, 255.0, 256.0, 300.0])
+@pytest.mark.parametrize("thr", [-1.0, -40.0, -300.0, 0.0, 0.9, 1e12, -1e12, float("nan"), 254.0, 255.0, 256.0, 300.0,
+                                 2147483647.0, -2147483648.0, -2147483548.0, -2147483393.0, -2147483392.0, float("-inf")])
 def test_threshold_edge_values(oracle, detector, thr):
+    """`threshold as i32` saturates and `mean - c` wraps in i32 like the reference's release build (detection.rs:186,211):
+    at and below -2147483393.0 pixels whose window mean reaches c + 2^31 are never foreground (-1e12: empty mask), one
+    above that every pixel is."""
     rng = np.random.default_rng(17)
     img = rng.integers(0, 256, (40, 70, 1), dtype=np.uint8)
-    check_frame(oracle, detector, img, min_size=1.0, max_size=1e9, threshold=thr)
+    res, ref = check_frame(oracle, detector, img, min_size=1.0, max_size=1e9, threshold=thr)
+    if thr in (-1e12, -2147483648.0, float("-inf")):
+        assert int(res.frames["fg_pixels"][0]) == 0
+    if thr == -2147483392.0:
+        assert int(res.frames["fg_pixels"][0]) == 40 * 70
+    if thr == -2147483548.0:   # T = 100: foreground exactly where the window mean is below 100
+        assert 0 < int(res.frames["fg_pixels"][0]) < 40 * 70
+    # the same on a frame with interior 128x32 tiles (TMA kernel, 16-px aligned)
+    big = rng.integers(60, 140, (96, 400, 1), dtype=np.uint8)
+    check_frame(oracle, detector, big, min_size=1.0, max_size=1e9, threshold=thr, check_blur=False)
 
 
 def test_size_filters_inclusive(oracle, detector):

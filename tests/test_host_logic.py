@@ -21,12 +21,35 @@ def test_division_free_threshold_test_is_equivalent():
             assert np.array_equal(px > mean - c, ~((px + c) * cnt <= S))
 
 
+def _wrap_i32(v):
+    return (v + 2 ** 31) % 2 ** 32 - 2 ** 31
+
+
 def test_threshold_clamp_does_not_change_results():
-    """Clamping c to [-256, 256] is exact for u8 data: beyond that the comparison is constant."""
+    """`mean - c` is i32 arithmetic that wraps in the reference's release build (detection.rs:211; rust/Cargo.toml
+    [profile.release] has no overflow-checks).  Clamping c to [-256, 256] is exact for u8 data as long as the
+    subtraction does not wrap, i.e. for c > 255 - 2^31; at and below that the library switches to the wrapped form
+    `mask = mean < c + 2^31` (hv_api.cu: threshold_plan)."""
     px = np.arange(256)[:, None]
     mean = np.arange(256)[None, :]
-    for c, cc in [(10 ** 9, 256), (257, 256), (-257, -256), (-2 ** 31, -256)]:
-        assert np.array_equal(px < mean - c, px < mean - cc)
+    for c, cc in [(10 ** 9, 256), (2 ** 31 - 1, 256), (257, 256), (-257, -256), (-2 ** 31 + 256, -256), (-10 ** 9, -256)]:
+        assert np.array_equal(px < _wrap_i32(mean - c), px < mean - cc)
+    for c in [-2 ** 31, -2 ** 31 + 1, -2 ** 31 + 100, -2 ** 31 + 255]:
+        t = c + 2 ** 31                                     # 0..255: pixels whose mean reaches t wrap to "never"
+        assert np.array_equal(px < _wrap_i32(mean - c), np.broadcast_to(mean < t, (256, 256)))
+
+
+def test_oracle_wraps_like_a_release_build():
+    from oracle import oracle as O
+    import ref_literal
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (23, 31, 1), dtype=np.uint8)
+    for thr in (-1e12, -2147483648.0, -2147483548.0, -2147483393.0, -2147483392.0, 2147483647.0, 1e12):
+        got = O.detect_contamination(img, 1.0, 1e9, thr)
+        lit = ref_literal.detect_contamination(img, 1.0, 1e9, thr)
+        assert np.array_equal(got.mask, np.array(lit["binary"], np.uint8)), thr
+    assert int(O.detect_contamination(img, threshold=-1e12).mask.sum()) == 0          # wraps everywhere: never foreground
+    assert int((O.detect_contamination(img, threshold=-2147483392.0).mask == 255).all())  # one above: no wrap, always
 
 
 def test_flat_tile_bound():
