@@ -3,7 +3,8 @@
 
 Workload (BASELINE.json configs[1]): one step = one pass of the hot path (blur -> adaptive threshold -> CCL -> blob
 statistics -> scoring -> reject decision) over a batch of 25 synthetic 1280x1024 u8 bottle frames -- one second of
-line at 90 000 bottles/h.  Inputs rotate over a pool of distinct batches whose total size exceeds the 126 MB L2.
+line at 90 000 bottles/h -- with the batch's results delivered to the host.  Inputs rotate over a pool of distinct
+batches whose total size exceeds the 126 MB L2.  Timing: --repeats windows of --steps steps, median window.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
   python bench.py --impl reference ...                            the reference's CPU path (oracle port, all host threads)
@@ -155,14 +156,14 @@ def cpu_model() -> str:
 # ---------------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank: int, world: int) -> None:
     """The reference arm: the reference's own CPU algorithm (its Rust sources cannot be built here: no cargo/rustc, see
-    DESIGN.md) as restated by the oracle port, with all host threads over independent frames."""
+    DESIGN.md) as restated by the oracle port, with all host threads over independent frames.  One step = the same
+    batch of `--frames` frames the CUDA arm processes per step."""
     if rank != 0:
         return
     import synth
     h, w, nf = args.height, args.width, args.frames
     threads = host_threads()
-    sample = max(1, min(nf, threads))          # frames per step: a bounded sample of the 25-frame batch
-    frames = synth.bottle_batch(sample, h, w, start_index=0)
+    frames = synth.bottle_batch(nf, h, w, start_index=0)
     from concurrent.futures import ThreadPoolExecutor
 
     from oracle import oracle as O
@@ -172,10 +173,10 @@ def run_reference(args, rank: int, world: int) -> None:
     def one(i):
         O.detect_contamination(frames[i][:, :, None], want_intermediates=False)
 
-    ex = ThreadPoolExecutor(threads)  # one pool for the whole run: a step is `sample` frames, one per thread
+    ex = ThreadPoolExecutor(threads)  # one pool for the whole run; ctypes releases the GIL inside the C call
 
     def step():
-        list(ex.map(one, range(sample)))
+        list(ex.map(one, range(nf)))
 
     for _ in range(max(args.warmup, 1)):
         step()
@@ -184,20 +185,39 @@ def run_reference(args, rank: int, world: int) -> None:
         step()
     dt = time.perf_counter() - t0
     ex.shutdown()
-    fps = sample * args.steps / dt
+    fps = nf * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"batch of {nf} synthetic {w}x{h} u8 bottle frames (BASELINE configs[1])",
-                   "frames_per_step_timed": sample, "height": h, "width": w},
+        "config": workload_config(args, 1),
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames per step x {args.steps} steps, one frame per thread; oracle port "
-                                   f"of detection.rs (the Rust reference cannot be built here); CPU: {cpu_model()}"},
+                         "sample": f"all {nf} frames of the batch per step x {args.steps} steps over {threads} threads; "
+                                   f"oracle port of detection.rs (the Rust reference cannot be built here); CPU: {cpu_model()}"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def workload_config(args, world: int) -> dict:
+    """The part of `config` both arms share (the driver compares it)."""
+    return {"workload": f"batch of {args.frames} synthetic {args.width}x{args.height} u8 bottle frames per GPU per step "
+                        f"(BASELINE configs[1]: one second of line at 90k BPH)",
+            "frames_per_step_per_gpu": args.frames, "height": args.height, "width": args.width, "channels": 1,
+            "params": "reference defaults min_size=10 max_size=3000 threshold=25"}
+
+
+def csrc_sha16() -> str:
+    """Fingerprint of the kernel sources: the ncu-measured DRAM traffic in profiles/ is only quoted for the code it was
+    captured from."""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(PKG, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()[:16]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -208,9 +228,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     import heimdall_core as hc
     import hv_dist
     import synth
+    from heimdall_core.batch import DEFECT_DTYPE, RESULT_DTYPE
 
     h, w, nf = args.height, args.width, args.frames
-    K, W = args.steps, args.warmup
+    K, W, R = args.steps, args.warmup, args.repeats
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -228,40 +249,40 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         b = base[perm].astype(np.int16) + rng.integers(-1, 2, size=base.shape, dtype=np.int16)
         pool_host.append(np.clip(b, 0, 255).astype(np.uint8))
     pool_dev = [torch.from_numpy(b).to(dev) for b in pool_host]
-    # hv_pipeline_depth() sets of outputs in rotation: the kernels of several batches are in flight at once (K1 of step
-    # i+1 starts while K1 of step i retires, the per-frame CCL kernels of the last few steps run next to them)
     det = hc.Detector(local_rank, num_slots=args.slots)
     # The output planes come from the library's allocator (hv_device_alloc): memory with L2 compute-data compression, so
     # the almost entirely zero mask / label planes cost less DRAM write time.  --no-compress: plain cudaMalloc memory.
-    n_out = det.pipeline_depth()  # output sets in rotation = batches the library keeps in flight on the device
-    d_mask = [det.device_alloc((nf, h, w), np.uint8, not args.no_compress) for _ in range(n_out)]
-    d_labels = [det.device_alloc((nf, h, w), np.int32, not args.no_compress) for _ in range(n_out)]
+    depth = det.pipeline_depth()  # output sets in rotation = batches the library keeps in flight on the device
+    d_mask = [det.device_alloc((nf, h, w), np.uint8, not args.no_compress) for _ in range(depth)]
+    d_labels = [det.device_alloc((nf, h, w), np.int32, not args.no_compress) for _ in range(depth)]
     out_mem = ("L2-compressible (cuMemCreate, CU_MEM_ALLOCATION_COMP_GENERIC)" if d_labels[0].compressed
                else "plain device memory")
     stream = torch.cuda.current_stream()
     det.set_stream(stream.cuda_stream)
     params = hc.make_params()
+    params_morph = hc.make_params(morph_open_k=3, morph_close_k=3)   # contamination_detector.py:81-87: 3x3 open, 3x3 close
 
-    # ---- parity gate: the timed configuration must agree with the oracle before any number counts ----------------------
-    parity = None
-    def check_against_oracle(res, batch_host, mask_t, labels_t, frames):
+    def check_against_oracle(res, batch_host, mask_t, labels_t, frames, **okw):
         from oracle import oracle as O
         O.build()
         ok = True
         for f in frames:
-            ref = O.detect_contamination(batch_host[f][:, :, None])
+            ref = O.detect_contamination(batch_host[f][:, :, None], **okw)
             ok = ok and (np.array_equal(mask_t.get(f, 1)[0], ref.mask) and
                          np.array_equal(labels_t.get(f, 1)[0], ref.labels) and
                          [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"]))
                           for d in res.defects_of(f)] ==
-                         [(d["position"], d["size"], d["confidence"]) for d in ref.defects])
+                         [(d["position"], d["size"], d["confidence"]) for d in ref.defects] and
+                         bool(res.rejected[f]) == ref.reject)
         return ok
 
+    # ---- parity gate, on EVERY rank: the timed configuration must agree with the oracle before any number counts ------
     res0 = det.detect_device(pool_dev[0].data_ptr(), nf, h, w, 1, params, d_mask[0].data_ptr(), d_labels[0].data_ptr())
-    if rank == 0 and not args.skip_parity:
+    parity = None
+    if not args.skip_parity:
         parity = check_against_oracle(res0, pool_host[0], d_mask[0], d_labels[0], (0, nf - 1))
         if not parity:
-            raise SystemExit("parity check against the oracle FAILED; refusing to report a number")
+            raise SystemExit(f"rank {rank}: parity check against the oracle FAILED; refusing to report a number")
 
     # ---- line statistics all-reduce (the only collective): 32 x u64, side stream, every --stats-every steps ----------------
     stats_view = torch.as_tensor(hv_dist.CudaArrayView(det.stats_device_ptr()), device=dev)
@@ -282,70 +303,169 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             stats_buf.copy_(stats_view)
             dist.all_reduce(stats_buf)
 
-    def step(i, collective=True):
-        det.enqueue_device(pool_dev[i % pool_n].data_ptr(), nf, h, w, 1, params, d_mask[i % n_out].data_ptr(),
-                           d_labels[i % n_out].data_ptr())
-        if collective and (i + 1) % args.stats_every == 0:
-            reduce_stats()
+    # Streaming loop: one step = enqueue one batch + collect the results of the batch depth-1 steps back, which the copy
+    # engine has meanwhile delivered to pinned host memory (hv_fetch_ticket).  EVERY batch's per-frame records and defect
+    # list reach the host inside the timed region; `host` accumulates what arrived so that it can be checked against the
+    # device-side line statistics afterwards.
+    class Stream_:
+        def __init__(self, prm):
+            self.prm = prm
+            self.tickets = [0] * depth
+            self.res = [np.zeros(nf, RESULT_DTYPE) for _ in range(depth)]
+            self.dfx = [np.zeros(nf * det.defect_cap, DEFECT_DTYPE) for _ in range(depth)]
+            self.i = 0
+            self.frames = self.rejected = self.defects = 0
+            self.last = None
+
+        def collect(self, slot):
+            r = det.fetch_into(self.tickets[slot], self.res[slot], self.dfx[slot])
+            self.frames += nf
+            self.rejected += int(r.frames["rejected"].sum())
+            self.defects += int(r.frames["n_defects"].sum())
+            self.tickets[slot] = 0
+            self.last = r
+
+        def step(self, collective=True):
+            i = self.i
+            slot = i % depth
+            self.tickets[slot] = det.enqueue_device(pool_dev[i % pool_n].data_ptr(), nf, h, w, 1, self.prm,
+                                                    d_mask[slot].data_ptr(), d_labels[slot].data_ptr())
+            nxt = (i + 1) % depth
+            if self.tickets[nxt]:
+                self.collect(nxt)
+            if collective and args.stats_every > 0 and (i + 1) % args.stats_every == 0:
+                reduce_stats()
+            self.i = i + 1
+
+        def drain(self):
+            for k in range(1, depth + 1):
+                slot = (self.i + k - 1) % depth
+                if self.tickets[slot]:
+                    self.collect(slot)
+
+    def timed_windows(S, repeats, collective=True):
+        """`repeats` windows of K steps back to back, a CUDA event on the launching stream at every window boundary.
+        Returns per-window milliseconds, launches and wall seconds."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
+        l0 = det.launch_count()
+        t0 = time.perf_counter()
+        evs[0].record(stream)
+        for r in range(repeats):
+            for _ in range(K):
+                S.step(collective)
+            evs[r + 1].record(stream)
+        S.drain()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return [evs[r].elapsed_time(evs[r + 1]) for r in range(repeats)], det.launch_count() - l0, wall
 
     # ---- settle clocks under load, then W warm-up steps ------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    S = Stream_(params)
     t_end = time.perf_counter() + args.settle_s
-    i = 0
     while time.perf_counter() < t_end:
         for _ in range(20):
-            step(i, collective=False)  # time-based loop: ranks do different numbers of iterations, so no collective here
-            i += 1
-        torch.cuda.synchronize()
-    for j in range(W):
-        step(j)
+            S.step(collective=False)  # time-based loop: ranks do different numbers of iterations, so no collective here
+    S.drain()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    for _ in range(W):
+        S.step()
+    S.drain()
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream ------------------------------------------------
-    # no per-kernel events inside the timed region: an event between two kernels would serialise them and hide the
-    # overlap of K1(step i+1) with the per-frame CCL of step i that production runs get
-    l0 = det.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for j in range(K):
-        step(j)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches = det.launch_count() - l0
-    ev_ms = e0.elapsed_time(e1)
-    last = det.fetch_results(nf)           # results of the final step: proves the pipeline ran to completion
-    clocks = sampler.stop()
+    # ---- timed region -----------------------------------------------------------------------------------------------------
+    stats_before = det.stats()
+    host_before = (S.frames, S.rejected, S.defects)
+    win_ms, launches, wall = timed_windows(S, R)
+    stats_after = det.stats()
+    host_delta = (S.frames - host_before[0], S.rejected - host_before[1], S.defects - host_before[2])
+    dev_delta = (stats_after["frames_inspected"] - stats_before["frames_inspected"],
+                 stats_after["frames_rejected"] - stats_before["frames_rejected"],
+                 stats_after["total_defects"] - stats_before["total_defects"])
+    if host_delta != dev_delta or host_delta[0] != R * K * nf:
+        raise SystemExit(f"rank {rank}: results delivered to the host {host_delta} != device line statistics {dev_delta} "
+                         f"(expected {R * K * nf} frames)")
     parity_after = None
-    if rank == 0 and not args.skip_parity:  # the overlapped steady state must still be bit-exact
-        j = K - 1
-        parity_after = check_against_oracle(last, pool_host[j % pool_n], d_mask[j % n_out], d_labels[j % n_out], (1, nf - 2))
+    if not args.skip_parity:  # the overlapped steady state must still be bit-exact (every rank checks its own last step)
+        j = S.i - 1
+        parity_after = check_against_oracle(S.last, pool_host[j % pool_n], d_mask[j % depth], d_labels[j % depth], (1, nf - 2))
         if not parity_after:
-            raise SystemExit("parity check of the last timed step FAILED; refusing to report a number")
+            raise SystemExit(f"rank {rank}: parity check of the last timed step FAILED; refusing to report a number")
+    clocks = sampler.stop()
 
-    t = torch.tensor([ev_ms], dtype=torch.float64, device=dev)
+    med, lo, hi = float(np.median(win_ms)), float(min(win_ms)), float(max(win_ms))
+    per_rank = [[med, lo, hi, wall / (R * K) * 1e3]]
+    if world > 1:
+        t = torch.tensor(per_rank[0], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [[float(x) for x in a.tolist()] for a in allr]
+    ms_window = max(p[0] for p in per_rank)          # max over ranks of the per-rank median window
+    value = world * nf * K / (ms_window * 1e-3)
+
+    # ---- the same without the collective (N > 1): is the all-reduce visible at all? ----------------------------------------
+    nocoll = None
+    if world > 1 and args.stats_every > 0:
+        w2, _, _ = timed_windows(S, max(5, R // 3), collective=False)
+        t = torch.tensor([float(np.median(w2))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nocoll = float(t.item()) / K
+
+    # ---- sustained: one event pair around R*K steps, no event in between (an event record between two batches makes the
+    #      next K1 wait for everything before it: one pipeline drain + fill per window) ----------------------------------------
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(R * K):
+        S.step()
+    e1.record(stream)
+    S.drain()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / (R * K)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * nf * K / (ms_total * 1e-3)
+    sustained_ms = float(t.item())
 
-    # ---- per-kernel durations: the same K steps again with a CUDA event pair around every kernel, on the launching
-    #      stream (the events serialise the kernels, so these are the isolated per-kernel times) ------------------------------
+    # ---- per-kernel durations: K steps with a CUDA event pair around every kernel, on the launching stream (the events
+    #      serialise the kernels, so these are the isolated per-kernel times) ------------------------------------------------
     det.profile_enable(None)
-    for j in range(K):
-        step(j)
+    for _ in range(K):
+        S.step(collective=False)
+    S.drain()
     torch.cuda.synchronize()
     prof = det.profile()
     shares = {k: (v["ms"] / v["launches"] if v["launches"] else 0.0) for k, v in prof.items()}
     det.profile_enable([])
+
+    # ---- the pipeline WITH morphology (blur -> threshold -> open 3x3 -> close 3x3 -> CCL): own parity gate, own timing ------
+    morph = None
+    if not args.no_morph:
+        resm = det.detect_device(pool_dev[1 % pool_n].data_ptr(), nf, h, w, 1, params_morph, d_mask[0].data_ptr(),
+                                 d_labels[0].data_ptr())
+        okm = True
+        if not args.skip_parity:
+            okm = check_against_oracle(resm, pool_host[1 % pool_n], d_mask[0], d_labels[0], (0, nf - 1),
+                                       morph_open_k=3, morph_close_k=3)
+            if not okm:
+                raise SystemExit(f"rank {rank}: morphology pipeline differs from the oracle; refusing to report a number")
+        SM = Stream_(params_morph)
+        for _ in range(max(W, 2 * depth)):
+            SM.step(collective=False)
+        SM.drain()
+        l0 = det.launch_count()
+        wm, lm, _ = timed_windows(SM, max(5, R // 3), collective=False)
+        t = torch.tensor([float(np.median(wm))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        morph = {"ms_per_step": float(t.item()) / K, "windows": len(wm), "launches_per_step": lm / (len(wm) * K),
+                 "parity_checked": bool(okm) and not args.skip_parity}
 
     # ---- end to end: pinned host frames -> H2D -> pipeline -> D2H of the results, through hv_submit / hv_wait -----------------
     n_pin = min(pool_n, max(args.slots, 3))
@@ -374,22 +494,29 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps(K)
+    e2e_steps(K * max(1, R // 3))
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = (time.perf_counter() - t0) / max(1, R // 3)
+    e2e_rank = [e2e_s]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * nf * K / float(t.item())
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        e2e_rank = [float(a.item()) for a in allr]
+    e2e_value = world * nf * K / max(e2e_rank)
     for ptr in pins:
         det.host_free(ptr)
-    d2h_bytes = nf * (24 + det.defect_cap * 48)
+    d2h_bytes = nf * (24 + 4 + det.defect_cap * 48)
 
+    torch.cuda.synchronize()
     if world > 1:
-        torch.cuda.synchronize()
         reduce_stats(final=True)
         torch.cuda.synchronize()
         total_stats = hv_dist.stats_dict(stats_buf.cpu().numpy())
+        fr = torch.tensor([det.stats()["frames_inspected"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(fr)
+        if total_stats["frames_inspected"] != int(fr.item()):
+            raise SystemExit("all-reduced line statistics do not add up to the ranks' own counters")
     else:
         total_stats = {k: v for k, v in det.stats().items() if k != "area_hist"}
 
@@ -403,16 +530,23 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     k1 = prof["preprocess_mask"]
     k1_ms = k1["ms"] / max(k1["launches"], 1)
     alg_bytes = ALG_BYTES_PER_PX * h * w * nf
-    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         pass
-    traffic = None
+    # DRAM bytes per launch from the ncu --set full capture of THIS code (profiles/traffic.json carries the fingerprint of
+    # the kernel sources it was taken from; a capture of other code is not quoted)
+    traffic, traffic_note = None, "no ncu capture of the current kernel sources under profiles/"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("csrc_sha16") == csrc_sha16():
+            traffic = tj["k1_dram_bytes_per_launch"]
+            traffic_note = (f"{tj['source']}: K1 {tj['k1_dram_bytes_per_launch'] / 1e6:.1f} MB + per-frame CCL kernel "
+                            f"{tj['ccl_dram_bytes_per_launch'] / 1e6:.1f} MB of DRAM traffic per step")
+        else:
+            traffic_note = f"profiles/traffic.json was captured from other kernel sources ({tj.get('csrc_sha16')}): not quoted"
     except Exception:
         pass
 
@@ -427,49 +561,69 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                          f"{fps_1t:.2f} frames/s over {n_1t} frames; CPU: {cpu_model()}",
                "single_thread_value": fps_1t}
 
+    step_ms = ms_window / K
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    cfg = workload_config(args, world)
+    cfg.update({
+        "l2_policy": f"inputs rotate over a pool of {pool_n} distinct batches ({pool_n * batch_bytes / 1e6:.0f} MB "
+                     f"> 126 MB L2); each step also writes {5 * batch_bytes / 1e6:.0f} MB of mask+labels",
+        "output_memory": out_mem,
+        "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B all-reduce of the running line statistics "
+                       f"every {args.stats_every} steps = {args.stats_every * nf} frames per GPU, on a side stream)",
+        "timed": f"{R} windows of K = {K} steps back to back, a CUDA event on the launching stream at every window boundary; "
+                 f"ms_per_step = median window / K (max over ranks of the per-rank medians).  One step = hv_enqueue_device "
+                 f"of one batch + hv_fetch_ticket of the batch {depth - 1} steps back: the per-frame records and defect "
+                 f"lists of EVERY batch reach pinned host memory inside the timed region (copy stream ordered by the "
+                 f"slot's device-side completion counter) and their sums are checked against the device's line statistics; "
+                 f"K1 of step i+1 overlaps the per-frame CCL kernels of the previous steps (programmatic dependent launch, "
+                 f"{depth} output sets in rotation)"})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"batch of {nf} synthetic {w}x{h} u8 bottle frames per GPU per step "
-                               f"(BASELINE configs[1]: one second of line at 90k BPH)",
-                   "frames_per_step_per_gpu": nf, "height": h, "width": w, "channels": 1,
-                   "params": "reference defaults min_size=10 max_size=3000 threshold=25",
-                   "l2_policy": f"inputs rotate over a pool of {pool_n} distinct batches ({pool_n * batch_bytes / 1e6:.0f} MB "
-                                f"> 126 MB L2); each step also writes {5 * batch_bytes / 1e6:.0f} MB of mask+labels",
-                   "output_memory": out_mem,
-                   "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B all-reduce of the running line statistics every {args.stats_every} steps = {args.stats_every * nf} frames per GPU, on a side stream)",
-                   "timed": "K x hv_enqueue_device on one stream, CUDA events on that stream; K1 of step i+1 overlaps the "
-                            "per-frame CCL kernels of the previous steps (programmatic dependent launch, device-side completion counters, "
-                            f"{n_out} output sets in rotation); "
-                            "results of every step stay on the device, the last step's are fetched and checked against "
-                            "the oracle"},
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": R,
+        "ms_per_step": step_ms, "ms_per_step_min": min(p[1] for p in per_rank) / K,
+        "ms_per_step_max": max(p[2] for p in per_rank) / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": cfg,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "how": f"hv_submit/hv_wait, {args.slots} batches in flight, pinned host frames, wall clock"},
-        "gpu_launches": int(launches),
-        # K1 is the dominant kernel and the critical path: its launches follow each other without a gap (each one starts as
-        # the CTAs of the previous one retire), the per-frame CCL kernels of the last few steps run next to them.  Its
-        # average time per launch over the timed region is therefore the step time; the isolated time (events around
-        # every launch, kernels serialised) is reported beside it.
-        "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms_total / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_bytes / (ms_total / K * 1e-3) / 1e9 / peak,
-                     "traffic": traffic, "kernel": "preprocess_mask (K1)", "kernel_ms": ms_total / K,
-                     "kernel_ms_how": "timed region / K launches, CUDA events on the launching stream: K1 launches are "
-                                      "back to back (programmatic dependent launch) and the other kernels run concurrently, "
-                                      "so this is K1's sustained time per launch; kernel_ms_isolated / isolated_frac: "
-                                      "mean over K launches with an event pair around every kernel in a separate pass of the "
-                                      "same K steps (that serialises the kernels and removes the overlap)",
-                     "kernel_ms_isolated": k1_ms, "isolated_achieved": achieved, "isolated_frac": achieved / peak,
+                "how": f"hv_submit/hv_wait, {args.slots} batches in flight, pinned host frames, wall clock, "
+                       f"{K * max(1, R // 3)} steps",
+                "h2d_gbs_per_rank": [batch_bytes * K / s / 1e9 for s in e2e_rank]},
+        "gpu_launches": int(round(launches / R)),
+        # The kernels of consecutive steps overlap (K1 launches follow each other without a gap, the per-frame CCL kernels
+        # of the last few steps run beside them), so no kernel's own duration appears in the step: `kernel_ms` is the STEP
+        # time, i.e. the throughput of the K1 -> CCL chain per batch, and `frac` is the pipeline's fraction of the HBM
+        # roofline.  K1's duration when run alone is kernel_ms_isolated.
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_note": traffic_note, "kernel": "preprocess_mask (K1) -> ccl_frame_fused chain",
+                     "kernel_ms": step_ms,
+                     "kernel_ms_how": "step time = chain throughput: median timed window / K launches (CUDA events on the "
+                                      "launching stream).  kernel_ms_isolated / isolated_frac: mean duration of K1 alone, "
+                                      "with an event pair around every kernel in a separate pass of K steps (that "
+                                      "serialises the kernels and removes the overlap)",
+                     "kernel_ms_isolated": k1_ms, "isolated_achieved": alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms else 0.0,
+                     "isolated_frac": alg_bytes / (k1_ms * 1e-3) / 1e9 / peak if k1_ms else 0.0,
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "pipeline_achieved": alg_bytes / (ms_total / K * 1e-3) / 1e9,
-                     "pipeline_frac": alg_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
+                     "sustained_ms_per_step": sustained_ms,
+                     "sustained_frac": alg_bytes / (sustained_ms * 1e-3) / 1e9 / peak,
+                     "sustained_how": f"one event pair around {R * K} steps, no event in between"},
         "kernel_ms_per_step": shares,
+        "per_rank_ms_per_step": [{"median": p[0] / K, "min": p[1] / K, "max": p[2] / K, "wall": p[3]} for p in per_rank],
         "clocks": clocks,
         "parity_checked": bool(parity) and bool(parity_after),
-        "wall_ms_per_step": wall / K * 1e3,
+        "parity_ranks": world,
+        "results_delivered": {"frames": host_delta[0], "rejected": host_delta[1], "defects": host_delta[2],
+                              "equal_to_device_line_stats": True},
+        "wall_ms_per_step": wall / (R * K) * 1e3,
         "line_stats": total_stats,
-        "last_step": {"rejected": int(last.rejected.sum()), "defects": int(last.frames["n_defects"].sum())},
+        "last_step": {"rejected": int(S.last.rejected.sum()), "defects": int(S.last.frames["n_defects"].sum())},
     }
+    if nocoll is not None:
+        line["ms_per_step_no_collective"] = nocoll
+    if morph is not None:
+        m_ach = alg_bytes / (morph["ms_per_step"] * 1e-3) / 1e9
+        line["roofline_morph"] = {"pipeline": "blur -> adaptive threshold -> open 3x3 -> close 3x3 -> CCL -> stats -> reject "
+                                              "(heimdall/detectors/contamination_detector.py:81-87)",
+                                  "bound": "hbm", "achieved": m_ach, "peak": peak, "unit": "GB/s", "frac": m_ach / peak,
+                                  "value": world * nf / (morph["ms_per_step"] * 1e-3), **morph}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     bad = [r for r in clocks.get("reasons", []) if r in ClockSampler.BAD]
@@ -489,8 +643,10 @@ def main() -> None:
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--repeats", type=int, default=15, help="timed windows of --steps steps, back to back; the median counts")
+    ap.add_argument("--no-morph", action="store_true", help="skip the roofline_morph sub-record")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=25)
     ap.add_argument("--height", type=int, default=1024)

@@ -20,17 +20,49 @@ using namespace hv;
 
 namespace {
 
-// scratch sets rotated by the synchronous / device-resident entry points = batches in flight on the device (see
-// enqueue_pipeline); HV_PIPELINE_DEPTH overrides the default for experiments
-int sync_slots() {
-    static const int v = [] {
-        const char *e = getenv("HV_PIPELINE_DEPTH");
-        const int d = e ? atoi(e) : 5;
-        return d < 2 ? 2 : (d > 8 ? 8 : d);
-    }();
-    return v;
+int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
 }
-#define kSyncSlots (sync_slots())
+bool env_flag(const char *name) { return getenv(name) != nullptr; }
+
+hv::Tunables read_tunables() {
+    hv::Tunables t;
+    t.pipeline_depth = env_int("HV_PIPELINE_DEPTH", t.pipeline_depth, 2, 8);
+    t.k1_ctas_per_sm = env_int("HV_K1_CTAS_PER_SM", t.k1_ctas_per_sm, 1, 5);
+    t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
+    t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
+    t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
+    t.k1_tail_rounds = env_int("HV_K1_TAIL_ROUNDS", t.k1_tail_rounds, 0, 1 << 20);
+    t.k1_prefetch = env_int("HV_K1_PREFETCH", t.k1_prefetch, 0, 1 << 20);
+    t.k1_claim_ahead = env_int("HV_K1_CLAIM_AHEAD", t.k1_claim_ahead, 0, 1);
+    t.k1_wait_hint_ns = env_int("HV_K1_WAIT_HINT_NS", t.k1_wait_hint_ns, 0, 2000000000);
+    t.morph_tiles_per_sm = env_int("HV_MORPH_TILES_PER_SM", t.morph_tiles_per_sm, 1, 8);
+    t.phase_frame = env_int("HV_PHASE_FRAME", 0, 0, 1 << 20);
+    t.k1_static = env_flag("HV_K1_STATIC");
+    t.k1_no_tma = env_flag("HV_K1_NO_TMA");
+    t.ccl_big = env_flag("HV_CCL_BIG");
+    t.no_k1_flag = env_flag("HV_NO_K1_FLAG");
+    t.no_early_k1 = env_flag("HV_NO_EARLY_K1");
+    t.no_pdl = env_flag("HV_NO_PDL");
+    t.no_pdl_tail = env_flag("HV_NO_PDL_TAIL");
+    t.no_compression = env_flag("HV_NO_COMPRESSION");
+    t.no_fused_gauss = env_flag("HV_NO_FUSED_GAUSS");
+    t.no_fused_morph = env_flag("HV_NO_FUSED_MORPH");
+    t.no_morph_chain = env_flag("HV_NO_MORPH_CHAIN");
+    t.no_k1_morph = env_flag("HV_NO_K1_MORPH");
+#ifdef HV_EXPERIMENTS
+    t.exp_k1_only = env_flag("HV_EXP_K1_ONLY");
+    t.exp_ccl_noop = env_flag("HV_EXP_CCL_NOOP");
+#endif
+    return t;
+}
+
+// scratch sets rotated by the synchronous / device-resident entry points = batches in flight on the device (see
+// enqueue_pipeline)
+#define kSyncSlots (hv::tunables().pipeline_depth)
 
 thread_local std::string g_create_error;
 
@@ -65,7 +97,7 @@ bool vmm_alloc_compressible(int device, size_t bytes, void **out, VmmRec *rec) {
     auto f_unmap = drv_fn<decltype(&cuMemUnmap)>("cuMemUnmap");
     int sup = 0;
     if (!(f_attr && f_gran && f_create && f_props && f_reserve && f_map && f_access && f_release && f_afree && f_unmap)) return false;
-    if (getenv("HV_NO_COMPRESSION")) return false;
+    if (tunables().no_compression) return false;
     if (f_attr(&sup, CU_DEVICE_ATTRIBUTE_GENERIC_COMPRESSION_SUPPORTED, device) != CUDA_SUCCESS || !sup) return false;
     CUmemAllocationProp prop = {};
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
@@ -172,11 +204,14 @@ struct Slot {
     DevBuf<uint8_t> in, gray, blur, mask, rowflags, rowflags_tmp, tile_occ;
     DevBuf<uint32_t> tile_list;
     DevBuf<uint16_t> gauss_tmp;
-    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, frame_flags, sched;
+    DevBuf<uint32_t> bits, bits_tmp, rootbits, rankbase, segbase, score_state, ncomp, fgcount, sched;
     uint32_t ccl_expected = 0;  // frames handed to the per-frame CCL kernel on this slot so far (sched[7] counts them done)
     uint32_t k1_expected = 0;   // K1 launches with a launch counter on this slot so far (sched[9] counts them done)
     uint32_t scan_expected = 0, tiles_expected = 0;  // likewise for the morphology kernels (sched[11], sched[12])
-    PinBuf<uint32_t> h_flags;
+    cudaEvent_t copied = nullptr;   // device-resident batches: results / flags / defects have arrived in the pinned buffers
+    bool pending = false;           // device-resident batch enqueued whose results have not been examined yet (retire_slot)
+    bool defects_on_host = false;   // the read-back included the defect table (else it is fetched on demand)
+    cudaStream_t batch_stream = nullptr;  // stream the batch's kernels were enqueued on
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
     bool used_small = false;  // ... its small build
@@ -185,8 +220,8 @@ struct Slot {
     DevBuf<int32_t> labels;
     DevBuf<hv_blob> blobs;
     DevBuf<hv_defect> defects;
-    DevBuf<hv_frame_result> results;
-    PinBuf<hv_frame_result> h_results;
+    DevBuf<hv_frame_result> results;    // n results followed by n u32 frame flags (one read-back for both)
+    PinBuf<hv_frame_result> h_results;  // same layout
     PinBuf<hv_defect> h_defects;
     // state of the batch currently held by the slot
     BatchView view{};
@@ -201,9 +236,11 @@ struct Slot {
         bits.release(), bits_tmp.release(), rootbits.release(), rankbase.release(), ncomp.release();
         segbase.release(), score_state.release();
         fgcount.release(), labels.release(), blobs.release(), defects.release(), results.release();
-        frame_flags.release(), h_flags.release(), sched.release();
+        sched.release();
         h_results.release(), h_defects.release(), h_stage.release();
         if (done) cudaEventDestroy(done);
+        if (copied) cudaEventDestroy(copied);
+        copied = nullptr;
         if (stream) cudaStreamDestroy(stream);
         done = nullptr;
         stream = nullptr;
@@ -211,6 +248,13 @@ struct Slot {
 };
 
 }  // namespace
+
+namespace hv {
+const Tunables &tunables() {
+    static const Tunables t = read_tunables();  // once per process (thread-safe static initialisation)
+    return t;
+}
+}  // namespace hv
 
 struct hv_ctx {
     int device = 0;
@@ -220,6 +264,10 @@ struct hv_ctx {
     std::vector<Slot> slots;
     cudaStream_t user_stream = nullptr;
     bool use_user_stream = false;
+    // results of device-resident batches travel on this stream: it waits (cuStreamWaitValue32) for the slot's completion
+    // counter, so nothing is ever inserted between two kernels of the launching stream
+    cudaStream_t copy_stream = nullptr;
+    CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     hv_line_stats *d_stats = nullptr;
     unsigned long long *d_phase_ns = nullptr;
     uint64_t launches = 0;
@@ -314,6 +362,10 @@ int blob_cap_for(const hv_ctx *ctx, int h, int w) {
     long long cap = ctx->cfg.max_blobs_per_frame > 0 ? ctx->cfg.max_blobs_per_frame : 131072;
     return (int)std::min(cap, max_possible);
 }
+
+// results buffer: n hv_frame_result entries followed by n u32 frame flags, in units of hv_frame_result
+size_t results_entries(int n) { return (size_t)n + ((size_t)n * sizeof(uint32_t) + sizeof(hv_frame_result) - 1) / sizeof(hv_frame_result); }
+uint32_t *flags_after(hv_frame_result *r, int n) { return reinterpret_cast<uint32_t *>(r + n); }
 
 int defect_cap_for(const hv_ctx *ctx) { return ctx->cfg.max_defects_per_frame > 0 ? ctx->cfg.max_defects_per_frame : 256; }
 
@@ -428,7 +480,6 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
     }
     HV_TRY_CUDA(ctx, s.ncomp.reserve(n));
     HV_TRY_CUDA(ctx, s.fgcount.reserve(n));
-    HV_TRY_CUDA(ctx, s.frame_flags.reserve(n));
     if (!s.sched.p) {  // K1's tile scheduler: {next tile, CTAs done}; the kernel rearms it itself
         // [0..1] K1's tile counter, [4..6] the fused morphology kernels, [7] frames the per-frame CCL kernel is through
         // with, [8] K1 CTAs done in the running launch, [9] K1 launches done, [10..12] morphology: scan CTAs done, scan
@@ -436,11 +487,10 @@ hv_status reserve_slot(hv_ctx *ctx, Slot &s, int n, int h, int w, bool need_in, 
         HV_TRY_CUDA(ctx, s.sched.reserve(16));
         HV_TRY_CUDA(ctx, cudaMemset(s.sched.p, 0, 16 * sizeof(uint32_t)));
     }
-    HV_TRY_CUDA(ctx, s.h_flags.reserve(n));
     HV_TRY_CUDA(ctx, s.blobs.reserve((size_t)n * blob_cap_for(ctx, h, w)));
     HV_TRY_CUDA(ctx, s.defects.reserve((size_t)n * defect_cap_for(ctx)));
-    HV_TRY_CUDA(ctx, s.results.reserve(n));
-    HV_TRY_CUDA(ctx, s.h_results.reserve(n));
+    HV_TRY_CUDA(ctx, s.results.reserve(results_entries(n)));
+    HV_TRY_CUDA(ctx, s.h_results.reserve(results_entries(n)));
     HV_TRY_CUDA(ctx, s.h_defects.reserve((size_t)n * defect_cap_for(ctx)));
     return HV_OK;
 }
@@ -475,6 +525,7 @@ hv_status enqueue_global_ccl(hv_ctx *ctx, const BatchView &b, const ScoreParams 
 hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_frames, int n, int h, int w, int c,
                            size_t row_stride, size_t frame_stride, const hv_params &pr, uint8_t *d_mask,
                            int32_t *d_labels, bool want_blur) {
+    const Tunables &tun = tunables();
     if (row_stride == 0) row_stride = (size_t)w * c;
     if (frame_stride == 0) frame_stride = row_stride * h;
     if (row_stride < (size_t)w * c || frame_stride < row_stride * (size_t)h)
@@ -532,9 +583,9 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p;
     b.stats = ctx->d_stats;
-    b.frame_flags = s.frame_flags.p;
+    b.frame_flags = flags_after(s.results.p, n);
     b.frame_select = nullptr;
-    b.ccl_done = (getenv("HV_NO_EARLY_K1") || getenv("HV_EXP_K1_ONLY")) ? nullptr : s.sched.p + 7;
+    b.ccl_done = (tun.no_early_k1 || tun.exp_k1_only) ? nullptr : s.sched.p + 7;
     b.ccl_wait_value = s.ccl_expected;
     // The caller's output planes are not tied to our slots: if this batch writes planes that one of the batches still in
     // flight wrote (a caller rotating fewer sets than we have slots), K1 also waits for that batch's per-frame kernel.
@@ -552,13 +603,12 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                 b.ccl_wait_n++;
             }
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
-    if (getenv("HV_EXP_CCL_NOOP")) b.phase_frame = -12345;
+    if (tun.exp_ccl_noop) b.phase_frame = -12345;
     if (b.phase_ns) {
         cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
         cudaMemsetAsync(ctx->d_phase_ns + 248, 0xff, sizeof(unsigned long long), st);
         cudaMemsetAsync(ctx->d_phase_ns + 252, 0xff, sizeof(unsigned long long), st);
-        const char *pf = getenv("HV_PHASE_FRAME");
-        b.phase_frame = pf ? atoi(pf) : 0;
+        b.phase_frame = tun.phase_frame;
     }
 
     // CCL path of this batch (decided before K1 runs: the fused kernel lets K1 skip the all-zero bit-mask words)
@@ -569,14 +619,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     }
     // Small build of the per-frame kernel (co-resident with K1 CTAs): box-blur path, with or without the fused morphology.  After a frame did
     // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
-    const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !getenv("HV_NO_FUSED_MORPH");
+    const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !tun.no_fused_morph;
     // counter chain through the morphology kernels too (K1 -> scan -> tiles -> CCL), HV_NO_MORPH_CHAIN: griddepcontrol.wait
     // (only for small batches: the chain needs the tiles kernel resident as a whole, two CTAs per SM, which pays when launch
     // gaps and serialisation dominate -- 8000 tiles: 78 -> 66 us -- and costs when the kernels are long -- 256 x 5 MP: 2.0 ->
     // 2.6 ms)
-    const bool morph_chain = morph_fused_plan && !getenv("HV_NO_MORPH_CHAIN") &&
+    const bool morph_chain = morph_fused_plan && !tun.no_morph_chain &&
                              (size_t)n * ((h + 31) / 32) * ((w + 127) / 128) <= 16384;
-    bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !getenv("HV_CCL_BIG");
+    bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !tun.ccl_big;
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
     PreprocessParams pp{};
     // resident K1 CTAs per SM (0 = the kernel's default, 5).  Next to the small CCL build: 3.  Four would fit beside one CTA
@@ -601,11 +651,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     pp.init_labels = (morph && !morph_fused_plan) ? 0 : 1;
     BatchView kb = b;  // view handed to K1 (its "gray" may be a separately blurred image)
     // K1 (TMA kernel) publishes a launch counter for the per-frame CCL kernel that follows it directly
-    unsigned int *k1_flag = (b.ccl_done && fused && (!morph || (morph_chain && ccl_small)) && !getenv("HV_NO_K1_FLAG")) ? s.sched.p + 9 : nullptr;
+    unsigned int *k1_flag = (b.ccl_done && fused && (!morph || (morph_chain && ccl_small)) && !tun.no_k1_flag) ? s.sched.p + 9 : nullptr;
     kb.k1_done = k1_flag;
     // Gaussian blur fused into the TMA kernel (k <= 15, 16-px aligned frames); otherwise two separable passes first
     bool gauss_fused = false, k1_tma = false;
-    if (gauss && pr.blur_ksize <= 15 && !(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) && !getenv("HV_NO_FUSED_GAUSS")) {
+    if (gauss && pr.blur_ksize <= 15 && !(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) && !tun.no_fused_gauss) {
         PreprocessParams gp = pp;
         gp.gauss_ksize = pr.blur_ksize;
         for (int t = 0; t < 16; t++) gp.gk[t] = t < pr.blur_ksize ? gk[t] : 0;
@@ -614,8 +664,8 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ProfScope ps(ctx, HV_K_PREPROCESS, st);
         const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 && !conflict_overflow &&
                          ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
-                         !getenv("HV_NO_PDL");
-        gp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
+                         !tun.no_pdl;
+        gp.static_sched = tun.k1_static ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
         HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, gp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &gauss_fused));
         if (gauss_fused) ctx->launches++;
         k1_tma = gauss_fused;
@@ -656,8 +706,8 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         // still running.  Anything else in between (copies, events, other kernels) means plain stream order.
         const bool pdl = ctx->last_valid && ctx->last_fused_tail && ctx->last_stream == st && ctx->prof_mask == 0 && c == 1 && !conflict_overflow &&
                          !separate_blur && ctx->last_mask != (const void *)b.mask && ctx->last_labels != (const void *)b.labels &&
-                         !getenv("HV_NO_PDL");
-        pp.static_sched = getenv("HV_K1_STATIC") ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
+                         !tun.no_pdl;
+        pp.static_sched = tun.k1_static ? 1 : 0;  // tiles handed out by an atomic counter (see k_preprocess.cu)
         if (!(ctx->cfg.flags & HV_FLAG_FORCE_GENERIC))
             HV_TRY_CUDA(ctx, launch_preprocess_tma(kb, pp, b.bits, s.sched.p, ctx->num_sms, pdl, st, &used_tma));
         if (!used_tma) HV_TRY_CUDA(ctx, launch_preprocess(kb, pp, b.bits, st));
@@ -675,7 +725,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         if (morph_fused_plan) {
             // open + close + expansion in one kernel, launched ahead of K1's completion; its result goes to the other
             // bit plane, which is the one the CCL reads from here on
-            const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !getenv("HV_NO_PDL");
+            const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !tun.no_pdl;
             // counter chain: the scan waits for K1's launch counter (b.k1_done), the tiles kernel for the scan's, and the
             // per-frame CCL kernel for the tiles kernel's (handed to it in the k1_done fields)
             unsigned int *chain = (b.k1_done && morph_chain) ? s.sched.p + 10 : nullptr;
@@ -701,14 +751,14 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         }
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
-    if (fused && getenv("HV_EXP_K1_ONLY")) {
+    if (fused && tun.exp_k1_only) {
         // experiment: K1 chain alone (results are NOT computed)
     } else if (fused) {
         ProfScope ps(ctx, HV_K_CCL_FRAME, st);
         // launched ahead of K1's completion when K1 (TMA kernel, which releases its dependents at once) is the kernel
         // right before it on the stream; the kernel waits for K1 itself (griddepcontrol.wait)
-        const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !getenv("HV_NO_PDL") &&
-                              !getenv("HV_NO_PDL_TAIL");
+        const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !tun.no_pdl &&
+                              !tun.no_pdl_tail;
         HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, ccl_small, st));
         s.ccl_expected += (uint32_t)n;
         s.used_small = ccl_small;
@@ -744,13 +794,41 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     return HV_OK;
 }
 
-hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
+// defect tables up to this size travel with every batch's results; larger ones (huge max_defects_per_frame x batch) are
+// fetched on demand, only the rows in use
+constexpr size_t kEagerDefectBytes = 2u << 20;
+
+// Read-back of results + frame flags (one copy: they share a buffer) and, when `with_defects`, the defect table.
+hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st, bool with_defects = true) {
     const BatchView &b = s.view;
-    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_results.p, b.results, sizeof(hv_frame_result) * b.n, cudaMemcpyDeviceToHost, st));
-    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_defects.p, b.defects, sizeof(hv_defect) * (size_t)b.n * b.defect_cap,
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_results.p, b.results, sizeof(hv_frame_result) * b.n + sizeof(uint32_t) * b.n,
                                      cudaMemcpyDeviceToHost, st));
-    if (s.used_fused)
-        HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_flags.p, b.frame_flags, sizeof(uint32_t) * b.n, cudaMemcpyDeviceToHost, st));
+    if (with_defects)
+        HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_defects.p, b.defects, sizeof(hv_defect) * (size_t)b.n * b.defect_cap,
+                                         cudaMemcpyDeviceToHost, st));
+    s.defects_on_host = with_defects;
+    return HV_OK;
+}
+
+// Device-resident batches: their results travel on the context's copy stream, which waits for the slot's completion
+// counter (the per-frame CCL kernel bumps it once per frame) with a stream memory operation -- nothing is inserted
+// between two kernels of the launching stream, so the kernels of consecutive batches keep overlapping.  Batches that
+// did not go through the per-frame kernel (global-memory CCL path) are ordered by an event instead.
+hv_status enqueue_async_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
+    const BatchView &b = s.view;
+    bool ordered = false;
+    if (s.used_fused && b.ccl_done && ctx->wait32)
+        ordered = ctx->wait32(reinterpret_cast<CUstream>(ctx->copy_stream), reinterpret_cast<CUdeviceptr>(b.ccl_done),
+                              s.ccl_expected, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+    if (!ordered) {
+        HV_TRY_CUDA(ctx, cudaEventRecord(s.done, st));
+        HV_TRY_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, s.done, 0));
+        ctx->last_valid = false;  // the event sits between this batch and the next: plain stream order across it
+    }
+    const bool eager = sizeof(hv_defect) * (size_t)b.n * b.defect_cap <= kEagerDefectBytes;
+    hv_status rs = enqueue_readback(ctx, s, ctx->copy_stream, eager);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, cudaEventRecord(s.copied, ctx->copy_stream));
     return HV_OK;
 }
 
@@ -758,11 +836,12 @@ hv_status enqueue_readback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
 // global-memory path on exactly those frames (same stream), read back again and wait.
 hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     if (!s.used_fused) return HV_OK;
+    const uint32_t *h_flags = flags_after(s.h_results.p, s.view.n);
     bool any = false;
     bool all_fit_small = true;
     for (int f = 0; f < s.view.n; f++) {
-        any |= (s.h_flags.p[f] & 1u) != 0;
-        all_fit_small &= s.h_flags.p[f] == 0;
+        any |= (h_flags[f] & 1u) != 0;
+        all_fit_small &= h_flags[f] == 0;
     }
     if (!any) {
         ctx->dense_hint = false;
@@ -773,6 +852,7 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
         ctx->ccl_small_ok = false;  // finishes the flagged frames of this batch)
         ctx->ccl_small_retry = 0;
     }
+    ctx->last_valid = false;  // kernels that are not part of the K1 / per-frame chain go onto the stream
     BatchView b = s.view;
     b.frame_select = b.frame_flags;
     if (s.sparse_bits) {
@@ -791,6 +871,25 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
         ctx->dense_batches = 0;
     }
     s.used_small = false;
+    return HV_OK;
+}
+
+// A device-resident batch whose results nobody has looked at yet: wait for its read-back, finish the frames the
+// per-frame kernel flagged (global path), update the CCL path selection.  Runs before the slot is reused, before a
+// batch that writes the same caller-owned output planes is enqueued, and when the batch is fetched.
+hv_status retire_slot(hv_ctx *ctx, Slot &s) {
+    if (!s.pending) return HV_OK;
+    HV_TRY_CUDA(ctx, cudaEventSynchronize(s.copied));
+    s.pending = false;
+    return resolve_fallback(ctx, s, s.batch_stream);
+}
+
+// next scratch set of the synchronous / device-resident entry points (its previous batch is retired first)
+hv_status advance_sync_slot(hv_ctx *ctx) {
+    const int next = (ctx->sync_cur + 1) % kSyncSlots;
+    hv_status rs = retire_slot(ctx, ctx->slots[next]);
+    if (rs != HV_OK) return rs;
+    ctx->sync_cur = next;
     return HV_OK;
 }
 
@@ -950,6 +1049,7 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
         g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return HV_ERR_CUDA;
     }
+    (void)tunables();  // the environment is read here, once per process
     hv_ctx *ctx = new (std::nothrow) hv_ctx();
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
     ctx->device = device;
@@ -964,12 +1064,19 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
         s.mask.want_compressible = s.labels.want_compressible = true;
         s.mask.device = s.labels.device = device;
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming) != cudaSuccess) {
             g_create_error = "stream/event creation failed";
             hv_destroy(ctx);
             return HV_ERR_CUDA;
         }
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "stream creation failed";
+        hv_destroy(ctx);
+        return HV_ERR_CUDA;
+    }
+    ctx->wait32 = drv_fn<decltype(&cuStreamWaitValue32)>("cuStreamWaitValue32");
     if (ctx->cfg.flags & HV_FLAG_PROFILE) ctx->prof_mask = 0xffffffffu;
     if (configure_ccl_frame() != cudaSuccess || configure_preprocess_tma() != cudaSuccess) {
         g_create_error = "cannot configure shared memory for the per-frame CCL kernel";
@@ -997,6 +1104,7 @@ void hv_destroy(hv_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots) s.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto &r : ctx->prof_recs) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -1092,19 +1200,77 @@ hv_status hv_device_write(hv_ctx *ctx, void *d_dst, const void *host_src, size_t
 
 hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
                             size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
-                            int32_t *d_labels) {
+                            int32_t *d_labels, int64_t *ticket) {
     if (!ctx || !d_frames) return HV_ERR_INVALID_ARGUMENT;
+    if (ticket) *ticket = 0;
     hv_status rs = validate_shape(ctx, n, h, w, c);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = sync_stream(ctx);
+    // The kernels of consecutive batches are ordered by device-side counters whose expected values are kernel
+    // arguments: a captured graph would replay stale values and every wait would pass at once.  Refuse.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone)
+        return fail(ctx, HV_ERR_UNSUPPORTED, "hv_enqueue_device cannot be captured into a CUDA graph (device-side batch counters)");
     hv_params pr;
     if (params)
         pr = *params;
     else
         hv_params_default(&pr);
-    ctx->sync_cur = (ctx->sync_cur + 1) % kSyncSlots;
-    return enqueue_pipeline(ctx, cur_sync_slot(ctx), sync_stream(ctx), d_frames, n, h, w, c, row_stride, frame_stride, pr,
-                            d_mask, d_labels, (ctx->cfg.flags & 4u) != 0);
+    rs = advance_sync_slot(ctx);
+    if (rs != HV_OK) return rs;
+    // A batch still pending on another slot that wrote the same caller-owned planes must be finished first: if the
+    // per-frame kernel flagged one of its frames, the global path completes it in those planes.
+    if (d_mask || d_labels)
+        for (int k = 0; k < kSyncSlots; k++) {
+            Slot &q = ctx->slots[k];
+            if (k != ctx->sync_cur && q.pending && q.has_batch &&
+                ((d_mask && q.view.mask == d_mask) || (d_labels && q.view.labels == d_labels))) {
+                rs = retire_slot(ctx, q);
+                if (rs != HV_OK) return rs;
+            }
+        }
+    Slot &s = cur_sync_slot(ctx);
+    s.has_batch = false;
+    rs = enqueue_pipeline(ctx, s, st, d_frames, n, h, w, c, row_stride, frame_stride, pr, d_mask, d_labels,
+                          (ctx->cfg.flags & 4u) != 0);
+    if (rs != HV_OK) return rs;
+    s.batch_stream = st;
+    s.ticket = ctx->next_ticket++;
+    if (ticket) *ticket = s.ticket;
+    if (tunables().exp_k1_only) return HV_OK;  // (experiment builds: nothing computes results)
+    rs = enqueue_async_readback(ctx, s, st);
+    if (rs != HV_OK) return rs;
+    s.pending = true;
+    return HV_OK;
+}
+
+hv_status hv_fetch_ticket(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
+                          size_t *n_defects_total) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    Slot *sp = nullptr;
+    for (int k = 0; k < kSyncSlots; k++)
+        if (ctx->slots[k].has_batch && ctx->slots[k].ticket == ticket && ticket > 0) sp = &ctx->slots[k];
+    if (!sp)
+        return fail(ctx, HV_ERR_BAD_TICKET, "unknown ticket, or the batch's scratch set has been reused (only the last "
+                                            "hv_pipeline_depth() batches can be fetched)");
+    Slot &s = *sp;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    hv_status rs = retire_slot(ctx, s);
+    if (rs != HV_OK) return rs;
+    if (!s.defects_on_host) {  // large defect tables: only the rows in use, now
+        const BatchView &b = s.view;
+        for (int f = 0; f < b.n; f++) {
+            const uint32_t nd = std::min<uint32_t>(s.h_results.p[f].n_defects, (uint32_t)b.defect_cap);
+            if (nd)
+                HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.h_defects.p + (size_t)f * b.defect_cap, b.defects + (size_t)f * b.defect_cap,
+                                                 sizeof(hv_defect) * nd, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        HV_TRY_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        s.defects_on_host = true;
+    }
+    return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
 }
 
 hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
@@ -1112,15 +1278,7 @@ hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *def
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
     Slot &s = cur_sync_slot(ctx);
     if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
-    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = sync_stream(ctx);
-    ctx->last_valid = false;  // the read-back sits between this batch and the next: no overlap across it
-    hv_status rs = enqueue_readback(ctx, s, st);
-    if (rs != HV_OK) return rs;
-    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-    rs = resolve_fallback(ctx, s, st);
-    if (rs != HV_OK) return rs;
-    return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
+    return hv_fetch_ticket(ctx, s.ticket, results, defects, defects_cap, n_defects_total);
 }
 
 hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug) {
@@ -1128,25 +1286,21 @@ hv_status hv_fetch_debug(hv_ctx *ctx, const hv_debug_outputs *debug) {
     Slot &s = cur_sync_slot(ctx);
     if (!s.has_batch) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "no batch has been enqueued");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->last_valid = false;
-    if (s.used_fused) {  // make sure flagged frames have been completed by the global path before copying
-        cudaStream_t st = sync_stream(ctx);
-        hv_status rs = enqueue_readback(ctx, s, st);
-        if (rs != HV_OK) return rs;
-        HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-        rs = resolve_fallback(ctx, s, st);
-        if (rs != HV_OK) return rs;
-    }
-    return copy_debug(ctx, s, sync_stream(ctx), debug);
+    ctx->last_valid = false;  // the copies below go onto the launching stream
+    // flagged frames must have been completed by the global path before anything is copied
+    hv_status rs = retire_slot(ctx, s);
+    if (rs != HV_OK) return rs;
+    return copy_debug(ctx, s, s.batch_stream ? s.batch_stream : sync_stream(ctx), debug);
 }
 
 hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
                                  size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
                                  int32_t *d_labels, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
                                  size_t *n_defects_total) {
-    hv_status rs = hv_enqueue_device(ctx, d_frames, n, h, w, c, row_stride, frame_stride, params, d_mask, d_labels);
+    int64_t ticket = 0;
+    hv_status rs = hv_enqueue_device(ctx, d_frames, n, h, w, c, row_stride, frame_stride, params, d_mask, d_labels, &ticket);
     if (rs != HV_OK) return rs;
-    return hv_fetch_results(ctx, results, defects, defects_cap, n_defects_total);
+    return hv_fetch_ticket(ctx, ticket, results, defects, defects_cap, n_defects_total);
 }
 
 hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t h, int32_t w, int32_t c,
@@ -1162,10 +1316,14 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
         pr = *params;
     else
         hv_params_default(&pr);
-    ctx->sync_cur = (ctx->sync_cur + 1) % kSyncSlots;
+    rs = advance_sync_slot(ctx);
+    if (rs != HV_OK) return rs;
     ctx->last_valid = false;
     Slot &s = cur_sync_slot(ctx);
+    s.has_batch = false;
     cudaStream_t st = sync_stream(ctx);
+    s.batch_stream = st;
+    s.ticket = ctx->next_ticket++;
     rs = upload_frames(ctx, s, st, frames, n, h, w, c, row_stride, frame_stride);
     if (rs != HV_OK) return rs;
     const bool want_blur = (debug && debug->blur) || (ctx->cfg.flags & 4u);
@@ -1435,6 +1593,7 @@ hv_status hv_apply_threshold(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t
     if (c != 1) return fail(ctx, HV_ERR_CHANNELS, "Image processing error: Thresholding requires a grayscale image");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
+    if (retire_slot(ctx, s) != HV_OK) return HV_ERR_CUDA;  // the scratch set may hold a device-resident batch
     cudaStream_t st = s.stream;
     const size_t px = (size_t)h * w;
     hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px, false, false, false, true, true);
@@ -1462,6 +1621,37 @@ hv_status hv_apply_threshold(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t
     return HV_OK;
 }
 
+// cv2.morphologyEx(MORPH_OPEN, rect k_open) then (MORPH_CLOSE, rect k_close) on a binary mask
+// (heimdall/detectors/contamination_detector.py:81-87; heimdall/core/pipeline.py:290-332 MorphologyStage).
+hv_status hv_morphology(hv_ctx *ctx, const uint8_t *mask, int32_t h, int32_t w, int32_t open_k, int32_t close_k,
+                        uint8_t *out) {
+    if (!ctx || !mask || !out || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (open_k < 0 || open_k > 31 || close_k < 0 || close_k > 31)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "morphology kernel size must be in [0, 31]");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    if (retire_slot(ctx, s) != HV_OK) return HV_ERR_CUDA;  // the scratch set may hold a device-resident batch
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px, false, false, false, true, true);
+    if (rs != HV_OK) return rs;
+    BatchView b{};
+    b.n = 1, b.h = h, b.w = w, b.ww = (w + 31) / 32;
+    b.mask = s.mask.p, b.bits = s.bits.p, b.bits_tmp = s.bits_tmp.p, b.labels = s.labels.p;
+    b.rowflags = s.rowflags.p, b.tiles_x = (w + 127) / 128, b.rf_stride = (size_t)((h + 31) / 32) * b.tiles_x * 32;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, mask, px, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, launch_bits_from_gt127(s.in.p, 1, h, w, b.ww, b.bits, st));
+    int nl = 0;
+    HV_TRY_CUDA(ctx, launch_morph(b, open_k, close_k, &nl, st));
+    HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
+    ctx->launches += 2 + nl;
+    s.has_batch = false;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(out, b.mask, px, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
+}
+
 static hv_status run_ccl_only(hv_ctx *ctx, Slot &s, cudaStream_t st, BatchView &b) {
     HV_TRY_CUDA(ctx, launch_ccl_merge(b, st));
     HV_TRY_CUDA(ctx, launch_ccl_flatten(b, st));
@@ -1481,7 +1671,7 @@ static void fill_view(hv_ctx *ctx, Slot &s, BatchView &b, int h, int w) {
     b.score_state = s.score_state.p, b.score_chunks = (b.blob_cap + 255) / 256;
     b.defects = s.defects.p, b.defect_cap = defect_cap_for(ctx);
     b.results = s.results.p, b.stats = ctx->d_stats;
-    b.frame_flags = s.frame_flags.p, b.frame_select = nullptr;
+    b.frame_flags = flags_after(s.results.p, 1), b.frame_select = nullptr;
 }
 
 hv_status hv_find_contours(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, double min_area,
@@ -1492,6 +1682,7 @@ hv_status hv_find_contours(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w
     if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
+    if (retire_slot(ctx, s) != HV_OK) return HV_ERR_CUDA;  // the scratch set may hold a device-resident batch
     cudaStream_t st = s.stream;
     const size_t px = (size_t)h * w;
     hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px, false, false, false, true, true);
@@ -1535,6 +1726,7 @@ hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w
     if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[0];
+    if (retire_slot(ctx, s) != HV_OK) return HV_ERR_CUDA;  // the scratch set may hold a device-resident batch
     cudaStream_t st = s.stream;
     const size_t px = (size_t)h * w;
     hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px * c, true, true, false, true, true);

@@ -112,6 +112,38 @@ __device__ __forceinline__ uint8_t gray_f64(uint32_t c0, uint32_t c1, uint32_t c
 
 #endif
 
+// Tuning knobs.  Read from the environment ONCE per process, when the first context is created (hv_create); nothing on
+// the enqueue path calls getenv.  Defaults are the measured optimum ("Experiment switches").  The HV_EXP_*
+// switches, which make the library skip work, exist only in builds with -DHV_EXPERIMENTS (make EXPERIMENTS=1).
+struct Tunables {
+    int pipeline_depth = 5;       // HV_PIPELINE_DEPTH: scratch sets in rotation = batches in flight on the device (2..8)
+    int k1_ctas_per_sm = 5;       // HV_K1_CTAS_PER_SM (1..5)
+    int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4)
+    int k1_lookahead = 2;         // HV_K1_LOOKAHEAD: tiles the TMA producer runs ahead
+    int k1_tail_lookahead = 1;    // HV_K1_TAIL_LOOKAHEAD
+    int k1_tail_rounds = 0;       // HV_K1_TAIL_ROUNDS
+    int k1_prefetch = 0;          // HV_K1_PREFETCH: L2 tensor prefetch distance in tiles (0 = off)
+    int k1_claim_ahead = 0;       // HV_K1_CLAIM_AHEAD
+    int k1_wait_hint_ns = 10000000;  // HV_K1_WAIT_HINT_NS
+    int morph_tiles_per_sm = 2;   // HV_MORPH_TILES_PER_SM
+    int phase_frame = 0;          // HV_PHASE_FRAME (with HV_FLAG_PHASE_TIMING)
+    bool k1_static = false;       // HV_K1_STATIC
+    bool k1_no_tma = false;       // HV_K1_NO_TMA
+    bool ccl_big = false;         // HV_CCL_BIG
+    bool no_k1_flag = false;      // HV_NO_K1_FLAG
+    bool no_early_k1 = false;     // HV_NO_EARLY_K1
+    bool no_pdl = false;          // HV_NO_PDL
+    bool no_pdl_tail = false;     // HV_NO_PDL_TAIL
+    bool no_compression = false;  // HV_NO_COMPRESSION
+    bool no_fused_gauss = false;  // HV_NO_FUSED_GAUSS
+    bool no_fused_morph = false;  // HV_NO_FUSED_MORPH
+    bool no_morph_chain = false;  // HV_NO_MORPH_CHAIN
+    bool no_k1_morph = false;     // HV_NO_K1_MORPH: never fold 3x3 / 5x5 open+close into K1 (use the tiles kernel)
+    bool exp_k1_only = false;     // HV_EXP_K1_ONLY  (-DHV_EXPERIMENTS only): K1 chain alone, NO results
+    bool exp_ccl_noop = false;    // HV_EXP_CCL_NOOP (-DHV_EXPERIMENTS only): per-frame kernels launched but idle, NO results
+};
+const Tunables &tunables();
+
 #define HV_CUDA_TRY(expr)                         \
     do {                                          \
         cudaError_t _e = (expr);                  \

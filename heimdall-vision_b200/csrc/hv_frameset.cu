@@ -86,6 +86,52 @@ hv_status fs_fail(hv_frameset *fs, hv_status s, const char *msg) {
     return s;
 }
 
+// Cut one batch off the complete sets (ascending id order) and hand it to the detector.  The sets leave `ready` only
+// once hv_submit_frames has accepted them: when every slot of the context is still in flight (HV_ERR_CAPACITY) the
+// batch stays queued, the status is returned to the caller -- who collects an earlier ticket with hv_frameset_wait and
+// calls hv_frameset_flush, or simply pushes on: the next completed set retries -- and nothing is lost silently.  The
+// queue of complete sets is bounded (max_pending_sets beyond a full batch): past that the oldest complete set is
+// dropped and accounted like an incomplete one.
+hv_status submit_ready(hv_frameset *fs, const hv_params *params, int64_t *ticket) {
+    const int spb = fs->cfg.sets_per_batch;
+    if ((int)fs->ready.size() < spb) return HV_OK;
+    std::vector<hv_camera_frame> batch;
+    for (int k = 0; k < spb; k++)
+        for (auto &m : fs->ready[k].meta) batch.push_back(m);
+    int64_t t = -(int64_t)(fs->st.batches_submitted + 1);
+    hv_status rs = fs->ctx ? hv_submit_frames(fs->ctx, batch.data(), (int32_t)batch.size(), params, &t) : HV_OK;
+    if (rs != HV_OK) {
+        fs->err = hv_last_error(fs->ctx);
+        while ((int)fs->ready.size() > spb + fs->cfg.max_pending_sets) {  // back-pressure has a bound
+            fs->st.sets_dropped++;
+            fs->st.frames_dropped += (uint64_t)fs->cfg.n_cameras;
+            fs->dropped_below = std::max(fs->dropped_below, fs->ready.front().id + 1);
+            fs->free_slabs.push_back(fs->ready.front().slab);
+            fs->ready.pop_front();
+        }
+        return rs;
+    }
+    hv_frameset::InFlight fl;
+    for (int k = 0; k < spb; k++) {
+        fl.sets.push_back(std::move(fs->ready.front()));
+        fs->ready.pop_front();
+    }
+    fs->dropped_below = std::max(fs->dropped_below, fl.sets.back().id + 1);
+    // sets older than the batch that are still incomplete can never be delivered in order any more
+    while (!fs->open.empty() && fs->open.begin()->first < fs->dropped_below) {
+        auto old = fs->open.begin();
+        fs->st.sets_dropped++;
+        fs->st.frames_dropped += (uint64_t)old->second.count;
+        fs->free_slabs.push_back(old->second.slab);
+        fs->open.erase(old);
+    }
+    fl.ticket = t;
+    fs->inflight.push_back(std::move(fl));
+    fs->st.batches_submitted++;
+    *ticket = t;
+    return HV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -187,35 +233,13 @@ hv_status hv_frameset_push(hv_frameset *fs, const hv_camera_frame *fr, const hv_
     auto pos = std::lower_bound(fs->ready.begin(), fs->ready.end(), done.id,
                                 [](const hv_frameset::Set &a, uint64_t v) { return a.id < v; });
     fs->ready.insert(pos, std::move(done));
-    if ((int)fs->ready.size() < fs->cfg.sets_per_batch) return HV_OK;
-    std::vector<hv_camera_frame> batch;
-    hv_frameset::InFlight fl;
-    for (int k = 0; k < fs->cfg.sets_per_batch; k++) {
-        for (auto &m : fs->ready.front().meta) batch.push_back(m);
-        fl.sets.push_back(std::move(fs->ready.front()));
-        fs->ready.pop_front();
-    }
-    fs->dropped_below = std::max(fs->dropped_below, fl.sets.back().id + 1);
-    // sets older than the batch that are still incomplete can never be delivered in order any more
-    while (!fs->open.empty() && fs->open.begin()->first < fs->dropped_below) {
-        auto old = fs->open.begin();
-        fs->st.sets_dropped++;
-        fs->st.frames_dropped += (uint64_t)old->second.count;
-        fs->free_slabs.push_back(old->second.slab);
-        fs->open.erase(old);
-    }
-    int64_t t = -(int64_t)(fs->st.batches_submitted + 1);
-    hv_status rs = fs->ctx ? hv_submit_frames(fs->ctx, batch.data(), (int32_t)batch.size(), params, &t) : HV_OK;
-    if (rs != HV_OK) {
-        for (auto &q : fl.sets) fs->free_slabs.push_back(q.slab);
-        fs->err = hv_last_error(fs->ctx);
-        return rs;
-    }
-    fl.ticket = t;
-    fs->inflight.push_back(std::move(fl));
-    fs->st.batches_submitted++;
-    *ticket = t;
-    return HV_OK;
+    return submit_ready(fs, params, ticket);
+}
+
+hv_status hv_frameset_flush(hv_frameset *fs, const hv_params *params, int64_t *ticket) {
+    if (!fs || !ticket) return HV_ERR_INVALID_ARGUMENT;
+    *ticket = 0;
+    return submit_ready(fs, params, ticket);
 }
 
 hv_status hv_frameset_batch_ids(hv_frameset *fs, int64_t ticket, uint64_t *set_ids, int32_t cap, int32_t *n_sets) {
@@ -237,7 +261,10 @@ hv_status hv_frameset_wait(hv_frameset *fs, int64_t ticket, hv_frame_result *res
         if (fs->inflight[i].ticket == ticket) {
             hv_status rs = fs->ctx ? hv_wait(fs->ctx, ticket, results, defects, defects_cap, n_defects_total)
                                    : HV_ERR_NO_DEVICE;
-            for (auto &q : fs->inflight[i].sets) fs->free_slabs.push_back(q.slab);  // the copy is done either way
+            // a failed wait says nothing about the H2D copy out of the slabs: make sure the device is through with
+            // them before they are handed out again
+            if (fs->ctx && rs != HV_OK && rs != HV_ERR_CAPACITY && cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();
+            for (auto &q : fs->inflight[i].sets) fs->free_slabs.push_back(q.slab);
             fs->inflight.erase(fs->inflight.begin() + i);
             if (rs != HV_OK) fs->err = fs->ctx ? hv_last_error(fs->ctx) : "dry mode: nothing was submitted";
             return rs;

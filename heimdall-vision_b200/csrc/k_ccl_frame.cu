@@ -185,10 +185,12 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
+#ifdef HV_EXPERIMENTS
     if (b.phase_frame == -12345) {  // experiment (HV_EXP_CCL_NOOP): the pipeline's structure without this kernel's work
         if (threadIdx.x == 0 && b.ccl_done) atomicAdd(b.ccl_done, 1u);
         return;
     }
+#endif
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     if (too_big) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
+            __threadfence();  // the flag is read (copy engine, host) by whoever sees the counter below
             if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
         }
         return;
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     if (nn > (uint32_t)kCapN) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
+            __threadfence();  // the flag is read (copy engine, host) by whoever sees the counter below
             if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
         }
         return;
@@ -400,6 +404,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     if (ne > (uint32_t)kCapE) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
+            __threadfence();  // the flag is read (copy engine, host) by whoever sees the counter below
             if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
         }
         return;
@@ -433,6 +438,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
     if (ncomp > (uint32_t)kCapB || ncomp > (uint32_t)b.blob_cap) {  // block-uniform
         if (tid == 0) {
             b.frame_flags[f] = 1u;
+            __threadfence();  // the flag is read (copy engine, host) by whoever sees the counter below
             if (b.ccl_done) atomicAdd(b.ccl_done, 1u);  // nothing of this frame's slot is touched from here on
         }
         return;

@@ -977,15 +977,7 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     return fn;
 }
 
-int k1_ctas_per_sm() {
-    static int v = 0;
-    if (!v) {
-        const char *e = getenv("HV_K1_CTAS_PER_SM");
-        v = e ? atoi(e) : 5;
-        if (v < 1 || v > 5) v = 5;
-    }
-    return v;
-}
+int k1_ctas_per_sm() { return tunables().k1_ctas_per_sm; }
 
 }  // namespace
 
@@ -1019,7 +1011,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     const bool gauss = p.gauss_ksize > 0;
     const uintptr_t base = reinterpret_cast<uintptr_t>(b.gray);
     if ((!gauss && p.blur_radius != 2) || !sched || (base & 15) || (b.gray_row_stride & 15) || (b.gray_frame_stride & 15) ||
-        (b.w & 15) || getenv("HV_K1_NO_TMA"))
+        (b.w & 15) || tunables().k1_no_tma)
         return cudaSuccess;
     if (gauss && (p.gauss_ksize > 2 * kGaussRB + 1 || !(p.gauss_ksize & 1) || b.h < 16 || b.w < 16)) return cudaSuccess;
     auto enc = tensor_map_encoder();
@@ -1035,7 +1027,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
-    static const int gauss_ctas = getenv("HV_K1_GAUSS_CTAS") ? std::max(1, std::min(4, atoi(getenv("HV_K1_GAUSS_CTAS")))) : 4;
+    const int gauss_ctas = tunables().k1_gauss_ctas;
     int grid = num_sms * (gauss ? gauss_ctas : (p.ctas_per_sm > 0 ? std::min(p.ctas_per_sm, k1_ctas_per_sm()) : k1_ctas_per_sm()));
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
@@ -1050,18 +1042,13 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     cfg.numAttrs = pdl ? 1 : 0;
     *used = true;
     PreprocessParams q = p;
-    static const int e_look = getenv("HV_K1_LOOKAHEAD") ? atoi(getenv("HV_K1_LOOKAHEAD")) : kTmaStages;
-    static const int e_tlook = getenv("HV_K1_TAIL_LOOKAHEAD") ? atoi(getenv("HV_K1_TAIL_LOOKAHEAD")) : 1;
-    static const int e_trounds = getenv("HV_K1_TAIL_ROUNDS") ? atoi(getenv("HV_K1_TAIL_ROUNDS")) : 0;
-    q.lookahead = e_look < 1 ? 1 : (e_look > kTmaStages ? kTmaStages : e_look);
-    q.tail_lookahead = e_tlook < 1 ? 1 : (e_tlook > q.lookahead ? q.lookahead : e_tlook);
-    q.tail_tiles = e_trounds * grid;
-    static const int e_pref = getenv("HV_K1_PREFETCH") ? atoi(getenv("HV_K1_PREFETCH")) : 0;
-    q.prefetch_tiles = e_pref;
-    static const int e_claim = getenv("HV_K1_CLAIM_AHEAD") ? atoi(getenv("HV_K1_CLAIM_AHEAD")) : 0;
-    q.claim_ahead = e_claim;
-    static const int e_hint = getenv("HV_K1_WAIT_HINT_NS") ? atoi(getenv("HV_K1_WAIT_HINT_NS")) : 10000000;
-    q.wait_hint_ns = e_hint;
+    const Tunables &tun = tunables();
+    q.lookahead = std::min(tun.k1_lookahead, kTmaStages);
+    q.tail_lookahead = std::min(tun.k1_tail_lookahead, q.lookahead);
+    q.tail_tiles = tun.k1_tail_rounds * grid;
+    q.prefetch_tiles = tun.k1_prefetch;
+    q.claim_ahead = tun.k1_claim_ahead;
+    q.wait_hint_ns = tun.k1_wait_hint_ns;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }

@@ -666,7 +666,7 @@ cudaError_t launch_morph_expand(const BatchView &b, int open_k, int close_k, uin
     // counter chain: one CTA per SM, so that the whole grid is resident next to K1 and the CCL kernels at once (it has to
     // be, to release the kernel behind it); otherwise one full wave
     static const int wave = one_wave_grid(k_morph_tiles, 256);
-    static const int chain_ctas = getenv("HV_MORPH_TILES_PER_SM") ? std::max(1, atoi(getenv("HV_MORPH_TILES_PER_SM"))) : 2;
+    const int chain_ctas = tunables().morph_tiles_per_sm;
     cfg.gridDim = dim3((unsigned)std::min<size_t>(tiles, (size_t)(chain ? std::min(num_sms * chain_ctas, wave) : wave)));
     cfg.numAttrs = 1;  // behind the scan, whatever preceded that
     return cudaLaunchKernelEx(&cfg, k_morph_tiles, b, open_k, close_k, bits_out, rowflags_out, (const uint32_t *)tile_list, ctrl,

@@ -21,7 +21,7 @@ import numpy as np
 from . import _abi
 from . import acquisition, batch, camera, detection, processing
 from ._abi import HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION
-from .batch import Detector, HeimdallCudaError, default_detector, make_params
+from .batch import Detector, HeimdallCudaError, default_detector, make_params, with_capacity_retry
 
 __all__ = ["process_image", "detect_contamination", "benchmark_processing", "acquisition", "processing", "detection",
            "batch", "camera", "Detector", "HeimdallCudaError", "make_params"]
@@ -41,10 +41,10 @@ def process_image(image, pipeline_type: str, params: Optional[dict] = None) -> D
     start = time.perf_counter()
     img = _image3(image)
     if pipeline_type == "basic":
-        out, _ = default_detector().process_image(img, HV_PIPELINE_BASIC)
+        out, _ = default_detector().process_image(img, HV_PIPELINE_BASIC)  # (no tables: cannot run out of capacity)
         result = {"processed_image": out}
     elif pipeline_type == "contamination":
-        out, contours = default_detector().process_image(img, HV_PIPELINE_CONTAMINATION)
+        out, contours = with_capacity_retry(lambda d: d.process_image(img, HV_PIPELINE_CONTAMINATION), *img.shape[:2])
         result = {"processed_image": out, "contours": contours}
     else:
         raise ValueError(f"Unsupported pipeline type: {pipeline_type}")  # lib.rs:80-84
@@ -60,7 +60,9 @@ def detect_contamination(image, min_size: Optional[float] = None, max_size: Opti
     img = _image3(image)
     p = make_params(10.0 if min_size is None else min_size, 3000.0 if max_size is None else max_size,
                     25.0 if threshold is None else threshold)
-    res = default_detector().detect_batch(img, p)
+    # the reference's defect list is unbounded: a frame beyond the default tables (131072 components, 256 defects) is
+    # run again on a context sized for the 4-connectivity maximum
+    res = with_capacity_retry(lambda d: d.detect_batch(img, p), *img.shape[:2])
     return {"defects": res.as_dicts(0), "processing_time": time.perf_counter() - start}
 
 

@@ -23,7 +23,6 @@ HV_ERR_UNSUPPORTED = -6
 HV_ERR_CHANNELS = -7
 HV_ERR_BAD_TICKET = -8
 
-HV_FLAG_NO_GRAPH = 1
 HV_FLAG_PROFILE = 2
 HV_FLAG_KEEP_BLUR = 4
 HV_FLAG_FORCE_GENERIC = 8
@@ -142,7 +141,8 @@ PROTOTYPES = {
                                _P(hv_defect), _sz, _P(_sz), _P(hv_debug_outputs)]),
     "hv_detect_batch_device": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _vp, _vp,
                                       _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
-    "hv_enqueue_device": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _vp, _vp]),
+    "hv_enqueue_device": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _vp, _vp, _P(_i64)]),
+    "hv_fetch_ticket": (_i32, [_vp, _i64, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
     "hv_fetch_results": (_i32, [_vp, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
     "hv_fetch_debug": (_i32, [_vp, _P(hv_debug_outputs)]),
     "hv_submit": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _P(_i64)]),
@@ -154,11 +154,13 @@ PROTOTYPES = {
     "hv_frameset_destroy": (None, [_vp]),
     "hv_frameset_last_error": (C.c_char_p, [_vp]),
     "hv_frameset_push": (_i32, [_vp, _P(hv_camera_frame), _P(hv_params), _P(_i64)]),
+    "hv_frameset_flush": (_i32, [_vp, _P(hv_params), _P(_i64)]),
     "hv_frameset_batch_ids": (_i32, [_vp, _i64, _P(C.c_uint64), _i32, _P(_i32)]),
     "hv_frameset_wait": (_i32, [_vp, _i64, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
     "hv_frameset_get_stats": (_i32, [_vp, _P(hv_frameset_stats)]),
     "hv_preprocess_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "hv_apply_threshold": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_uint8, _i32, _i32, _vp]),
+    "hv_morphology": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hv_find_contours": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _f64, _P(hv_contour), _sz, _P(_sz), _vp]),
     "hv_process_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _P(hv_center), _sz, _P(_sz)]),
     "hv_stats_get": (_i32, [_vp, _P(hv_line_stats)]),

@@ -79,7 +79,7 @@ class BatchResult:
 
 
 class Detector:
-    """One CUDA device, one hv_ctx.  Not thread-safe by itself; calls are serialised with a lock."""
+    """One CUDA device, one hv_ctx.  The context is not thread-safe; every call into it is serialised with a lock."""
 
     def __init__(self, device: int = 0, *, max_blobs_per_frame: int = 0, max_defects_per_frame: int = 0,
                  num_slots: int = 0, profile: bool = False, keep_blur: bool = False, force_generic: bool = False,
@@ -94,7 +94,8 @@ class Detector:
                      (A.HV_FLAG_GLOBAL_CCL if global_ccl else 0) |
                      (A.HV_FLAG_PHASE_TIMING if phase_timing else 0))
         self._ctx = C.c_void_p()
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()
+        self._inflight_frames: Dict[int, tuple] = {}  # ticket -> raw camera frames that must outlive their H2D copy
         self.device = device
         self.defect_cap = max_defects_per_frame or 256
         st = _lib.hv_create(device, C.byref(cfg), C.byref(self._ctx))
@@ -182,8 +183,11 @@ class Detector:
         res, dfx, cap = self._out_arrays(n, defects_cap)
         total = C.c_size_t(0)
         with self._lock:
-            st = _lib.hv_wait(self._ctx, ticket, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
-                              dfx.ctypes.data_as(C.POINTER(A.hv_defect)), cap, C.byref(total))
+            try:
+                st = _lib.hv_wait(self._ctx, ticket, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
+                                  dfx.ctypes.data_as(C.POINTER(A.hv_defect)), cap, C.byref(total))
+            finally:
+                self._inflight_frames.pop(ticket, None)  # hv_wait has returned: the H2D copy of the raw frames is over
             if st not in (A.HV_OK, A.HV_ERR_CAPACITY):
                 _raise(st, self._ctx)
         return BatchResult(res, dfx[:total.value], st)
@@ -210,16 +214,11 @@ class Detector:
             st = _lib.hv_submit_frames(self._ctx, arr, len(frames), C.byref(p), C.byref(t))
             if st != A.HV_OK:
                 _raise(st, self._ctx)
-        self._inflight_frames = getattr(self, "_inflight_frames", {})
-        self._inflight_frames[t.value] = (arr, list(frames))  # the raw data must outlive the copy
+            self._inflight_frames[t.value] = (arr, list(frames))  # the raw data must outlive the copy; wait() drops it
         return t.value
 
     def detect_frames(self, frames, params: Optional[A.hv_params] = None) -> BatchResult:
-        t = self.submit_frames(frames, params)
-        try:
-            return self.wait(t, len(frames))
-        finally:
-            self._inflight_frames.pop(t, None)
+        return self.wait(self.submit_frames(frames, params), len(frames))
 
     def host_alloc(self, nbytes: int) -> int:
         p = _lib.hv_host_alloc(self._ctx, nbytes)
@@ -243,25 +242,49 @@ class Detector:
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         """Run on the caller's stream (0 = legacy default stream, e.g. torch's current stream); None = own stream."""
-        st = _lib.hv_set_stream(self._ctx, cuda_stream or None, 0 if cuda_stream is None else 1)
-        if st != A.HV_OK:
-            _raise(st, self._ctx)
+        with self._lock:
+            st = _lib.hv_set_stream(self._ctx, cuda_stream or None, 0 if cuda_stream is None else 1)
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
 
     def enqueue_device(self, d_frames: int, n: int, h: int, w: int, c: int = 1,
-                       params: Optional[A.hv_params] = None, d_mask: int = 0, d_labels: int = 0) -> None:
+                       params: Optional[A.hv_params] = None, d_mask: int = 0, d_labels: int = 0) -> int:
+        """Enqueue one device-resident batch (no host synchronisation); returns its ticket.  The results travel to
+        page-locked host memory behind the batch's last kernel; `fetch(ticket, n)` returns them.  The context keeps
+        the last `pipeline_depth()` batches."""
         p = params if params is not None else make_params()
-        st = _lib.hv_enqueue_device(self._ctx, d_frames, n, h, w, c, 0, 0, C.byref(p), d_mask or None,
-                                    d_labels or None)
-        if st != A.HV_OK:
-            _raise(st, self._ctx)
+        t = C.c_int64(0)
+        with self._lock:
+            st = _lib.hv_enqueue_device(self._ctx, d_frames, n, h, w, c, 0, 0, C.byref(p), d_mask or None,
+                                        d_labels or None, C.byref(t))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        return t.value
+
+    def fetch(self, ticket: int, n: int, defects_cap: Optional[int] = None, raise_on_capacity: bool = True) -> BatchResult:
+        """Results of the batch `ticket` (hv_fetch_ticket); blocks until its read-back has arrived."""
+        res, dfx, cap = self._out_arrays(n, defects_cap)
+        return self.fetch_into(ticket, res, dfx, raise_on_capacity)
+
+    def fetch_into(self, ticket: int, res: np.ndarray, dfx: np.ndarray, raise_on_capacity: bool = True) -> BatchResult:
+        """Like fetch, into caller-provided arrays (RESULT_DTYPE[n], DEFECT_DTYPE[cap]): no allocation per batch."""
+        total = C.c_size_t(0)
+        with self._lock:
+            st = _lib.hv_fetch_ticket(self._ctx, ticket, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
+                                      dfx.ctypes.data_as(C.POINTER(A.hv_defect)), len(dfx), C.byref(total))
+            if st != A.HV_OK and not (st == A.HV_ERR_CAPACITY and not raise_on_capacity):
+                _raise(st, self._ctx)
+        return BatchResult(res, dfx[:total.value], st)
 
     def fetch_results(self, n: int, defects_cap: Optional[int] = None, raise_on_capacity: bool = True) -> BatchResult:
+        """Results of the most recently enqueued batch."""
         res, dfx, cap = self._out_arrays(n, defects_cap)
         total = C.c_size_t(0)
-        st = _lib.hv_fetch_results(self._ctx, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
-                                   dfx.ctypes.data_as(C.POINTER(A.hv_defect)), cap, C.byref(total))
-        if st != A.HV_OK and not (st == A.HV_ERR_CAPACITY and not raise_on_capacity):
-            _raise(st, self._ctx)
+        with self._lock:
+            st = _lib.hv_fetch_results(self._ctx, res.ctypes.data_as(C.POINTER(A.hv_frame_result)),
+                                       dfx.ctypes.data_as(C.POINTER(A.hv_defect)), cap, C.byref(total))
+            if st != A.HV_OK and not (st == A.HV_ERR_CAPACITY and not raise_on_capacity):
+                _raise(st, self._ctx)
         return BatchResult(res, dfx[:total.value], st)
 
     def fetch_debug(self, n: int, h: int, w: int, names: Sequence[str]) -> Dict[str, np.ndarray]:
@@ -279,16 +302,17 @@ class Detector:
             else:
                 raise ValueError(f"unknown debug output {name}")
             setattr(dbg, name, out[name].ctypes.data)
-        st = _lib.hv_fetch_debug(self._ctx, C.byref(dbg))
-        if st != A.HV_OK:
-            _raise(st, self._ctx)
+        with self._lock:
+            st = _lib.hv_fetch_debug(self._ctx, C.byref(dbg))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
         return out
 
     def detect_device(self, d_frames: int, n: int, h: int, w: int, c: int = 1, params: Optional[A.hv_params] = None,
                       d_mask: int = 0, d_labels: int = 0) -> BatchResult:
         with self._lock:
-            self.enqueue_device(d_frames, n, h, w, c, params, d_mask, d_labels)
-            return self.fetch_results(n)
+            t = self.enqueue_device(d_frames, n, h, w, c, params, d_mask, d_labels)
+            return self.fetch(t, n)
 
     # ---- single-frame utilities (processing.rs / detection.rs pyfunctions) ---------------------------------------
     def preprocess_image(self, img: np.ndarray, grayscale: bool, blur_size: int) -> np.ndarray:
@@ -307,6 +331,17 @@ class Detector:
         with self._lock:
             st = _lib.hv_apply_threshold(self._ctx, img.ctypes.data, h, w, c, thr, int(adaptive), int(inverse),
                                          out.ctypes.data)
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        return out
+
+    def morphology(self, mask: np.ndarray, open_k: int = 0, close_k: int = 0) -> np.ndarray:
+        """cv2 MORPH_OPEN (rect open_k) then MORPH_CLOSE (rect close_k) of a binary (H, W) u8 mask on the GPU."""
+        m = np.ascontiguousarray(mask, np.uint8)
+        h, w = m.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        with self._lock:
+            st = _lib.hv_morphology(self._ctx, m.ctypes.data, h, w, int(open_k), int(close_k), out.ctypes.data)
             if st != A.HV_OK:
                 _raise(st, self._ctx)
         return out
@@ -340,16 +375,18 @@ class Detector:
     # ---- statistics / measurement ----------------------------------------------------------------------------------
     def stats(self) -> dict:
         s = A.hv_line_stats()
-        st = _lib.hv_stats_get(self._ctx, C.byref(s))
-        if st != A.HV_OK:
-            _raise(st, self._ctx)
+        with self._lock:
+            st = _lib.hv_stats_get(self._ctx, C.byref(s))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
         return {"frames_inspected": s.frames_inspected, "frames_rejected": s.frames_rejected,
                 "total_defects": s.total_defects, "total_components": s.total_components,
                 "total_defect_area": s.total_defect_area, "total_fg_pixels": s.total_fg_pixels,
                 "area_hist": list(s.area_hist), "capacity_errors": s.capacity_errors}
 
     def stats_reset(self) -> None:
-        _lib.hv_stats_reset(self._ctx)
+        with self._lock:
+            _lib.hv_stats_reset(self._ctx)
 
     def stats_device_ptr(self) -> int:
         return int(_lib.hv_stats_device_ptr(self._ctx) or 0)
@@ -422,6 +459,37 @@ class DeviceArray:
             self.free()
         except Exception:
             pass
+
+
+_unbounded: Dict[int, Tuple[int, Detector]] = {}
+
+
+def unbounded_detector(h: int, w: int, device: Optional[int] = None) -> Detector:
+    """A context whose per-frame tables hold the 4-connectivity maximum of an h x w frame (h*w/2 + 1 components and
+    defects).  The reference has no limits (its lists are Vecs); the drop-in wrappers retry here when the default
+    context reports HV_ERR_CAPACITY, so callers of the reference API never see a capacity error."""
+    import os
+    if device is None:
+        device = int(os.environ.get("HEIMDALL_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    need = h * w // 2 + 1
+    with _default_lock:
+        have = _unbounded.get(device)
+        if have is None or have[0] < need:
+            if have is not None:
+                have[1].close()
+            have = (need, Detector(device, max_blobs_per_frame=need, max_defects_per_frame=need))
+            _unbounded[device] = have
+        return have[1]
+
+
+def with_capacity_retry(call, h: int, w: int):
+    """call(detector) on the default context; on HV_ERR_CAPACITY once more on the unbounded one."""
+    try:
+        return call(default_detector())
+    except HeimdallCudaError as e:
+        if e.status != A.HV_ERR_CAPACITY:
+            raise
+    return call(unbounded_detector(h, w))
 
 
 _default: Dict[int, Detector] = {}

@@ -130,8 +130,26 @@ class FrameSetBatcher:
         p = self._params
         st = A.lib.hv_frameset_push(self._h, C.byref(fa), C.byref(p) if p is not None else None, C.byref(t))
         if st != A.HV_OK:
-            raise ValueError(A.lib.hv_frameset_last_error(self._h).decode() or A.lib.hv_status_string(st).decode())
+            self._raise(st)
         return t.value
+
+    def flush(self) -> int:
+        """Retry the submission of a batch that push() could not hand over (HeimdallCudaError, status HV_ERR_CAPACITY:
+        collect an earlier ticket with wait() first).  Returns the ticket, or 0 when nothing is queued."""
+        C = self._C
+        t = C.c_int64(0)
+        p = self._params
+        st = A.lib.hv_frameset_flush(self._h, C.byref(p) if p is not None else None, C.byref(t))
+        if st != A.HV_OK:
+            self._raise(st)
+        return t.value
+
+    def _raise(self, st: int):
+        from .batch import HeimdallCudaError
+        msg = A.lib.hv_frameset_last_error(self._h).decode() or A.lib.hv_status_string(st).decode()
+        if st == A.HV_ERR_CAPACITY:
+            raise HeimdallCudaError(st, msg)
+        raise ValueError(msg)
 
     def batch_ids(self, ticket: int):
         C = self._C

@@ -32,11 +32,11 @@ def _dfs_pop_order(pixels: set, start):
 def find_contours(image, min_area: Optional[float] = None, max_area: Optional[float] = None) -> List[dict]:
     """Blobs (4-connected, foreground `> 127`) with min_area <= area <= max_area (defaults 10, 10000) in discovery
     order: {"position": (cy, cx), "area": float, "pixel_count": int[, "points": [(y, x), ...] if <= 100 pixels]}."""
-    from .batch import default_detector
+    from .batch import with_capacity_retry
     img = _image3(image)
     lo = 10.0 if min_area is None else float(min_area)
     hi = 10000.0 if max_area is None else float(max_area)
-    recs, labels = default_detector().find_contours(img, lo, hi, want_labels=True)
+    recs, labels = with_capacity_retry(lambda d: d.find_contours(img, lo, hi, want_labels=True), *img.shape[:2])
     small = {int(r.label) for r in recs if r.pixel_count <= 100}
     by_label = {}
     if small:

@@ -87,3 +87,40 @@ def high_contamination_frame(h: int = 3000, w: int = 4096, index: int = 0, pitch
     if noise > 0:
         img += rng.integers(-noise, noise + 1, size=(h, w), dtype=np.int16)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def near_threshold_frame(h: int = 1024, w: int = 1280, index: int = 0, *, spots: int = 6, noise: int = 3,
+                         background: int = 200) -> np.ndarray:
+    """An empty line position (no bottle) with `spots` faint blemishes whose contrast straddles the detector's decision
+    boundaries: blurred contrast around the adaptive threshold c = 25 (detection.rs:186,211), areas around min_size = 10 and shapes
+    whose confidence falls on either side of 0.3 (detection.rs:250,298).  spots=0 gives a noisy frame with nothing to
+    find.  Most such frames are NOT rejected -- the bottle frames always are (the reference flags the bottle outline
+    itself) -- so these are the inputs that exercise reject == False on realistic data."""
+    rng = np.random.default_rng(BASE_SEED + 200000 + index)
+    img = np.full((h, w), background, np.int16)
+    # slow illumination gradient, as a camera sees it (amplitude well below the threshold)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img += ((xx * 6) // max(w, 1) + (yy * 4) // max(h, 1)).astype(np.int16)
+    for _ in range(spots):
+        depth = int(rng.integers(70, 150))             # blur - mean peaks near 0.27 * depth three pixels inside an edge:
+                                                       # on either side of c = 25 for depths around 92
+        kind = int(rng.integers(0, 3))
+        cy, cx = int(rng.integers(20, max(h - 20, 21))), int(rng.integers(20, max(w - 20, 21)))
+        if kind == 0:                                  # small square: area around min_size
+            s = int(rng.integers(3, 12))
+            img[cy:cy + s, cx:cx + s] -= depth
+        elif kind == 1:                                # disc
+            r = int(rng.integers(2, 12))
+            y0, y1, x0, x1 = max(cy - r, 0), min(cy + r + 1, h), max(cx - r, 0), min(cx + r + 1, w)
+            sy, sx = np.mgrid[y0:y1, x0:x1]
+            sel = (sx - cx) ** 2 + (sy - cy) ** 2 <= r * r
+            img[y0:y1, x0:x1][sel] -= depth
+        else:                                          # thin streak: low fill of its bounding box -> high shape score
+            ln = int(rng.integers(6, 40))
+            for t in range(ln):
+                y, x = cy + t // 3, cx + t
+                if 0 <= y < h and 0 <= x < w:
+                    img[y, x] -= depth
+    if noise > 0:
+        img += rng.integers(-noise, noise + 1, size=(h, w), dtype=np.int16)
+    return np.clip(img, 0, 255).astype(np.uint8)

@@ -9,8 +9,10 @@
  * Threading: an hv_ctx is bound to one CUDA device and is NOT thread-safe; use one context per (thread, device).
  * The library keeps no global mutable state.  There is no CPU fallback: without a usable CUDA device hv_create fails.
  *
- * Results are bit-exact with the reference's Rust CPU path (masks, labels in raster-first-pixel order, blob
- * statistics, defect list order, confidences as IEEE f64, reject decision).
+ * Results are bit-exact with oracle/hv_oracle.c, the line-for-line C restatement of the reference's Rust CPU path
+ * (masks, labels in raster-first-pixel order, blob statistics, defect list order, confidences as IEEE f64, reject
+ * decision).  The Rust path itself cannot be built in this environment and the reference holds no golden vectors for
+ * it, so parity with the Rust binary is pinned only through that restatement ("Oracle and parity status").
  */
 #ifndef HEIMDALL_CUDA_H
 #define HEIMDALL_CUDA_H
@@ -28,7 +30,7 @@ extern "C" {
 #define HV_API __attribute__((visibility("default")))
 #endif
 
-#define HV_ABI_VERSION 1
+#define HV_ABI_VERSION 2
 
 typedef struct hv_ctx hv_ctx;
 typedef int32_t hv_status;
@@ -47,18 +49,18 @@ enum {
     HV_ERR_BAD_TICKET = -8
 };
 
-/* Context sizing. Zero means "default / grow on demand". */
+/* Context sizing. Zero means "default". */
 typedef struct {
-    int32_t max_batch;              /* frames per hv_detect_* call the scratch is pre-sized for */
-    int32_t max_height, max_width;
-    int32_t max_blobs_per_frame;    /* stats-table rows per frame; 0 -> h*w/2+1 (the 4-connectivity maximum) */
+    int32_t max_batch;              /* accepted for forward compatibility and ignored: scratch always grows on demand */
+    int32_t max_height, max_width;  /* (likewise) */
+    int32_t max_blobs_per_frame;    /* stats-table rows per frame; 0 -> min(h*w/2+1, 131072); h*w/2+1 is the 4-connectivity
+                                       maximum: ask for it explicitly when frames can be that dense (40 B per row) */
     int32_t max_defects_per_frame;  /* device-side defect slots per frame; 0 -> 256 */
     int32_t num_slots;              /* in-flight batches for hv_submit/hv_wait; 0 -> 3 */
     int32_t flags;                  /* HV_FLAG_* */
     int32_t reserved;
 } hv_config;
 
-#define HV_FLAG_NO_GRAPH 1u   /* launch kernels directly instead of replaying a captured CUDA graph */
 #define HV_FLAG_PROFILE 2u    /* record a CUDA event pair around every kernel (hv_profile_get) */
 #define HV_FLAG_FORCE_GENERIC 8u /* testing: K1 never takes the packed fast path nor the flat-tile skip */
 #define HV_FLAG_GLOBAL_CCL 16u   /* always use the global-memory CCL kernels (K2..K6), never the fused per-frame kernel */
@@ -225,11 +227,24 @@ HV_API hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, in
                                         uint8_t *d_mask, int32_t *d_labels, hv_frame_result *results,
                                         hv_defect *defects, size_t defects_cap, size_t *n_defects_total);
 
-/* Device-resident, asynchronous: enqueue only (no host synchronisation, no result read-back); results stay in the
- * context until hv_fetch_results().  This is the form CUDA-graph replay and kernel timing use. */
+/* Device-resident, asynchronous, streaming: enqueue only (no host synchronisation on the launching stream).  The
+ * batch's results (per-frame records, frame flags, defect table) are copied to page-locked host memory by the copy
+ * engine on the context's own copy stream as soon as the batch's last kernel has finished (the stream waits for the
+ * slot's device-side completion counter, so nothing is inserted between the kernels of consecutive batches), and
+ * *ticket (optional) names the batch for hv_fetch_ticket.  The context keeps the last hv_pipeline_depth() batches:
+ * enqueueing one more first retires the oldest -- waits for its read-back and, if the per-frame CCL kernel flagged
+ * frames it could not hold, finishes them with the global-memory kernels -- so every batch is completed and counted
+ * in the line statistics whether or not it is ever fetched, and the host runs at most hv_pipeline_depth() batches
+ * ahead of the device.  The launch order of the kernels is tied to device-side counters whose expected values are
+ * kernel arguments: a stream that is being captured into a CUDA graph is refused (HV_ERR_UNSUPPORTED). */
 HV_API hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
                                    size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
-                                   int32_t *d_labels);
+                                   int32_t *d_labels, int64_t *ticket);
+/* Results of a batch enqueued with hv_enqueue_device, by ticket: blocks until its read-back has arrived.
+ * HV_ERR_BAD_TICKET once the batch's scratch set has been reused (more than hv_pipeline_depth() - 1 batches later). */
+HV_API hv_status hv_fetch_ticket(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects,
+                                 size_t defects_cap, size_t *n_defects_total);
+/* Results of the most recently enqueued batch. */
 HV_API hv_status hv_fetch_results(hv_ctx *ctx, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
                                   size_t *n_defects_total);
 /* Copy intermediates of the last enqueued batch to the host (parity checks). */
@@ -315,6 +330,11 @@ HV_API const char *hv_frameset_last_error(const hv_frameset *fs);
  * slab before the call returns.  *ticket = the batch's ticket when this frame completed a batch, else 0. */
 HV_API hv_status hv_frameset_push(hv_frameset *fs, const hv_camera_frame *frame, const hv_params *params,
                                   int64_t *ticket);
+/* Retry the submission of a batch that hv_frameset_push could not hand over (it returned the detector's status, e.g.
+ * HV_ERR_CAPACITY while all num_slots tickets were in flight; the complete sets stayed queued).  *ticket = 0 when there
+ * is nothing to submit.  Complete sets queue up to max_pending_sets beyond one batch; past that the oldest is dropped
+ * and counted in sets_dropped / frames_dropped. */
+HV_API hv_status hv_frameset_flush(hv_frameset *fs, const hv_params *params, int64_t *ticket);
 /* Set ids (trigger numbers / Freerun indices) of a submitted batch, ascending. */
 HV_API hv_status hv_frameset_batch_ids(hv_frameset *fs, int64_t ticket, uint64_t *set_ids, int32_t cap, int32_t *n_sets);
 /* hv_wait for a batch submitted by the batcher (also recycles its slabs): n_cameras * sets_per_batch results. */
@@ -330,6 +350,13 @@ HV_API hv_status hv_preprocess_image(hv_ctx *ctx, const uint8_t *img, int32_t h,
 /* heimdall_core.processing.apply_threshold (processing.rs:104-185): c must be 1. */
 HV_API hv_status hv_apply_threshold(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
                                     uint8_t threshold_value, int32_t adaptive, int32_t inverse, uint8_t *out);
+
+/* Rect morphology on a binary {0, 255} mask (`> 127` counts as set): cv2.morphologyEx(MORPH_OPEN, k_open x k_open) followed
+ * by cv2.morphologyEx(MORPH_CLOSE, k_close x k_close), MORPH_RECT, OpenCV's default border; 0 skips an operation.  The
+ * stage the reference's Python detector and pipeline run on their masks (heimdall/detectors/contamination_detector.py:
+ * 81-87; heimdall/core/pipeline.py:290-332 `MorphologyStage`).  Kernel sizes up to 31. */
+HV_API hv_status hv_morphology(hv_ctx *ctx, const uint8_t *mask, int32_t h, int32_t w, int32_t open_k, int32_t close_k,
+                               uint8_t *out);
 
 /* heimdall_core.detection.find_contours (detection.rs:36-124): foreground is `> 127`; blobs with
  * min_area <= area <= max_area in discovery order. labels (optional, h*w i32) receives the full label map. */

@@ -1,129 +1,23 @@
 //! heimdall-cuda -- safe Rust wrapper over the C ABI of `include/heimdall_cuda.h`.
 //!
-//! SOURCE ONLY: not compiled or tested in this environment (no cargo/rustc).  The `extern "C"` block is a one-to-one
-//! transcription of the header; the wrapper gives the signature of `heimdall_core::detection::detect_contamination`
-//! (rust/heimdall-core/src/detection.rs:127-132) so that `lib.rs:111-113` can switch to it under a `cuda` feature.
+//! SOURCE ONLY: not compiled or tested in this environment (no cargo/rustc).  `ffi.rs` (constants, `#[repr(C)]` structs and
+//! the complete `extern "C"` block, one declaration per `HV_API` symbol) is GENERATED from the header by
+//! `tools/gen_rust_ffi.py`, and `tests/test_abi.py` fails when it is out of date.  The wrapper below gives the signature of
+//! `heimdall_core::detection::detect_contamination` (rust/heimdall-core/src/detection.rs:127-132) so that
+//! `rust/heimdall-core/src/lib.rs:111-113` can switch to it under a `cuda` feature, plus the batched streaming form a
+//! camera loop uses (heimdall-camera / heimdall-gige frames -> pinned staging -> `hv_submit` / `hv_wait`).
+//!
+//! Multi-GPU: the C ABI is per device.  A host that shards camera streams over several GPUs creates one `CudaDetector`
+//! per device (stream s -> device s % G, rust/heimdall-gige/src/lib.rs:584-616 is the per-camera fan-out it replaces) and
+//! owns the NCCL communicator itself: `stats_device_ptr()` is the 32 x u64 vector to pass to
+//! `ncclAllReduce(ncclUint64, ncclSum)` on a side stream.  This crate ships no sharding helper.
 #![allow(non_camel_case_types)]
+
+pub mod ffi;
+pub use ffi::*;
 
 use ndarray::ArrayView3;
 use std::ffi::CStr;
-use std::os::raw::{c_char, c_void};
-
-#[repr(C)]
-pub struct hv_ctx {
-    _private: [u8; 0],
-}
-pub type hv_status = i32;
-pub const HV_OK: hv_status = 0;
-pub const HV_ERR_INVALID_DIMENSIONS: hv_status = -1;
-pub const HV_ERR_CAPACITY: hv_status = -4;
-
-#[repr(C)]
-#[derive(Clone, Copy, Default)]
-pub struct hv_config {
-    pub max_batch: i32,
-    pub max_height: i32,
-    pub max_width: i32,
-    pub max_blobs_per_frame: i32,
-    pub max_defects_per_frame: i32,
-    pub num_slots: i32,
-    pub flags: i32,
-    pub reserved: i32,
-}
-
-#[repr(C)]
-#[derive(Clone, Copy)]
-pub struct hv_params {
-    pub min_size: f64,
-    pub max_size: f64,
-    pub threshold: f64,
-    pub min_confidence: f64,
-    pub gauss_sigma: f64,
-    pub blur_mode: i32,
-    pub blur_ksize: i32,
-    pub morph_open_k: i32,
-    pub morph_close_k: i32,
-    pub reserved: [i32; 4],
-}
-
-#[repr(C)]
-#[derive(Clone, Copy)]
-pub struct hv_defect {
-    pub y: i32,
-    pub x: i32,
-    pub size: f64,
-    pub confidence: f64,
-    pub ymin: i32,
-    pub xmin: i32,
-    pub ymax: i32,
-    pub xmax: i32,
-    pub label: u32,
-    pub frame: u32,
-}
-
-#[repr(C)]
-#[derive(Clone, Copy, Default)]
-pub struct hv_frame_result {
-    pub n_components: u32,
-    pub n_defects: u32,
-    pub defects_offset: u32,
-    pub rejected: u32,
-    pub fg_pixels: u32,
-    pub status: i32,
-}
-
-extern "C" {
-    pub fn hv_params_default(p: *mut hv_params);
-    pub fn hv_create(device: i32, cfg: *const hv_config, out: *mut *mut hv_ctx) -> hv_status;
-    pub fn hv_destroy(ctx: *mut hv_ctx);
-    pub fn hv_last_error(ctx: *const hv_ctx) -> *const c_char;
-    pub fn hv_host_alloc(ctx: *mut hv_ctx, bytes: usize) -> *mut c_void;
-    pub fn hv_host_free(ctx: *mut hv_ctx, p: *mut c_void);
-    /// Device buffers for the device-resident entry points; flags = HV_ALLOC_COMPRESSIBLE (1) asks for L2
-    /// compute-data compression (the mostly-zero mask / label planes then cost less DRAM write time).
-    pub fn hv_pipeline_depth() -> i32;
-    pub fn hv_device_alloc(ctx: *mut hv_ctx, bytes: usize, flags: u32, d_ptr: *mut *mut c_void, compressed_out: *mut i32) -> hv_status;
-    pub fn hv_device_free(ctx: *mut hv_ctx, d_ptr: *mut c_void) -> hv_status;
-    pub fn hv_device_read(ctx: *mut hv_ctx, host_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> hv_status;
-    pub fn hv_device_write(ctx: *mut hv_ctx, d_dst: *mut c_void, host_src: *const c_void, bytes: usize) -> hv_status;
-    pub fn hv_detect_batch(
-        ctx: *mut hv_ctx,
-        frames: *const u8,
-        n: i32,
-        h: i32,
-        w: i32,
-        c: i32,
-        row_stride: usize,
-        frame_stride: usize,
-        params: *const hv_params,
-        results: *mut hv_frame_result,
-        defects: *mut hv_defect,
-        defects_cap: usize,
-        n_defects_total: *mut usize,
-        debug: *const c_void,
-    ) -> hv_status;
-    pub fn hv_submit(
-        ctx: *mut hv_ctx,
-        frames: *const u8,
-        n: i32,
-        h: i32,
-        w: i32,
-        c: i32,
-        row_stride: usize,
-        frame_stride: usize,
-        params: *const hv_params,
-        ticket: *mut i64,
-    ) -> hv_status;
-    pub fn hv_wait(
-        ctx: *mut hv_ctx,
-        ticket: i64,
-        results: *mut hv_frame_result,
-        defects: *mut hv_defect,
-        defects_cap: usize,
-        n_defects_total: *mut usize,
-    ) -> hv_status;
-    pub fn hv_stats_device_ptr(ctx: *mut hv_ctx) -> *mut u64;
-}
 
 /// Same fields as `heimdall_core::detection::Defect` (detection.rs:12-18); metadata is filled by the Python layer.
 #[derive(Debug, Clone)]
@@ -144,18 +38,43 @@ pub enum DetectionError {
 /// One CUDA device, one context.  Not `Sync`: use one per thread, as the C ABI requires.
 pub struct CudaDetector {
     ctx: *mut hv_ctx,
+    defect_cap: usize,
+}
+
+fn default_params(min_size: f64, max_size: f64, threshold: f64) -> hv_params {
+    let mut p = std::mem::MaybeUninit::<hv_params>::uninit();
+    let mut p = unsafe {
+        hv_params_default(p.as_mut_ptr());
+        p.assume_init()
+    };
+    p.min_size = min_size;
+    p.max_size = max_size;
+    p.threshold = threshold;
+    p
 }
 
 impl CudaDetector {
     pub fn new(device: i32) -> Result<Self, DetectionError> {
         let mut ctx = std::ptr::null_mut();
-        let cfg = hv_config::default();
+        let mut cfg = std::mem::MaybeUninit::<hv_config>::uninit();
+        let cfg = unsafe {
+            hv_config_default(cfg.as_mut_ptr());
+            cfg.assume_init()
+        };
         let st = unsafe { hv_create(device, &cfg, &mut ctx) };
         if st != HV_OK {
             let msg = unsafe { CStr::from_ptr(hv_last_error(std::ptr::null())) }.to_string_lossy().into_owned();
             return Err(DetectionError::Detection(msg));
         }
-        Ok(Self { ctx })
+        Ok(Self { ctx, defect_cap: 256 })
+    }
+
+    fn error(&self, st: hv_status) -> DetectionError {
+        if st == HV_ERR_INVALID_DIMENSIONS {
+            return DetectionError::InvalidDimensions;
+        }
+        let msg = unsafe { CStr::from_ptr(hv_last_error(self.ctx)) }.to_string_lossy().into_owned();
+        DetectionError::Detection(msg)
     }
 
     /// Drop-in for `detection::detect_contamination(image, min_size, max_size, threshold)`.
@@ -172,33 +91,64 @@ impl CudaDetector {
                 owned.as_slice().expect("contiguous after to_owned")
             }
         };
-        let mut p = std::mem::MaybeUninit::<hv_params>::uninit();
-        let mut p = unsafe {
-            hv_params_default(p.as_mut_ptr());
-            p.assume_init()
-        };
-        p.min_size = min_size;
-        p.max_size = max_size;
-        p.threshold = threshold;
-        let mut res = hv_frame_result::default();
-        let cap = 256usize;
+        let p = default_params(min_size, max_size, threshold);
+        let mut res = hv_frame_result { n_components: 0, n_defects: 0, defects_offset: 0, rejected: 0, fg_pixels: 0, status: 0 };
+        let cap = self.defect_cap;
         let mut defects: Vec<hv_defect> = Vec::with_capacity(cap);
         let mut n = 0usize;
         let st = unsafe {
             hv_detect_batch(self.ctx, data.as_ptr(), 1, h as i32, w as i32, c as i32, 0, 0, &p, &mut res, defects.as_mut_ptr(), cap, &mut n, std::ptr::null())
         };
-        if st == HV_ERR_INVALID_DIMENSIONS {
-            return Err(DetectionError::InvalidDimensions);
-        }
         if st != HV_OK {
-            let msg = unsafe { CStr::from_ptr(hv_last_error(self.ctx)) }.to_string_lossy().into_owned();
-            return Err(DetectionError::Detection(msg));
+            return Err(self.error(st));
         }
         unsafe { defects.set_len(n) };
         Ok(defects
             .iter()
             .map(|d| Defect { position: (d.y as usize, d.x as usize), size: d.size, confidence: d.confidence })
             .collect())
+    }
+
+    /// Asynchronous batch from page-locked host memory (`hv_host_alloc`): returns a ticket for `wait`.
+    /// `frames` holds `n` tightly packed `h x w` Mono8 frames and must stay valid until `wait` returns.
+    pub fn submit(&self, frames: &[u8], n: usize, h: usize, w: usize, min_size: f64, max_size: f64, threshold: f64) -> Result<i64, DetectionError> {
+        assert!(frames.len() >= n * h * w);
+        let p = default_params(min_size, max_size, threshold);
+        let mut ticket = 0i64;
+        let st = unsafe { hv_submit(self.ctx, frames.as_ptr(), n as i32, h as i32, w as i32, 1, 0, 0, &p, &mut ticket) };
+        if st != HV_OK {
+            return Err(self.error(st));
+        }
+        Ok(ticket)
+    }
+
+    /// Per-frame reject decisions (`has_defects`, heimdall/inspection/base_inspector.py:40-42) and defect lists of a batch.
+    pub fn wait(&self, ticket: i64, n: usize) -> Result<Vec<(bool, Vec<Defect>)>, DetectionError> {
+        let mut res = vec![hv_frame_result { n_components: 0, n_defects: 0, defects_offset: 0, rejected: 0, fg_pixels: 0, status: 0 }; n];
+        let cap = n * self.defect_cap;
+        let mut defects: Vec<hv_defect> = Vec::with_capacity(cap);
+        let mut total = 0usize;
+        let st = unsafe { hv_wait(self.ctx, ticket, res.as_mut_ptr(), defects.as_mut_ptr(), cap, &mut total) };
+        if st != HV_OK {
+            return Err(self.error(st));
+        }
+        unsafe { defects.set_len(total) };
+        Ok(res
+            .iter()
+            .map(|r| {
+                let o = r.defects_offset as usize;
+                let list = defects[o..o + r.n_defects as usize]
+                    .iter()
+                    .map(|d| Defect { position: (d.y as usize, d.x as usize), size: d.size, confidence: d.confidence })
+                    .collect();
+                (r.rejected != 0, list)
+            })
+            .collect())
+    }
+
+    /// Device pointer of the 32 x u64 line statistics, for the host's own `ncclAllReduce`.
+    pub fn stats_device_ptr(&self) -> *mut u64 {
+        unsafe { hv_stats_device_ptr(self.ctx) }
     }
 }
 

@@ -62,11 +62,41 @@ def pixfmt():
     np.savez_compressed(os.path.join(HERE, "cv2_pixfmt.npz"), **d)
 
 
+MORPH_PIPE_CASES = [("240x333_11", (240, 333, 11, {"contaminants": 3})), ("1024x1280_1", (1024, 1280, 1, {"contaminants": 2})),
+                    ("96x128_7", (96, 128, 7, {"contaminants": 2}))]
+MORPH_PIPE_KS = [(3, 3), (3, 0), (0, 5), (5, 7), (9, 3), (15, 15)]
+
+
+def morph_pipeline():
+    """cv2_morph_pipeline.npz: cv2.morphologyEx(MORPH_OPEN k_open) then (MORPH_CLOSE k_close), MORPH_RECT, applied by
+    opencv-python to the reference-path mask of synthetic bottle frames (heimdall/detectors/contamination_detector.py:81-87
+    is the call sequence).  The GPU test runs the same frames through the detector WITH morphology and must reproduce
+    these masks bit for bit: the fused morphology kernels are pinned to OpenCV itself, not to the oracle's restatement
+    (the pre-morphology mask both sides start from is checked separately).  Masks are stored bit-packed."""
+    d = {}
+    for name, (h, w, idx, kw) in MORPH_PIPE_CASES:
+        fr = synth.bottle_frame(h, w, idx, **kw)
+        pre = O.detect_contamination(fr).mask
+        d[f"{name}_pre"] = np.packbits(pre > 0)
+        for ko, kc in MORPH_PIPE_KS:
+            m = pre
+            if ko:
+                m = cv2.morphologyEx(m, cv2.MORPH_OPEN, cv2.getStructuringElement(cv2.MORPH_RECT, (ko, ko)))
+            if kc:
+                m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (kc, kc)))
+            d[f"{name}_o{ko}_c{kc}"] = np.packbits(m > 0)
+    np.savez_compressed(os.path.join(HERE, "cv2_morph_pipeline.npz"), **d)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "pixfmt":
         pixfmt()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "morph_pipeline":
+        morph_pipeline()
+        return
     pixfmt()
+    morph_pipeline()
     rng = np.random.default_rng(20261018)
     meta = {"opencv": cv2.__version__, "numpy": np.__version__}
 

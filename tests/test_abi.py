@@ -44,7 +44,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_status_strings_and_defaults():
     import heimdall_core._abi as A
-    assert A.lib.hv_abi_version() == 1
+    assert A.lib.hv_abi_version() == 2
     assert b"sm_100a" in A.lib.hv_version()
     assert A.lib.hv_status_string(A.HV_ERR_INVALID_DIMENSIONS) == b"Invalid image dimensions: expected 3D array"
     p = A.hv_params()
@@ -145,3 +145,96 @@ def test_reference_bridge_picks_the_module_up(monkeypatch):
     import importlib
     m = importlib.import_module("heimdall_core")
     assert all(hasattr(m, n) for n in ("process_image", "detect_contamination", "benchmark_processing"))
+
+
+def test_rust_crate_is_generated_from_the_header():
+    """rust/heimdall-cuda/src/ffi.rs (constants, #[repr(C)] structs, the extern "C" block) and build.rs (the .cu source
+    list) are generated by tools/gen_rust_ffi.py from include/heimdall_cuda.h and the Makefile; the committed files must be
+    what the generator produces now, every HV_API symbol must have its `pub fn`, every header struct its `pub struct` with
+    the same field names in the same order, and build.rs must list exactly the Makefile's sources."""
+    gen = os.path.join(ROOT, "tools", "gen_rust_ffi.py")
+    r = subprocess.run(["python", gen, "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ffi = open(os.path.join(ROOT, "rust", "heimdall-cuda", "src", "ffi.rs")).read()
+    assert sorted(re.findall(r"pub fn (hv_\w+)\(", ffi)) == header_symbols()
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for body, name in re.findall(r"typedef\s+struct\s*\{(.*?)\}\s*(\w+)\s*;", hdr, flags=re.S):
+        c_fields = []
+        for decl in body.split(";"):
+            for part in decl.split(","):
+                m = re.search(r"([A-Za-z_]\w*)\s*(\[[^\]]*\])?\s*$", part.strip())
+                if m and part.strip():
+                    c_fields.append(m.group(1))
+        m = re.search(r"pub struct %s \{(.*?)\n\}" % name, ffi, flags=re.S)
+        assert m, name
+        assert re.findall(r"pub (\w+):", m.group(1)) == c_fields, name
+    mk = open(os.path.join(ROOT, "heimdall-vision_b200", "Makefile")).read()
+    srcs = [os.path.basename(s) for s in re.search(r"^SRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()]
+    build_rs = open(os.path.join(ROOT, "rust", "heimdall-cuda", "build.rs")).read()
+    listed = re.findall(r'"(\w+\.cu)"', build_rs)
+    assert listed == srcs and set(srcs) == {f for f in os.listdir(os.path.join(ROOT, "heimdall-vision_b200", "csrc")) if f.endswith(".cu")}
+    lib_rs = open(os.path.join(ROOT, "rust", "heimdall-cuda", "src", "lib.rs")).read()
+    for used in set(re.findall(r"\b(hv_[a-z_]+)\(", lib_rs)):
+        assert used in header_symbols(), used
+
+
+REFERENCE = os.environ.get("HEIMDALL_REFERENCE_ROOT", "/root/reference")
+
+_BRIDGE_PROBE = r'''
+import json, sys
+sys.path.insert(0, %(pkg)r)
+sys.path.insert(0, %(ref)r)
+import logging
+logging.disable(logging.CRITICAL)
+import numpy as np
+import heimdall_core
+calls = []
+real = heimdall_core.detect_contamination
+def spy(image, min_size=None, max_size=None, threshold=None):
+    calls.append((image.shape, min_size, max_size, threshold))
+    if %(stub)r:
+        return {"defects": [{"position": (1, 2), "size": 3.0, "confidence": 0.5, "metadata": {}}], "processing_time": 0.0}
+    return real(image, min_size, max_size, threshold)
+heimdall_core.detect_contamination = spy
+import heimdall.rust_bridge as rb                      # the UNMODIFIED reference bridge
+img = np.full((64, 96, 1), 220, np.uint8)
+img[20:30, 40:52] = 30
+out = rb.RustBridge.detect_contamination(img, 10.0, 3000.0, 25.0)
+print(json.dumps({"available": rb.RUST_AVAILABLE, "is_available": rb.RustBridge.is_available(),
+                  "module": heimdall_core.__file__, "calls": [[list(c[0])] + list(c[1:]) for c in calls],
+                  "defects": [[list(d["position"]), d["size"], d["confidence"]] for d in out["defects"]],
+                  "keys": sorted(out)}))
+'''
+
+
+def _run_bridge(stub: bool):
+    import json
+    code = _BRIDGE_PROBE % {"pkg": os.path.join(ROOT, "heimdall-vision_b200"), "ref": REFERENCE, "stub": stub}
+    r = subprocess.run(["python", "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "heimdall")), reason="reference checkout not present")
+def test_unmodified_reference_bridge_routes_to_this_module():
+    """heimdall/rust_bridge.py:20-26,118-137 of the reference, imported UNMODIFIED with this package on sys.path:
+    `import heimdall_core` succeeds, RUST_AVAILABLE flips to True, and RustBridge.detect_contamination hands the frame and
+    the three scalars to heimdall_core.detect_contamination and returns its dict untouched.  (CPU box: the call itself
+    is answered by a stub here; with a GPU the same probe runs the real kernels, see the gpu test below.)"""
+    out = _run_bridge(stub=True)
+    assert out["available"] is True and out["is_available"] is True
+    assert out["module"].startswith(os.path.join(ROOT, "heimdall-vision_b200"))
+    assert out["calls"] == [[[64, 96, 1], 10.0, 3000.0, 25.0]]
+    assert out["defects"] == [[[1, 2], 3.0, 0.5]] and out["keys"] == ["defects", "processing_time"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "heimdall")),
+                    reason="reference checkout not present (it does not travel to the GPU box)")
+def test_unmodified_reference_bridge_on_the_gpu(oracle):
+    """The same probe with the real kernels behind it: what the reference's dashboard / benchmark would get."""
+    out = _run_bridge(stub=False)
+    img = np.full((64, 96, 1), 220, np.uint8)
+    img[20:30, 40:52] = 30
+    ref = oracle.detect_contamination(img)
+    assert out["available"] is True and out["defects"] == [[list(d["position"]), d["size"], d["confidence"]] for d in ref.defects]

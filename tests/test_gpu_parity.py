@@ -328,13 +328,39 @@ def test_morphology_fused_kernel_and_fallback(oracle, detector, k_open, k_close,
             [(d["position"][0], d["position"][1], d["size"], d["confidence"]) for d in ref.defects]
 
 
-def test_morphology_matches_opencv_golden(detector, golden_dir):
-    """Mask-level check against committed cv2 outputs: run open/close via detect on an image whose mask is known."""
-    import heimdall_core as hc
+def test_morphology_entry_matches_opencv_golden(detector, golden_dir):
+    """hv_morphology (separable bit-packed erode / dilate kernels) against committed outputs of cv2.morphologyEx on two
+    masks: every operation and kernel size of tests/golden/make_golden.py, bit for bit."""
     z = np.load(os.path.join(golden_dir, "cv2_morph.npz"))
-    # build an image whose adaptive mask equals m2 is not possible in general; instead check via the oracle-validated
-    # path: oracle.morph == cv2 golden is asserted in test_oracle.py, GPU == oracle in test_morphology_open_close.
-    assert "m2_open_3" in z.files and hc is not None
+    for name in ("m1", "m2"):
+        m = z[name]
+        for k in (2, 3, 4, 5, 7, 9, 11, 13, 15):
+            assert np.array_equal(detector.morphology(m, open_k=k), z[f"{name}_open_{k}"]), (name, "open", k)
+            assert np.array_equal(detector.morphology(m, close_k=k), z[f"{name}_close_{k}"]), (name, "close", k)
+        assert np.array_equal(detector.morphology(m), m)
+
+
+@pytest.mark.parametrize("case", ["240x333_11", "1024x1280_1", "96x128_7"])
+def test_morphology_pipeline_matches_opencv_golden(detector, golden_dir, case):
+    """The morphology the detector runs between threshold and CCL (folded into K1 for 3x3 / 5x5 kernels, the tiles kernel
+    up to 15x15) against masks produced by opencv-python itself: cv2 MORPH_OPEN then MORPH_CLOSE of the frame's
+    pre-morphology mask, committed bit-packed in cv2_morph_pipeline.npz.  No oracle involved."""
+    import heimdall_core as hc
+    z = np.load(os.path.join(golden_dir, "cv2_morph_pipeline.npz"))
+    hw, idx = case.split("_")
+    h, w = map(int, hw.split("x"))
+    kw = {"240x333_11": {"contaminants": 3}, "1024x1280_1": {"contaminants": 2}, "96x128_7": {"contaminants": 2}}[case]
+    fr = synth.bottle_frame(h, w, int(idx), **kw)
+
+    def unpack(a):
+        return (np.unpackbits(a)[:h * w].reshape(h, w) * 255).astype(np.uint8)
+
+    pre = detector.detect_batch(fr, debug=["mask"]).debug["mask"][0]
+    assert np.array_equal(pre, unpack(z[f"{case}_pre"]))
+    for ko, kc in [(3, 3), (3, 0), (0, 5), (5, 7), (9, 3), (15, 15)]:
+        got = detector.detect_batch(fr, hc.make_params(morph_open_k=ko, morph_close_k=kc), debug=["mask"]).debug["mask"][0]
+        assert np.array_equal(got, unpack(z[f"{case}_o{ko}_c{kc}"])), (case, ko, kc)
+        assert np.array_equal(detector.morphology(pre, ko, kc), got)
 
 
 @pytest.mark.parametrize("k,s", [(5, 0.0), (3, 0.0), (7, 1.0), (13, 2.0), (15, 3.0), (9, 1.5)])
@@ -663,4 +689,191 @@ def test_small_ccl_build_overflow_escalates(oracle):
                 assert [((int(d["y"]), int(d["x"])), float(d["size"])) for d in res.defects_of(f)] == \
                     [(d["position"], d["size"]) for d in ref.defects]
     finally:
+        det.close()
+
+
+# ---- BASELINE configs[2] and [3] at their stated sizes, against the oracle ---------------------------------------------
+def _compare_full(res, ref, f=0):
+    assert np.array_equal(res.debug["mask"][f], ref.mask), "mask"
+    assert np.array_equal(res.debug["labels"][f], ref.labels), "labels"
+    assert int(res.frames["n_components"][f]) == ref.ncomp
+    got = [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in res.defects_of(f)]
+    assert got == [(d["position"], d["size"], d["confidence"]) for d in ref.defects]
+    assert bool(res.rejected[f]) == ref.reject
+
+
+def test_12mp_high_contamination_matches_oracle(oracle):
+    """configs[3]: one 4096x3000 frame with >= 10k blobs -- mask, label plane and defect list equal to the oracle's
+    (the per-frame kernel flags the frame, the global-memory CCL kernels finish it)."""
+    import heimdall_core as hc
+    fr = synth.high_contamination_frame(3000, 4096, 1)
+    ref = oracle.detect_contamination(fr[:, :, None])
+    assert ref.ncomp >= 10000 and len(ref.defects) > 100
+    for global_ccl in (False, True):
+        det = hc.Detector(0, max_blobs_per_frame=400000, max_defects_per_frame=200000, global_ccl=global_ccl)
+        try:
+            _compare_full(det.detect_batch(fr, debug=["mask", "labels"]), ref)
+        finally:
+            det.close()
+
+
+@pytest.mark.parametrize("gauss,morph", [((5, 0.0), 0), ((15, 3.0), 0), (None, 3), (None, 15), ((5, 0.0), 3)])
+def test_5mp_gaussian_and_morphology_match_oracle(oracle, detector, gauss, morph):
+    """configs[2]: a 2448x2048 frame through the Gaussian variants of K1 (k = 5 sigma 0, k = 15 sigma 3) and through
+    open + close (3x3: folded into K1; 15x15: the tiles kernel), each compared with the oracle: mask, labels, defects."""
+    import heimdall_core as hc
+    fr = synth.bottle_frame(2048, 2448, 5, contaminants=3)
+    kw, okw = {}, {}
+    if gauss is not None:
+        kw.update(blur_mode=hc._abi.HV_BLUR_GAUSSIAN, blur_ksize=gauss[0], gauss_sigma=gauss[1])
+        okw.update(gauss_ksize=gauss[0], gauss_sigma=gauss[1])
+    if morph:
+        kw.update(morph_open_k=morph, morph_close_k=morph)
+        okw.update(morph_open_k=morph, morph_close_k=morph)
+    ref = oracle.detect_contamination(fr[:, :, None], **okw)
+    res = detector.detect_batch(fr, hc.make_params(**kw), debug=["mask", "labels"])
+    _compare_full(res, ref)
+
+
+# ---- frames that are NOT rejected --------------------------------------------------------------------------------------
+def test_near_threshold_and_empty_frames(oracle, detector):
+    """The bottle frames are always rejected (the reference flags the bottle outline itself), so reject == False would only
+    ever be seen on the two flat KATs.  Here: empty line positions with camera noise and an illumination gradient, with
+    and without faint blemishes whose blurred contrast, area and confidence straddle c = 25, min_size = 10 and 0.3.
+    One batch of 24 frames at 256x320, one at the headline resolution; both decisions must occur and agree."""
+    frames = np.stack([synth.near_threshold_frame(256, 320, i, spots=(0 if i % 4 == 0 else 3)) for i in range(24)])
+    res = detector.detect_batch(frames[..., None], debug=["mask", "labels"])
+    refs = [oracle.detect_contamination(frames[f][:, :, None]) for f in range(len(frames))]
+    for f, ref in enumerate(refs):
+        _compare_full(res, ref, f)
+    decisions = [r.reject for r in refs]
+    assert 5 <= sum(decisions) <= 19, decisions       # a real mix of accepted and rejected frames
+    assert any(r.ncomp > 0 and not r.reject for r in refs)   # components seen, none of them a defect
+    big = np.stack([synth.near_threshold_frame(1024, 1280, 100 + i, spots=(0 if i == 0 else 4)) for i in range(4)])
+    res = detector.detect_batch(big[..., None], debug=["mask", "labels"])
+    for f in range(len(big)):
+        _compare_full(res, oracle.detect_contamination(big[f][:, :, None]), f)
+    assert not res.rejected[0]
+    # min_confidence boundary: a defect whose confidence is exactly the threshold is kept (>=, detection.rs:298)
+    import heimdall_core as hc
+    ref = next(r for r in refs if r.defects)
+    c0 = ref.defects[0]["confidence"]
+    f0 = refs.index(ref)
+    for mc, keep in ((c0, True), (np.nextafter(c0, 2.0), False)):
+        r2 = detector.detect_batch(frames[f0], hc.make_params(min_confidence=mc))
+        assert (c0 in [float(d["confidence"]) for d in r2.defects_of(0)]) == keep
+
+
+# ---- streaming: every batch's results reach the host ---------------------------------------------------------------------
+def test_streaming_tickets_deliver_every_batch(oracle):
+    """hv_enqueue_device returns a ticket per batch; the batch's results travel to pinned host memory behind its last
+    kernel (copy stream ordered by the slot's device-side counter) and hv_fetch_ticket returns them while later batches
+    are already running.  Every one of 17 batches is fetched -- lagging the enqueue by depth - 1 -- and equals the oracle;
+    tickets older than the pipeline depth are refused; the line statistics count every frame."""
+    import heimdall_core as hc
+    n, h, w = 3, 256, 384
+    n_batches = 17
+    batches = [synth.bottle_batch(n, h, w, start_index=9000 + 10 * i, contaminants=(i % 4)) for i in range(n_batches)]
+    refs = [[oracle.detect_contamination(b[f][:, :, None], want_intermediates=False) for f in range(n)] for b in batches]
+    det = hc.Detector(0)
+    try:
+        depth = det.pipeline_depth()
+        d_in = [det.device_alloc((n, h, w), np.uint8, compressible=False) for _ in range(n_batches)]
+        for a, bt in zip(d_in, batches):
+            a.set(bt)
+        masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(depth)]
+        labels = [det.device_alloc((n, h, w), np.int32) for _ in range(depth)]
+        tickets, fetched = [], {}
+
+        def fetch(i):
+            fetched[i] = det.fetch(tickets[i], n)
+
+        for i in range(n_batches):
+            tickets.append(det.enqueue_device(d_in[i].ptr, n, h, w, 1, None, masks[i % depth].ptr, labels[i % depth].ptr))
+            if i >= depth - 1:
+                fetch(i - (depth - 1))
+        assert tickets == sorted(set(tickets)) and all(t > 0 for t in tickets)
+        for i in range(n_batches - (depth - 1), n_batches):
+            fetch(i)
+        for i in range(n_batches):
+            for f in range(n):
+                got = [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in fetched[i].defects_of(f)]
+                assert got == [(d["position"], d["size"], d["confidence"]) for d in refs[i][f].defects], (i, f)
+                assert bool(fetched[i].rejected[f]) == refs[i][f].reject
+        with pytest.raises(hc.HeimdallCudaError) as ei:
+            det.fetch(tickets[0], n)                   # its scratch set has long been reused
+        assert ei.value.status == hc._abi.HV_ERR_BAD_TICKET
+        again = det.fetch(tickets[-1], n)              # a batch can be fetched more than once while it is held
+        assert np.array_equal(again.defects, fetched[n_batches - 1].defects)
+        s = det.stats()
+        assert s["frames_inspected"] == n * n_batches
+        assert s["total_defects"] == sum(len(r.defects) for b in refs for r in b)
+        assert s["frames_rejected"] == sum(r.reject for b in refs for r in b)
+    finally:
+        det.close()
+
+
+def test_streaming_finishes_flagged_frames_without_fetch(oracle):
+    """A frame too busy for the per-frame CCL kernel in the middle of a stream of batches nobody fetches: the slot is
+    retired before it is reused -- the global-memory kernels finish the flagged frame in the caller's planes, the line
+    statistics count it -- and the batches behind it switch to the bigger build (the selection state is updated at every
+    retirement, not only at a fetch)."""
+    import heimdall_core as hc
+    n, h, w = 2, 512, 640
+    busy = synth.high_contamination_frame(h, w, 3)   # 2333 non-zero words: beyond the small build
+    calm = [synth.bottle_frame(h, w, 40 + i, contaminants=1) for i in range(12)]
+    batches = [np.stack([calm[i], busy if i == 3 else calm[(i + 5) % 12]]) for i in range(12)]
+    det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=20000)
+    try:
+        depth = det.pipeline_depth()
+        d_in = [det.device_alloc((n, h, w), np.uint8, compressible=False) for _ in batches]
+        for a, bt in zip(d_in, batches):
+            a.set(bt)
+        masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(len(batches))]
+        labels = [det.device_alloc((n, h, w), np.int32) for _ in range(len(batches))]
+        tickets = [det.enqueue_device(d_in[i].ptr, n, h, w, 1, None, masks[i].ptr, labels[i].ptr) for i in range(len(batches))]
+        last = det.fetch(tickets[-1], n)
+        exp_defects = 0
+        for i, bt in enumerate(batches):
+            got_m, got_l = masks[i].get(), labels[i].get()
+            for f in range(n):
+                ref = oracle.detect_contamination(bt[f][:, :, None])
+                exp_defects += len(ref.defects)
+                assert np.array_equal(got_m[f], ref.mask), (i, f)
+                assert np.array_equal(got_l[f], ref.labels), (i, f)
+        s = det.stats()
+        assert s["frames_inspected"] == n * len(batches) and s["total_defects"] == exp_defects
+        assert len(last.defects_of(0)) == len(oracle.detect_contamination(batches[-1][0][:, :, None]).defects)
+        assert depth >= 2
+    finally:
+        det.close()
+
+
+def test_enqueue_refuses_graph_capture():
+    """The kernels of consecutive batches are ordered by device-side counters whose expected values are kernel arguments:
+    replaying a captured graph would replay stale values.  hv_enqueue_device refuses a capturing stream."""
+    import torch
+
+    import heimdall_core as hc
+    n, h, w = 2, 128, 256
+    det = hc.Detector(0)
+    try:
+        d_in = torch.from_numpy(synth.bottle_batch(n, h, w, start_index=1)).cuda()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            det.set_stream(side.cuda_stream)
+            det.enqueue_device(d_in.data_ptr(), n, h, w)          # fine outside a capture
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(capture_error_mode="relaxed")
+            try:
+                with pytest.raises(ValueError, match="cannot be captured"):
+                    det.enqueue_device(d_in.data_ptr(), n, h, w)
+            finally:
+                g.capture_end()
+            det.enqueue_device(d_in.data_ptr(), n, h, w)          # and fine again afterwards
+            assert det.fetch_results(n).frames.shape == (n,)
+        torch.cuda.synchronize()
+    finally:
+        det.set_stream(None)
         det.close()
