@@ -541,7 +541,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     if (gauss && !gaussian_kernel_q8(pr.blur_ksize, pr.gauss_sigma, gk))
         return fail(ctx, HV_ERR_INVALID_ARGUMENT, "Gaussian kernel size must be odd and in [1, 31]");
     const bool separate_blur = box_other || gauss;
-    const bool morph = pr.morph_open_k > 0 || pr.morph_close_k > 0;
+    const bool morph_req = pr.morph_open_k > 0 || pr.morph_close_k > 0;
 
     hv_status rs = reserve_slot(ctx, s, n, h, w, false, 0, c == 3, separate_blur || want_blur, gauss, d_mask == nullptr,
                                 d_labels == nullptr);
@@ -611,6 +611,19 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         b.phase_frame = tun.phase_frame;
     }
 
+    // Morphology with 3x3 / 5x5 rectangles (total reach <= 4 px) is folded into K1 itself (k_preprocess.cu, MTile): the
+    // kernels behind K1 are then exactly those of the plain pipeline.  Anything else goes through the tiles kernels.
+    PreprocessParams pp{};
+    pp.c_thresh = threshold_plan(pr.threshold, &pp.wrap_t1);
+    pp.inverse = 1;
+    pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
+    bool k1_morph = false;
+    if (morph_req && fused_box && !want_blur) {
+        PreprocessParams probe = pp;
+        probe.blur_radius = 2, probe.write_mask = 1, probe.init_labels = 1;
+        k1_morph = preprocess_tma_morph_supported(b, probe, pr.morph_open_k, pr.morph_close_k);
+    }
+    const bool morph = morph_req && !k1_morph;
     // CCL path of this batch (decided before K1 runs: the fused kernel lets K1 skip the all-zero bit-mask words)
     bool fused = !(ctx->cfg.flags & HV_FLAG_GLOBAL_CCL) && ccl_frame_supported(b);
     if (fused && ctx->dense_hint) {
@@ -628,16 +641,13 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                              (size_t)n * ((h + 31) / 32) * ((w + 127) / 128) <= 16384;
     bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !tun.ccl_big;
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
-    PreprocessParams pp{};
     // resident K1 CTAs per SM (0 = the kernel's default, 5).  Next to the small CCL build: 3.  Four would fit beside one CTA
     // of it, but those CTAs often land two to an SM, and two of them leave room for two K1 CTAs whatever K1 asked for --
     // with three the loss is one CTA instead of two (measured in one call: 41.9 us per step with 4, 41.1 with 3, although
     // K1 alone is slower with 3: 53.5 vs 50.4 us).  The morphology tiles kernel needs the room as well.
     pp.ctas_per_sm = ccl_small ? 3 : 0;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
-    pp.c_thresh = threshold_plan(pr.threshold, &pp.wrap_t1);
-    pp.inverse = 1;
-    pp.force_generic = (ctx->cfg.flags & HV_FLAG_FORCE_GENERIC) ? 1 : 0;
+    if (k1_morph) pp.morph_open_k = pr.morph_open_k, pp.morph_close_k = pr.morph_close_k;
     // Morphology in the fused kernel (k <= 15): K1 writes mask and labels as usual and the morphology kernel rewrites only
     // the tiles in reach of foreground.  Multi-pass fallback: K1 writes the bit plane only, everything is expanded later.
     if (morph_fused_plan) {

@@ -79,6 +79,8 @@ struct PreprocessParams {
     int wait_hint_ns;   // TMA kernel: suspend-time hint of mbarrier.try_wait
     int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)
+    int morph_open_k;  // TMA kernel, morphology variant: 3x3 / 5x5 open and close folded into K1 (0 = none); both 0 = the
+    int morph_close_k; // plain kernel
     int sparse_aux;    // flat tiles do not write their (all-zero) bit-mask words: only the fused per-frame CCL kernel, which
                        // reads nothing but the words flagged in rowflags, may follow (densify_bits() repairs it otherwise)
 };
@@ -156,6 +158,8 @@ cudaError_t launch_gray3(const uint8_t *d_img, int n, int h, int w, size_t row_s
 cudaError_t launch_preprocess(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, cudaStream_t s);
 cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out, unsigned int *sched,
                                   int num_sms, bool pdl, cudaStream_t s, bool *used);
+// can open_k / close_k be folded into the TMA kernel for this batch?  (3x3 / 5x5 rectangles, total reach <= 4 px)
+bool preprocess_tma_morph_supported(const BatchView &b, const PreprocessParams &p, int open_k, int close_k);
 cudaError_t launch_bits_to_mask_labels(const BatchView &b, cudaStream_t s);
 cudaError_t launch_rowflags_from_bits(const BatchView &b, cudaStream_t s);
 cudaError_t launch_densify_bits(const BatchView &b, cudaStream_t s);

@@ -24,6 +24,7 @@
 #include <cudaTypedefs.h>
 
 #include "hv_common.cuh"
+#include "expand_tile.cuh"
 
 namespace hv {
 
@@ -621,6 +622,366 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
                                                  smem + T::G_BYTES + T::U1_BYTES, f, blockIdx.x, x0, y0, flat, tid, nullptr);
 }
 
+constexpr int kTmaStages = 2;  // stages per CTA.  4 stages and 4 CTAs per SM ran the headline batch in 49.2 us, 2 stages and 5 CTAs per
+                               // SM (37.9 KB and 40 registers each) in 47.1 us: the kernel is latency-bound, residency wins
+constexpr int kK1Consumers = 256;              // threads that test, compute and store tiles
+constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler + TMA issue)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 with the morphology folded in (A8 for small kernels): cv2 MORPH_OPEN then MORPH_CLOSE with 3x3 / 5x5 rectangles
+// (heimdall/detectors/contamination_detector.py:81-87 runs 3x3 open + 3x3 close) cannot reach further than MR = 4
+// pixels, so the tile's final mask is a function of the thresholded mask of the tile + 4 px, which is a function of the
+// gray tile + 11 px: the staged box grows from 46 to 54 rows (its 16-column halo already covers the 11 columns), the
+// mask is computed for the tile + ring in shared memory, bit-packed, eroded / dilated / eroded there, and only the final
+// planes are written.  No pre-morphology plane, no tile scan, no second pass over a quarter of the frame: the kernels
+// behind K1 are exactly those of the plain pipeline.
+//
+// Geometry of a tile (x0, y0), MR = morphology reach; "box column" c is image column x0 - 16 + c:
+//   gray stage s_g  [GH = 32 + 2 (7 + MR)][160]          row g  = image row y0 - 7 - MR + g
+//   s_v   u16 [BH = 32 + 2 (5 + MR)][VP]  vertical 5-sums  row r  = image row y0 - 5 - MR + r, box column c at index c + 4
+//   s_bl  u8  [BH][BP]                    blur             same rows, box column c at index c
+//   s_h11 u16 [BH][HP]  (aliases s_v)     horizontal 11-sums of the blur, column j = box column 8 + j (image x0 - 8 + j)
+//   s_f2  u8  [MH = 32 + 2 MR][FP]        pre-morphology mask bytes, row m = image row y0 - MR + m, column j as s_h11
+//   s_ma / s_mb u32 [MH][6]               bit-packed mask, word k = image columns x0 + 32 (k - 1) ..+31
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MRv>
+struct MTile {
+    static constexpr int MR = MRv;
+    static constexpr int HX = 16;
+    static constexpr int HALO = 2 + kAdaptHalf + MR;
+    static constexpr int GW = 160;
+    static constexpr int GH = 32 + 2 * HALO;
+    static constexpr int BH = 32 + 2 * (kAdaptHalf + MR);
+    static constexpr int MH = 32 + 2 * MR;
+    static constexpr int VP = 168, BP = 168, HP = 144, FP = 144;
+    static constexpr int G_BYTES = GH * GW;
+    static constexpr int U1_BYTES = BH * VP * 2;
+    static constexpr int BL_BYTES = BH * BP;
+    static constexpr int F_BYTES = MH * FP;
+    static constexpr int M_BYTES = MH * 6 * 4;
+    static constexpr int SCRATCH = U1_BYTES + BL_BYTES + F_BYTES + 2 * M_BYTES + 32 * 4 * 4;
+    static_assert(MR == 4, "thread mappings below: 6 x 9 gray rows, 7 x 6 mask rows");
+    static_assert(BH * HP * 2 <= U1_BYTES && (U1_BYTES % 16) == 0 && (BL_BYTES % 16) == 0 && (F_BYTES % 16) == 0, "layout");
+};
+
+// pre-morphology mask bytes of the tile + ring, interior tiles (the whole staged box lies inside the image): the packed
+// u16x2 pipeline of fast_blur_rb2 / fast_threshold over the larger region
+template <int MR>
+__device__ __forceinline__ void morph_fast_mask(uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw, uint8_t *f_raw, int tid, int cth,
+                                                uint64_t *empty_bar) {
+    using T = MTile<MR>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(u1_raw);
+    uint16_t(*s_h11)[T::HP] = reinterpret_cast<uint16_t(*)[T::HP]>(u1_raw);
+    uint8_t(*s_bl)[T::BP] = reinterpret_cast<uint8_t(*)[T::BP]>(bl_raw);
+    uint8_t(*s_f2)[T::FP] = reinterpret_cast<uint8_t(*)[T::FP]>(f_raw);
+    // A. vertical 5-sums: thread = (column quad q of 40, segment of 9 rows) -> 240 threads; blur row r sums gray rows r..r+4
+    if (tid < 40 * 6) {
+        const int q = tid % 40, seg = tid / 40;
+        const int r0 = seg * 9;
+        const int nrows = min(9, T::BH - r0);
+        uint32_t lo[5], hi[5];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k][4 * q]);
+            lo[k] = prmt(v, 0, 0x4140);
+            hi[k] = prmt(v, 0, 0x4342);
+        }
+        uint32_t alo = lo[0] + lo[1] + lo[2] + lo[3], ahi = hi[0] + hi[1] + hi[2] + hi[3];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            if (k < nrows) {
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + k + 4][4 * q]);
+                const uint32_t nlo = prmt(v, 0, 0x4140), nhi = prmt(v, 0, 0x4342);
+                alo += nlo;
+                ahi += nhi;
+                *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q + 4]) = make_uint2(alo, ahi);
+                alo -= lo[k % 5];
+                ahi -= hi[k % 5];
+                lo[(k + 4) % 5] = nlo;
+                hi[(k + 4) % 5] = nhi;
+            }
+        }
+    }
+    tile_sync<true>();
+    if (tid == 0) mbar_arrive(empty_bar);  // the gray stage is dead: the producer may refill it
+    // B. horizontal 5-sums + /25: thread = (row, group of 32 box columns) -> 50 x 5 = 250 threads.  Box column c sums
+    //    s_v indices c + 2 .. c + 6; a group loads indices 32g .. 32g + 39 (columns 0, 1, 158, 159 come out as garbage
+    //    and are never used).
+    if (tid < T::BH * 5) {
+        const int g = tid % 5, r = tid / 5;
+        const uint16_t *vrow = &s_v[r][32 * g];
+        uint32_t pk[20];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(vrow + 4 * k);
+            pk[2 * k] = t.x;
+            pk[2 * k + 1] = t.y;
+        }
+        auto el = [&](int e) -> uint32_t { return (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xffffu); };
+        uint32_t s = el(2) + el(3) + el(4) + el(5);
+        uint32_t *brow = reinterpret_cast<uint32_t *>(&s_bl[r][32 * g]);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            uint32_t q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = 4 * j4 + u;
+                s += el(j + 6);
+                q[u] = __umulhi(s, 5243u << 15);  // floor(s / 25)
+                s -= el(j + 2);
+            }
+            brow[j4] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+        }
+    }
+    tile_sync<true>();
+    // C. horizontal 11-sums of the blur: thread = (row, group of 36 output columns) -> 50 x 4 = 200 threads.  Output column
+    //    j (box column 8 + j) sums box columns 3 + j .. 13 + j; a group loads the 13 words from box column 36g.
+    if (tid < T::BH * 4) {
+        const int g = tid & 3, r = tid >> 2;
+        const uint32_t *brow = reinterpret_cast<const uint32_t *>(&s_bl[r][36 * g]);
+        uint32_t wd[13];
+#pragma unroll
+        for (int k = 0; k < 13; k++) wd[k] = brow[k];
+        auto by = [&](int e) -> uint32_t { return (wd[e >> 2] >> (8 * (e & 3))) & 0xffu; };
+        uint32_t s = 0;
+#pragma unroll
+        for (int e = 3; e < 13; e++) s += by(e);
+        uint32_t *hrow = reinterpret_cast<uint32_t *>(&s_h11[r][36 * g]);
+#pragma unroll
+        for (int c2 = 0; c2 < 18; c2++) {
+            s += by(2 * c2 + 13);
+            const uint32_t a = s;
+            s -= by(2 * c2 + 3);
+            s += by(2 * c2 + 14);
+            hrow[c2] = a | (s << 16);
+            s -= by(2 * c2 + 4);
+        }
+    }
+    tile_sync<true>();
+    // D. vertical 11-sums + threshold test: thread = (column quad of 36, segment of 6 mask rows) -> 252 threads.  Mask row m
+    //    sums s_h11 rows m .. m + 10, its own pixel is blur row m + 5.
+    if (tid < 36 * 7) {
+        const int q = tid % 36, seg = tid / 36;
+        const int r0 = seg * 6;
+        const int nrows = min(6, T::MH - r0);
+        const uint32_t K2 = (uint32_t)((cth + 1) * 121) * 0x00010001u;
+        uint32_t rl[11], rh[11];
+        uint32_t alo = 0x00010001u, ahi = 0x00010001u;  // the "+ 1"
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(&s_h11[r0 + k][4 * q]);
+            rl[k] = t.x;
+            rh[k] = t.y;
+            alo += t.x;
+            ahi += t.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            if (k < nrows) {
+                const uint2 t = *reinterpret_cast<const uint2 *>(&s_h11[r0 + k + 10][4 * q]);
+                alo += t.x;
+                ahi += t.y;
+                const uint32_t px4 = *reinterpret_cast<const uint32_t *>(&s_bl[r0 + k + 5][4 * q + 8]);
+                const uint32_t xlo = prmt(px4, 0, 0x4140) * 121u + K2, xhi = prmt(px4, 0, 0x4342) * 121u + K2;
+                const uint32_t dlo = __vminu2(__vmaxu2(alo, xlo) - xlo, 0x00010001u);
+                const uint32_t dhi = __vminu2(__vmaxu2(ahi, xhi) - xhi, 0x00010001u);
+                *reinterpret_cast<uint32_t *>(&s_f2[r0 + k][4 * q]) = prmt(dlo, dhi, 0x6420) * 255u;
+                alo -= rl[k % 11];
+                ahi -= rh[k % 11];
+                rl[(k + 10) % 11] = t.x;
+                rh[(k + 10) % 11] = t.y;
+            }
+        }
+    }
+    tile_sync<true>();
+}
+
+// the same for tiles whose box is clipped by the image: per-pixel loops with the border rules (blur passes through outside
+// the interior, the 11x11 window is truncated and divides by its own count), zero outside the image
+template <int MR>
+__device__ __forceinline__ void morph_generic_mask(const BatchView &b, uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw,
+                                                   uint8_t *f_raw, int x0, int y0, int tid, int cth, uint64_t *empty_bar) {
+    using T = MTile<MR>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint16_t(*s_h11)[T::HP] = reinterpret_cast<uint16_t(*)[T::HP]>(u1_raw);
+    uint8_t(*s_bl)[T::BP] = reinterpret_cast<uint8_t(*)[T::BP]>(bl_raw);
+    uint8_t(*s_f2)[T::FP] = reinterpret_cast<uint8_t(*)[T::FP]>(f_raw);
+    const int H = b.h, W = b.w;
+    // blur over box columns 2..157 of the BH ring rows (zero outside the image: TMA zero fill + explicit test)
+    for (int idx = tid; idx < T::BH * 156; idx += kK1Consumers) {
+        const int r = idx / 156, c = idx - r * 156 + 2;
+        const int gy = y0 - kAdaptHalf - MR + r, gx = x0 - T::HX + c;
+        uint32_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            if (gy >= 2 && gy < H - 2 && gx >= 2 && gx < W - 2) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+                    for (int dx = -2; dx <= 2; dx++) s += s_g[r + dy][c + dx];
+                v = div25(s);
+            } else {
+                v = s_g[r + 2][c];
+            }
+        }
+        s_bl[r][c] = (uint8_t)v;
+    }
+    tile_sync<true>();
+    if (tid == 0) mbar_arrive(empty_bar);
+    for (int idx = tid; idx < T::BH * T::HP; idx += kK1Consumers) {
+        const int r = idx / T::HP, j = idx - r * T::HP;
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_bl[r][j + 3 + k];
+        s_h11[r][j] = (uint16_t)s;
+    }
+    tile_sync<true>();
+    for (int idx = tid; idx < T::MH * T::FP; idx += kK1Consumers) {
+        const int m = idx / T::FP, j = idx - m * T::FP;
+        const int gy = y0 - MR + m, gx = x0 - 8 + j;
+        uint8_t fg = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < 2 * kAdaptHalf + 1; k++) s += s_h11[m + k][j];
+            const int rows = min(gy + kAdaptHalf, H - 1) - max(gy - kAdaptHalf, 0) + 1;
+            const int cols = min(gx + kAdaptHalf, W - 1) - max(gx - kAdaptHalf, 0) + 1;
+            const int px = s_bl[m + kAdaptHalf][j + 8];
+            fg = ((px + cth + 1) * rows * cols <= s) ? 255 : 0;
+        }
+        s_f2[m][j] = fg;
+    }
+    tile_sync<true>();
+}
+
+// One erode / dilate pass with a (2r+1) x (2r+1) rectangle over the bit-packed region, one thread per word.  OpenCV's
+// default border ("outside the image never wins") is applied when a word is READ: bits outside the image count as 1 for
+// erode and 0 for dilate.  Words and rows beyond the staged region read as the identity as well (what they would really
+// hold is unknown, but nothing that far away can reach the tile).
+template <bool DILATE, int MH>
+__device__ __forceinline__ uint32_t morph_rect_word(const uint32_t (*src)[6], int m, int k, int r, int m_lo, int m_hi,
+                                                    const uint32_t (&inm)[3]) {
+    uint32_t acc = DILATE ? 0u : 0xffffffffu;
+    const int a_lo = max(m - r, m_lo), a_hi = min(m + r, m_hi);
+    for (int mm = a_lo; mm <= a_hi; mm++) {
+        uint32_t L = k > 0 ? src[mm][k - 1] : 0u, M = src[mm][k], R = k < 5 ? src[mm][k + 1] : 0u;
+        L = DILATE ? (L & inm[0]) : (L | ~inm[0]);
+        M = DILATE ? (M & inm[1]) : (M | ~inm[1]);
+        R = DILATE ? (R & inm[2]) : (R | ~inm[2]);
+        uint32_t h = M;
+        for (int dx = 1; dx <= r; dx++) {
+            const uint32_t tr = __funnelshift_r(M, R, dx), tl = __funnelshift_l(L, M, dx);
+            h = DILATE ? (h | tr | tl) : (h & tr & tl);
+        }
+        acc = DILATE ? (acc | h) : (acc & h);
+    }
+    return acc;
+}
+
+// Everything after the flat decision for the morphology variant: pre-morphology mask of the tile + ring, bit-packing,
+// erode(ro) -> dilate(ro + rc) -> erode(rc) (open = erode, dilate; close = dilate, erode; the two dilations in the middle are
+// one), final planes.  Block-uniform control flow; contains barriers.
+template <int MR>
+__device__ __forceinline__ void morph_tile_compute_and_store(const BatchView &b, const PreprocessParams &p, uint32_t *bits_out,
+                                                             uint8_t *g_raw, uint8_t *scratch, int f, int tx, int ty, bool flat,
+                                                             bool box_inside, int tid, uint64_t *empty_bar) {
+    using T = MTile<MR>;
+    uint8_t *u1_raw = scratch, *bl_raw = u1_raw + T::U1_BYTES, *f_raw = bl_raw + T::BL_BYTES;
+    uint32_t(*s_ma)[6] = reinterpret_cast<uint32_t(*)[6]>(f_raw + T::F_BYTES);
+    uint32_t(*s_mb)[6] = reinterpret_cast<uint32_t(*)[6]>(f_raw + T::F_BYTES + T::M_BYTES);
+    uint32_t(*s_w)[4] = reinterpret_cast<uint32_t(*)[4]>(f_raw + T::F_BYTES + 2 * T::M_BYTES);
+    uint8_t(*s_f2)[T::FP] = reinterpret_cast<uint8_t(*)[T::FP]>(f_raw);
+    const int H = b.h, W = b.w, WW = b.ww;
+    const int x0 = tx * 128, y0 = ty * 32;
+    bool any = false;
+    if (flat) {
+        if (tid == 0) mbar_arrive(empty_bar);  // every thread is past its flat-test reads of the stage
+    } else {
+        if (box_inside)
+            morph_fast_mask<MR>(g_raw, u1_raw, bl_raw, f_raw, tid, p.c_thresh, empty_bar);
+        else
+            morph_generic_mask<MR>(b, g_raw, u1_raw, bl_raw, f_raw, x0, y0, tid, p.c_thresh, empty_bar);
+        // bit-packing: thread = (mask row m, word k); word k holds image columns x0 + 32 (k - 1) .. + 31 = s_f2 columns
+        // 32k - 24 .. 32k + 7, of which 0 .. 143 exist.  Bits outside the image are cleared.
+        const int m = tid / 6, k = tid - 6 * m;
+        uint32_t word = 0, in_m = 0;
+        if (tid < T::MH * 6) {
+            const int gy = y0 - MR + m;
+            const int gx0 = x0 + 32 * (k - 1);  // image column of bit 0
+            if (gy >= 0 && gy < H && gx0 + 31 >= 0 && gx0 < W) {
+                in_m = 0xffffffffu;
+                if (gx0 < 0) in_m = 0u;  // (tiles start at multiples of 128: a word is inside or outside as a whole on the left)
+                if (gx0 + 32 > W) in_m &= (1u << (W - gx0)) - 1u;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int j = 32 * k - 24 + 4 * i;
+                if (j >= 0 && j <= T::FP - 4) {
+                    const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_f2[m][j]);
+                    word |= (((v & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
+                }
+            }
+            word &= in_m;
+            s_ma[m][k] = word;
+        }
+        any = tile_sync_or<true>(word);  // also: s_ma complete
+        if (any) {
+            // in-image masks of the three words a thread reads, rows of the region that lie inside the image
+            uint32_t inm[3] = {0u, in_m, 0u};
+            const int m_lo = max(0, MR - y0), m_hi = min(T::MH - 1, MR + (H - 1 - y0));
+            if (tid < T::MH * 6) {
+                auto col_mask = [&](int kk) -> uint32_t {
+                    const int gx0 = x0 + 32 * (kk - 1);
+                    if (kk < 0 || kk > 5 || gx0 < 0 || gx0 >= W) return 0u;
+                    return gx0 + 32 > W ? (1u << (W - gx0)) - 1u : 0xffffffffu;
+                };
+                inm[0] = col_mask(k - 1), inm[1] = col_mask(k), inm[2] = col_mask(k + 1);
+            }
+            const int ro = p.morph_open_k > 0 ? (p.morph_open_k - 1) / 2 : 0, rc = p.morph_close_k > 0 ? (p.morph_close_k - 1) / 2 : 0;
+            const uint32_t(*src)[6] = s_ma;
+            uint32_t(*dst)[6] = s_mb;
+            const bool row_in = m >= m_lo && m <= m_hi;
+            auto flip = [&]() {
+                tile_sync<true>();
+                const uint32_t(*t)[6] = dst;
+                dst = const_cast<uint32_t(*)[6]>(src);
+                src = t;
+            };
+            if (ro > 0) {
+                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<false, T::MH>(src, m, k, ro, m_lo, m_hi, inm) & inm[1]) : 0u;
+                flip();
+            }
+            if (ro + rc > 0) {
+                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<true, T::MH>(src, m, k, ro + rc, m_lo, m_hi, inm) & inm[1]) : 0u;
+                flip();
+            }
+            if (rc > 0) {
+                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<false, T::MH>(src, m, k, rc, m_lo, m_hi, inm) & inm[1]) : 0u;
+                flip();
+            }
+            if (tid < 128) s_w[tid >> 2][tid & 3] = src[MR + (tid >> 2)][1 + (tid & 3)];
+            tile_sync<true>();
+        }
+    }
+    // final bit-mask words, occupancy records, then the mask bytes and the label plane
+    uint32_t word = 0;
+    if (tid < 128) {
+        const int r = tid >> 2, wq = tid & 3;
+        if (any) word = s_w[r][wq];
+        const int gy = y0 + r, gwx = 4 * tx + wq;
+        if (gy >= H || gwx >= WW) word = 0;
+        if (gy < H && gwx < WW && !(p.sparse_aux && !any)) bits_out[((size_t)f * H + gy) * WW + gwx] = word;
+        const uint32_t bal = __ballot_sync(0xffffffffu, word != 0);
+        if (b.rowflags && wq == 0 && gy < H)
+            b.rowflags[(size_t)f * b.rf_stride + rowflag_index(gy, tx, b.tiles_x)] = (uint8_t)((bal >> (tid & 31)) & 0xfu);
+    }
+    const bool any_out = tile_sync_or<true>(word);
+    expand_tile(b, (size_t)f, tx, ty, s_w, any_out, tid);
+    // s_w / s_ma / s_mb are rewritten by the next tile only behind its flat-test barrier, which every consumer reaches after
+    // its reads here
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K1 v3: persistent CTAs, TMA-staged tiles (cp.async.bulk.tensor.3d + mbarrier), double buffering, dynamic tile scheduler.
 // The v2 kernel above is one CTA per tile: load -> barrier -> compute -> store, so every tile exposes a full DRAM latency
@@ -628,35 +989,37 @@ __global__ void __launch_bounds__(256, 8) k_preprocess(BatchView b, PreprocessPa
 // from an atomic counter and the TMA unit loads tile k+1 (zero-filling outside the image) while the threads test, compute
 // and store tile k; no thread ever issues a global load for pixels.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTmaStages = 2;  // stages per CTA.  4 stages and 4 CTAs per SM ran the headline batch in 49.2 us, 2 stages and 5 CTAs per
-                               // SM (37.9 KB and 40 registers each) in 47.1 us: the kernel is latency-bound, residency wins
 
-template <int TW, int TH, int RB>
+template <int TW, int TH, int RB, int MR = 0>
 struct TmaSmem {
     using T = Tile<TW, TH, RB, 16>;  // 16-column halo: TMA boxes must start on a 16-byte boundary
     static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
     static constexpr int BYTES = kTmaStages * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
 };
+template <int TW, int TH>
+struct TmaSmem<TW, TH, 2, 4> {  // box blur + 3x3 / 5x5 open + close folded in
+    using T = MTile<4>;
+    static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
+    static constexpr int BYTES = kTmaStages * STAGE + T::SCRATCH;
+};
 
-constexpr int kK1Consumers = 256;              // threads that test, compute and store tiles
-constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler + TMA issue)
 
 // Warp-specialised: warp 8 is the producer (one elected lane takes tile numbers from the scheduler and issues the TMA
 // loads, running up to kTmaStages tiles ahead), warps 0..7 are the consumers.  In the first TMA version thread 0 did the
 // refill between two tiles: the TMA issue sits behind that thread's own outstanding global stores, and every barrier of
 // the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
 // producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
-template <int TW, int TH, int RB>
-__global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(const __grid_constant__ CUtensorMap tmap,
-                                                                            const __grid_constant__ BatchView b,
-                                                                            const __grid_constant__ PreprocessParams p,
-                                                                            uint32_t *bits_out, unsigned int *sched) {
-    using T = typename TmaSmem<TW, TH, RB>::T;
-    constexpr int STAGE = TmaSmem<TW, TH, RB>::STAGE;
+template <int TW, int TH, int RB, int MR = 0>
+__global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
+    k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BatchView b,
+                     const __grid_constant__ PreprocessParams p, uint32_t *bits_out, unsigned int *sched) {
+    using T = typename TmaSmem<TW, TH, RB, MR>::T;
+    constexpr int STAGE = TmaSmem<TW, TH, RB, MR>::STAGE;
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t full[kTmaStages], empty[kTmaStages];
     __shared__ int4 s_tile[kTmaStages];  // {tile number, frame, tile x, tile y}, decoded once by the producer
     uint8_t *f_raw = sm + kTmaStages * STAGE, *u1_raw = f_raw + TH * TW, *bl_raw = u1_raw + T::U1_BYTES;
+    (void)u1_raw, (void)bl_raw;
 
     const int tid = threadIdx.x;
     const int H = b.h, W = b.w;
@@ -762,7 +1125,7 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
     // flat test of a box that lies entirely inside the image: columns [8, 152) of all GH rows as
     //   - 16-byte items over columns [16, 144): 8 per row -> rows 0..31 one per thread, rows 32..45 threads 0..111
     //   - 8-byte edge items (columns 8..15 and 144..151): 2 per row -> threads 128..219
-    static_assert(TW == 128 && TH == 32 && T::GW == 160 && T::GOFF == 8 && (RB != 2 || T::GH == 46), "flat-test thread mapping");
+    static_assert(TW == 128 && TH == 32 && T::GW == 160 && (MR > 0 || RB != 2 || T::GH == 46), "flat-test thread mapping");
     const uint32_t ft0 = (uint32_t)((tid >> 3) * T::GW + 16 + (tid & 7) * 16);
     const uint32_t ft1 = (uint32_t)((32 + (tid >> 3)) * T::GW + 16 + (tid & 7) * 16);  // tid < 112
     const uint32_t fte = (uint32_t)((((tid - 128) >> 1)) * T::GW + (((tid - 128) & 1) ? 144 : 8));  // 128 <= tid < 220
@@ -791,7 +1154,29 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
         // flatness test straight from shared memory, over the in-image part of the tile + halo
         uint8_t *cur_stage = sm + st * STAGE;
         uint32_t acc = 0;
-        if (RB != 2) {
+        if constexpr (MR > 0) {
+            // morphology variant: every 16-byte item of the box that lies inside the image (the image is 16-px aligned, so an
+            // item is inside or outside as a whole).  The mask of the tile + MR ring depends on columns [5, 155) of the box:
+            // the outer four columns on either side are ignored.
+            if (try_flat) {
+                constexpr int IPR = T::GW / 16;
+                int r_lo = 0, r_hi = T::GH, j_lo = 0, j_hi = IPR;
+                if (!box_inside) {
+                    r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
+                    j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
+                }
+                const uint32_t ref4 = 0x01010101u * cur_stage[min(T::HALO + TH / 2, r_hi - 1) * T::GW + min(T::HX + TW / 2, 16 * j_hi - 1)];
+                for (int idx = tid; idx < T::GH * IPR; idx += kK1Consumers) {
+                    const int r = idx / IPR, j = idx - r * IPR;
+                    if (r >= r_lo && r < r_hi && j >= j_lo && j < j_hi) {
+                        uint4 v = *reinterpret_cast<const uint4 *>(cur_stage + r * T::GW + 16 * j);
+                        if (j == 0) v.x = ref4;
+                        if (j == IPR - 1) v.w = ref4;
+                        absd(v.x, ref4, acc), absd(v.y, ref4, acc), absd(v.z, ref4, acc), absd(v.w, ref4, acc);
+                    }
+                }
+            }
+        } else if (RB != 2) {
             // Gaussian variant.  BORDER_REFLECT_101: cells of the box that lie outside the image (TMA zero fill) but within
             // reach of the filters (RB + 5 <= 12 px) take the value of their mirror image, which is inside the box.
             uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(cur_stage);
@@ -889,6 +1274,9 @@ __global__ void __launch_bounds__(kK1Threads, RB == 2 ? 5 : 4) k_preprocess_tma(
                 *reinterpret_cast<int4 *>(b.rowflags + (size_t)f * b.rf_stride + rowflag_index(y0, tx, tiles_x) + 16 * tid) = z;
             if (b.tile_occ && tid == 2) reinterpret_cast<uint32_t *>(b.tile_occ)[cur.x] = 0u;  // (the tile number is its index)
             if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
+        } else if constexpr (MR > 0) {
+            morph_tile_compute_and_store<MR>(b, p, bits_out, cur_stage, sm + kTmaStages * STAGE, f, tx, ty, flat, box_inside, tid,
+                                             &empty[st]);
         } else {
             tile_compute_and_store<TW, TH, RB, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
                                                          tid, &empty[st]);
@@ -989,6 +1377,12 @@ cudaError_t configure_preprocess_tma() {
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TmaSmem<128, 32, kGaussRB>::BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TmaSmem<128, 32, 2, 4>::BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     // ask for the largest shared-memory carve-out: residency of these kernels is limited by shared memory, not by L1
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -1001,6 +1395,20 @@ cudaError_t configure_preprocess_tma() {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_preprocess<128, 32, 0>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 cudaSharedmemCarveoutMaxShared);
+}
+
+// 3x3 / 5x5 open and close whose total reach is at most 4 px (MTile<4>), on a batch the TMA kernel takes at all, with
+// the standard comparison (inverse, 0 <= c <= 255, no blur debug plane, no forced generic path)
+bool preprocess_tma_morph_supported(const BatchView &b, const PreprocessParams &p, int open_k, int close_k) {
+    auto ok_k = [](int k) { return k == 0 || k == 3 || k == 5; };
+    if (!ok_k(open_k) || !ok_k(close_k) || (open_k == 0 && close_k == 0)) return false;
+    if ((open_k > 0 ? open_k - 1 : 0) + (close_k > 0 ? close_k - 1 : 0) > 4) return false;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(b.gray);
+    if (p.blur_radius != 2 || p.gauss_ksize > 0 || (base & 15) || (b.gray_row_stride & 15) || (b.gray_frame_stride & 15) || (b.w & 15) ||
+        tunables().k1_no_tma || tunables().no_k1_morph)
+        return false;
+    return p.inverse && p.c_thresh >= 0 && p.c_thresh <= 255 && !p.write_blur && !p.force_generic && !p.wrap_t1 && p.write_mask &&
+           p.init_labels && tensor_map_encoder() != nullptr;
 }
 
 // TMA path: 3-D tensor map {w, h, n} over the gray frames, box = tile + halo, zero fill outside the image.
@@ -1016,7 +1424,9 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     if (gauss && (p.gauss_ksize > 2 * kGaussRB + 1 || !(p.gauss_ksize & 1) || b.h < 16 || b.w < 16)) return cudaSuccess;
     auto enc = tensor_map_encoder();
     if (!enc) return cudaSuccess;
-    const int gh = gauss ? Tile<128, 32, kGaussRB, 16>::GH : Tile<128, 32, 2, 16>::GH;
+    const bool morph = !gauss && (p.morph_open_k > 0 || p.morph_close_k > 0);
+    if (morph && !preprocess_tma_morph_supported(b, p, p.morph_open_k, p.morph_close_k)) return cudaSuccess;
+    const int gh = gauss ? Tile<128, 32, kGaussRB, 16>::GH : (morph ? MTile<4>::GH : Tile<128, 32, 2, 16>::GH);
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)b.w, (cuuint64_t)b.h, (cuuint64_t)b.n};
     const cuuint64_t strides[2] = {(cuuint64_t)b.gray_row_stride, (cuuint64_t)b.gray_frame_stride};
@@ -1029,11 +1439,12 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
     const int gauss_ctas = tunables().k1_gauss_ctas;
     int grid = num_sms * (gauss ? gauss_ctas : (p.ctas_per_sm > 0 ? std::min(p.ctas_per_sm, k1_ctas_per_sm()) : k1_ctas_per_sm()));
+    if (morph) grid = std::min(grid, num_sms * 4);  // 50 KB of shared memory per CTA
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kK1Threads);
-    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES : TmaSmem<128, 32, 2>::BYTES;
+    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES : (morph ? TmaSmem<128, 32, 2, 4>::BYTES : TmaSmem<128, 32, 2>::BYTES);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1050,6 +1461,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.claim_ahead = tun.k1_claim_ahead;
     q.wait_hint_ns = tun.k1_wait_hint_ns;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
+    if (morph) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 4>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
 

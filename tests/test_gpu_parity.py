@@ -756,9 +756,8 @@ def test_near_threshold_and_empty_frames(oracle, detector):
     assert not res.rejected[0]
     # min_confidence boundary: a defect whose confidence is exactly the threshold is kept (>=, detection.rs:298)
     import heimdall_core as hc
-    ref = next(r for r in refs if r.defects)
-    c0 = ref.defects[0]["confidence"]
-    f0 = refs.index(ref)
+    f0 = next(f for f, r in enumerate(refs) if r.defects)
+    c0 = refs[f0].defects[0]["confidence"]
     for mc, keep in ((c0, True), (np.nextafter(c0, 2.0), False)):
         r2 = detector.detect_batch(frames[f0], hc.make_params(min_confidence=mc))
         assert (c0 in [float(d["confidence"]) for d in r2.defects_of(0)]) == keep
