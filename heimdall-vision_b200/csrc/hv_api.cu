@@ -33,6 +33,7 @@ hv::Tunables read_tunables() {
     t.pipeline_depth = env_int("HV_PIPELINE_DEPTH", t.pipeline_depth, 2, 8);
     t.k1_ctas_per_sm = env_int("HV_K1_CTAS_PER_SM", t.k1_ctas_per_sm, 1, 5);
     t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
+    t.k1_stages_coresident = env_int("HV_K1_STAGES", t.k1_stages_coresident, 2, 3);
     t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
     t.k1_tail_rounds = env_int("HV_K1_TAIL_ROUNDS", t.k1_tail_rounds, 0, 1 << 20);
@@ -646,6 +647,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // with three the loss is one CTA instead of two (measured in one call: 41.9 us per step with 4, 41.1 with 3, although
     // K1 alone is slower with 3: 53.5 vs 50.4 us).  The morphology tiles kernel needs the room as well.
     pp.ctas_per_sm = ccl_small ? 3 : 0;
+    pp.stages = ccl_small ? tun.k1_stages_coresident : 2;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
     if (k1_morph) pp.morph_open_k = pr.morph_open_k, pp.morph_close_k = pr.morph_close_k;
     // Morphology in the fused kernel (k <= 15): K1 writes mask and labels as usual and the morphology kernel rewrites only

@@ -76,6 +76,7 @@ struct PreprocessParams {
     int tail_lookahead; // tile numbers handed out are within tail_tiles of the end (set by launch_preprocess_tma)
     int tail_tiles;
     int ctas_per_sm;    // TMA kernel: resident CTAs per SM to launch (0 = default); 4 leaves room for the small CCL build
+    int stages;         // TMA kernel: 0 / 2 = two stages per CTA, 3 = three (box-blur variants; used at three CTAs per SM)
     int wait_hint_ns;   // TMA kernel: suspend-time hint of mbarrier.try_wait
     int claim_ahead;    // TMA kernel: request the next tile number one tile early (hides the atomic's round trip)
     int prefetch_tiles; // TMA kernel: L2-prefetch the box of the tile this many tile numbers ahead of every claimed tile (0 = off)
@@ -118,8 +119,9 @@ __device__ __forceinline__ uint8_t gray_f64(uint32_t c0, uint32_t c1, uint32_t c
 // the enqueue path calls getenv.  Defaults are the measured optimum ("Experiment switches").  The HV_EXP_*
 // switches, which make the library skip work, exist only in builds with -DHV_EXPERIMENTS (make EXPERIMENTS=1).
 struct Tunables {
-    int pipeline_depth = 5;       // HV_PIPELINE_DEPTH: scratch sets in rotation = batches in flight on the device (2..8)
+    int pipeline_depth = 6;       // HV_PIPELINE_DEPTH: scratch sets in rotation = batches in flight on the device (2..8)
     int k1_ctas_per_sm = 5;       // HV_K1_CTAS_PER_SM (1..5)
+    int k1_stages_coresident = 2; // HV_K1_STAGES: TMA stages of K1 when it runs at three CTAs per SM next to the CCL kernel (2 | 3)
     int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4)
     int k1_lookahead = 2;         // HV_K1_LOOKAHEAD: tiles the TMA producer runs ahead
     int k1_tail_lookahead = 1;    // HV_K1_TAIL_LOOKAHEAD

@@ -642,7 +642,7 @@ constexpr int kK1Threads = kK1Consumers + 32;  // + one producer warp (scheduler
 //   s_bl  u8  [BH][BP]                    blur             same rows, box column c at index c
 //   s_h11 u16 [BH][HP]  (aliases s_v)     horizontal 11-sums of the blur, column j = box column 8 + j (image x0 - 8 + j)
 //   s_f2  u8  [MH = 32 + 2 MR][FP]        pre-morphology mask bytes, row m = image row y0 - MR + m, column j as s_h11
-//   s_ma / s_mb u32 [MH][6]               bit-packed mask, word k = image columns x0 + 32 (k - 1) ..+31
+//   s_ma / s_mb u32 [MH][8]               bit-packed mask, word k (at column k + 1) = image columns x0 + 32 (k - 1) ..+31
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MRv>
 struct MTile {
@@ -658,7 +658,7 @@ struct MTile {
     static constexpr int U1_BYTES = BH * VP * 2;
     static constexpr int BL_BYTES = BH * BP;
     static constexpr int F_BYTES = MH * FP;
-    static constexpr int M_BYTES = MH * 6 * 4;
+    static constexpr int M_BYTES = MH * 8 * 4;  // rows padded to 8 words: word k at column k + 1
     static constexpr int SCRATCH = U1_BYTES + BL_BYTES + F_BYTES + 2 * M_BYTES + 32 * 4 * 4;
     static_assert(MR == 4, "thread mappings below: 6 x 9 gray rows, 7 x 6 mask rows");
     static_assert(BH * HP * 2 <= U1_BYTES && (U1_BYTES % 16) == 0 && (BL_BYTES % 16) == 0 && (F_BYTES % 16) == 0, "layout");
@@ -859,24 +859,36 @@ __device__ __forceinline__ void morph_generic_mask(const BatchView &b, uint8_t *
 // default border ("outside the image never wins") is applied when a word is READ: bits outside the image count as 1 for
 // erode and 0 for dilate.  Words and rows beyond the staged region read as the identity as well (what they would really
 // hold is unknown, but nothing that far away can reach the tile).
-template <bool DILATE, int MH>
-__device__ __forceinline__ uint32_t morph_rect_word(const uint32_t (*src)[6], int m, int k, int r, int m_lo, int m_hi,
-                                                    const uint32_t (&inm)[3]) {
+template <bool DILATE, int R>
+__device__ __forceinline__ uint32_t morph_rect_word(const uint32_t (*src)[8], int m, int k, int m_lo, int m_hi, const uint32_t (&inm)[3]) {
+    // src rows are padded: word k of the region sits at column k + 1, columns 0 and 7 are never written and masked out by
+    // inm[0] / inm[2] = 0 for k = 0 / k = 5
     uint32_t acc = DILATE ? 0u : 0xffffffffu;
-    const int a_lo = max(m - r, m_lo), a_hi = min(m + r, m_hi);
+    const int a_lo = max(m - R, m_lo), a_hi = min(m + R, m_hi);
     for (int mm = a_lo; mm <= a_hi; mm++) {
-        uint32_t L = k > 0 ? src[mm][k - 1] : 0u, M = src[mm][k], R = k < 5 ? src[mm][k + 1] : 0u;
+        uint32_t L = src[mm][k], M = src[mm][k + 1], Rw = src[mm][k + 2];
         L = DILATE ? (L & inm[0]) : (L | ~inm[0]);
         M = DILATE ? (M & inm[1]) : (M | ~inm[1]);
-        R = DILATE ? (R & inm[2]) : (R | ~inm[2]);
+        Rw = DILATE ? (Rw & inm[2]) : (Rw | ~inm[2]);
         uint32_t h = M;
-        for (int dx = 1; dx <= r; dx++) {
-            const uint32_t tr = __funnelshift_r(M, R, dx), tl = __funnelshift_l(L, M, dx);
+#pragma unroll
+        for (int dx = 1; dx <= R; dx++) {
+            const uint32_t tr = __funnelshift_r(M, Rw, dx), tl = __funnelshift_l(L, M, dx);
             h = DILATE ? (h | tr | tl) : (h & tr & tl);
         }
         acc = DILATE ? (acc | h) : (acc & h);
     }
     return acc;
+}
+template <bool DILATE>
+__device__ __forceinline__ uint32_t morph_rect_word_r(const uint32_t (*src)[8], int m, int k, int r, int m_lo, int m_hi,
+                                                      const uint32_t (&inm)[3]) {
+    switch (r) {  // block-uniform
+        case 1: return morph_rect_word<DILATE, 1>(src, m, k, m_lo, m_hi, inm);
+        case 2: return morph_rect_word<DILATE, 2>(src, m, k, m_lo, m_hi, inm);
+        case 3: return morph_rect_word<DILATE, 3>(src, m, k, m_lo, m_hi, inm);
+        default: return morph_rect_word<DILATE, 4>(src, m, k, m_lo, m_hi, inm);
+    }
 }
 
 // Everything after the flat decision for the morphology variant: pre-morphology mask of the tile + ring, bit-packing,
@@ -888,8 +900,8 @@ __device__ __forceinline__ void morph_tile_compute_and_store(const BatchView &b,
                                                              bool box_inside, int tid, uint64_t *empty_bar) {
     using T = MTile<MR>;
     uint8_t *u1_raw = scratch, *bl_raw = u1_raw + T::U1_BYTES, *f_raw = bl_raw + T::BL_BYTES;
-    uint32_t(*s_ma)[6] = reinterpret_cast<uint32_t(*)[6]>(f_raw + T::F_BYTES);
-    uint32_t(*s_mb)[6] = reinterpret_cast<uint32_t(*)[6]>(f_raw + T::F_BYTES + T::M_BYTES);
+    uint32_t(*s_ma)[8] = reinterpret_cast<uint32_t(*)[8]>(f_raw + T::F_BYTES);
+    uint32_t(*s_mb)[8] = reinterpret_cast<uint32_t(*)[8]>(f_raw + T::F_BYTES + T::M_BYTES);
     uint32_t(*s_w)[4] = reinterpret_cast<uint32_t(*)[4]>(f_raw + T::F_BYTES + 2 * T::M_BYTES);
     uint8_t(*s_f2)[T::FP] = reinterpret_cast<uint8_t(*)[T::FP]>(f_raw);
     const int H = b.h, W = b.w, WW = b.ww;
@@ -905,62 +917,62 @@ __device__ __forceinline__ void morph_tile_compute_and_store(const BatchView &b,
         // bit-packing: thread = (mask row m, word k); word k holds image columns x0 + 32 (k - 1) .. + 31 = s_f2 columns
         // 32k - 24 .. 32k + 7, of which 0 .. 143 exist.  Bits outside the image are cleared.
         const int m = tid / 6, k = tid - 6 * m;
-        uint32_t word = 0, in_m = 0;
-        if (tid < T::MH * 6) {
-            const int gy = y0 - MR + m;
-            const int gx0 = x0 + 32 * (k - 1);  // image column of bit 0
-            if (gy >= 0 && gy < H && gx0 + 31 >= 0 && gx0 < W) {
-                in_m = 0xffffffffu;
-                if (gx0 < 0) in_m = 0u;  // (tiles start at multiples of 128: a word is inside or outside as a whole on the left)
-                if (gx0 + 32 > W) in_m &= (1u << (W - gx0)) - 1u;
-            }
+        const bool mine = tid < T::MH * 6;
+        // in-image masks of the word and of its two neighbours, rows of the region inside the image: all ones / the whole
+        // region when the box lies inside the image
+        uint32_t inm[3] = {k > 0 ? 0xffffffffu : 0u, 0xffffffffu, k < 5 ? 0xffffffffu : 0u};
+        int m_lo = 0, m_hi = T::MH - 1;
+        if (!box_inside) {
+            auto col_mask = [&](int kk) -> uint32_t {
+                const int gx0 = x0 + 32 * (kk - 1);  // image column of bit 0 (tiles start at multiples of 128: a word lies
+                if (kk < 0 || kk > 5 || gx0 < 0 || gx0 >= W) return 0u;  // inside or outside as a whole on the left)
+                return gx0 + 32 > W ? (1u << (W - gx0)) - 1u : 0xffffffffu;
+            };
+            inm[0] = col_mask(k - 1), inm[1] = col_mask(k), inm[2] = col_mask(k + 1);
+            m_lo = max(0, MR - y0), m_hi = min(T::MH - 1, MR + (H - 1 - y0));
+        }
+        const bool row_in = m >= m_lo && m <= m_hi;
+        uint32_t word = 0;
+        if (mine) {
+            if (k >= 1 && k <= 4) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f2[m][32 * k - 24]);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int j = 32 * k - 24 + 4 * i;
-                if (j >= 0 && j <= T::FP - 4) {
-                    const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_f2[m][j]);
-                    word |= (((v & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
-                }
+                for (int i = 0; i < 8; i++) word |= (((src[i] & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
+            } else if (k == 0) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f2[m][0]);
+                word = ((((src[0] & 0x01010101u) * 0x10204080u) >> 28) << 24) | ((((src[1] & 0x01010101u) * 0x10204080u) >> 28) << 28);
+            } else {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_f2[m][136]);
+                word = (((src[0] & 0x01010101u) * 0x10204080u) >> 28) | ((((src[1] & 0x01010101u) * 0x10204080u) >> 28) << 4);
             }
-            word &= in_m;
-            s_ma[m][k] = word;
+            if (!row_in) word = 0;
+            word &= inm[1];
+            s_ma[m][k + 1] = word;
         }
         any = tile_sync_or<true>(word);  // also: s_ma complete
         if (any) {
-            // in-image masks of the three words a thread reads, rows of the region that lie inside the image
-            uint32_t inm[3] = {0u, in_m, 0u};
-            const int m_lo = max(0, MR - y0), m_hi = min(T::MH - 1, MR + (H - 1 - y0));
-            if (tid < T::MH * 6) {
-                auto col_mask = [&](int kk) -> uint32_t {
-                    const int gx0 = x0 + 32 * (kk - 1);
-                    if (kk < 0 || kk > 5 || gx0 < 0 || gx0 >= W) return 0u;
-                    return gx0 + 32 > W ? (1u << (W - gx0)) - 1u : 0xffffffffu;
-                };
-                inm[0] = col_mask(k - 1), inm[1] = col_mask(k), inm[2] = col_mask(k + 1);
-            }
             const int ro = p.morph_open_k > 0 ? (p.morph_open_k - 1) / 2 : 0, rc = p.morph_close_k > 0 ? (p.morph_close_k - 1) / 2 : 0;
-            const uint32_t(*src)[6] = s_ma;
-            uint32_t(*dst)[6] = s_mb;
-            const bool row_in = m >= m_lo && m <= m_hi;
+            const uint32_t(*src)[8] = s_ma;
+            uint32_t(*dst)[8] = s_mb;
             auto flip = [&]() {
                 tile_sync<true>();
-                const uint32_t(*t)[6] = dst;
-                dst = const_cast<uint32_t(*)[6]>(src);
+                const uint32_t(*t)[8] = dst;
+                dst = const_cast<uint32_t(*)[8]>(src);
                 src = t;
             };
             if (ro > 0) {
-                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<false, T::MH>(src, m, k, ro, m_lo, m_hi, inm) & inm[1]) : 0u;
+                if (mine) dst[m][k + 1] = row_in ? (morph_rect_word_r<false>(src, m, k, ro, m_lo, m_hi, inm) & inm[1]) : 0u;
                 flip();
             }
             if (ro + rc > 0) {
-                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<true, T::MH>(src, m, k, ro + rc, m_lo, m_hi, inm) & inm[1]) : 0u;
+                if (mine) dst[m][k + 1] = row_in ? (morph_rect_word_r<true>(src, m, k, ro + rc, m_lo, m_hi, inm) & inm[1]) : 0u;
                 flip();
             }
             if (rc > 0) {
-                if (tid < T::MH * 6) dst[m][k] = row_in ? (morph_rect_word<false, T::MH>(src, m, k, rc, m_lo, m_hi, inm) & inm[1]) : 0u;
+                if (mine) dst[m][k + 1] = row_in ? (morph_rect_word_r<false>(src, m, k, rc, m_lo, m_hi, inm) & inm[1]) : 0u;
                 flip();
             }
-            if (tid < 128) s_w[tid >> 2][tid & 3] = src[MR + (tid >> 2)][1 + (tid & 3)];
+            if (tid < 128) s_w[tid >> 2][tid & 3] = src[MR + (tid >> 2)][2 + (tid & 3)];
             tile_sync<true>();
         }
     }
@@ -990,17 +1002,17 @@ __device__ __forceinline__ void morph_tile_compute_and_store(const BatchView &b,
 // and store tile k; no thread ever issues a global load for pixels.
 // ---------------------------------------------------------------------------------------------------------------------
 
-template <int TW, int TH, int RB, int MR = 0>
+template <int TW, int TH, int RB, int MR = 0, int NS = kTmaStages>
 struct TmaSmem {
     using T = Tile<TW, TH, RB, 16>;  // 16-column halo: TMA boxes must start on a 16-byte boundary
     static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
-    static constexpr int BYTES = kTmaStages * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
+    static constexpr int BYTES = NS * STAGE + TH * TW + T::U1_BYTES + T::BL_BYTES;
 };
-template <int TW, int TH>
-struct TmaSmem<TW, TH, 2, 4> {  // box blur + 3x3 / 5x5 open + close folded in
+template <int TW, int TH, int NS>
+struct TmaSmem<TW, TH, 2, 4, NS> {  // box blur + 3x3 / 5x5 open + close folded in
     using T = MTile<4>;
     static constexpr int STAGE = (T::G_BYTES + 127) & ~127;
-    static constexpr int BYTES = kTmaStages * STAGE + T::SCRATCH;
+    static constexpr int BYTES = NS * STAGE + T::SCRATCH;
 };
 
 
@@ -1009,16 +1021,16 @@ struct TmaSmem<TW, TH, 2, 4> {  // box blur + 3x3 / 5x5 open + close folded in
 // refill between two tiles: the TMA issue sits behind that thread's own outstanding global stores, and every barrier of
 // the next tile waited for it (0.4-0.7 us per tile of 1.3-5 us).  Stage hand-over: full[st] (TMA transaction barrier,
 // producer -> consumers) and empty[st] (one consumer arrival after the last read of the stage, consumers -> producer).
-template <int TW, int TH, int RB, int MR = 0>
+template <int TW, int TH, int RB, int MR = 0, int NS = kTmaStages>
 __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
     k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ BatchView b,
                      const __grid_constant__ PreprocessParams p, uint32_t *bits_out, unsigned int *sched) {
-    using T = typename TmaSmem<TW, TH, RB, MR>::T;
-    constexpr int STAGE = TmaSmem<TW, TH, RB, MR>::STAGE;
+    using T = typename TmaSmem<TW, TH, RB, MR, NS>::T;
+    constexpr int STAGE = TmaSmem<TW, TH, RB, MR, NS>::STAGE;
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t full[kTmaStages], empty[kTmaStages];
-    __shared__ int4 s_tile[kTmaStages];  // {tile number, frame, tile x, tile y}, decoded once by the producer
-    uint8_t *f_raw = sm + kTmaStages * STAGE, *u1_raw = f_raw + TH * TW, *bl_raw = u1_raw + T::U1_BYTES;
+    __shared__ __align__(8) uint64_t full[NS], empty[NS];
+    __shared__ int4 s_tile[NS];  // {tile number, frame, tile x, tile y}, decoded once by the producer
+    uint8_t *f_raw = sm + NS * STAGE, *u1_raw = f_raw + TH * TW, *bl_raw = u1_raw + T::U1_BYTES;
     (void)u1_raw, (void)bl_raw;
 
     const int tid = threadIdx.x;
@@ -1045,7 +1057,7 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
             __threadfence();
         }
 #pragma unroll
-        for (int k = 0; k < kTmaStages; k++) {
+        for (int k = 0; k < NS; k++) {
             mbar_init(&full[k], 1);
             mbar_init(&empty[k], 1);
         }
@@ -1057,11 +1069,11 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
         // ---- producer warp ---------------------------------------------------------------------------------------------
         if (tid != kK1Consumers) return;
         // Tiles claimed ahead are tiles no other CTA can take.  A non-flat tile costs four times a flat one, so with every
-        // CTA holding kTmaStages claims (a third of the batch over the whole grid) the CTAs used to finish up to 17 us
+        // CTA holding NS claims (a third of the batch over the whole grid) the CTAs used to finish up to 17 us
         // apart.  The producer therefore runs `look` tiles ahead of the consumers -- p.lookahead in the steady state,
         // p.tail_lookahead once the tile numbers handed out are within p.tail_tiles of the end -- and claims a tile only
         // when it is about to issue its load.  Tile it may be issued once tile it - look has been released; the stage's
-        // own barrier (tile it - kTmaStages) is implied because the consumers release in order.
+        // own barrier (tile it - NS) is implied because the consumers release in order.
         // p.claim_ahead (off): request the next tile number one tile early, so that the round trip of the atomic overlaps
         // the wait below.  Measured: the TMA wait per tile drops from 0.71 to 0.52 us, but one more tile per CTA is spoken
         // for and the step gets 0.9 us longer (49.7 -> 50.6 us): balance is worth more than the hidden latency.
@@ -1070,9 +1082,9 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
         int pending = 0;
         if (p.claim_ahead) pending = p.static_sched ? (int)blockIdx.x : (int)atomicAdd(sched, 1u);
         for (int it = 0;; it++) {
-            const int st = it % kTmaStages;
+            const int st = it % NS;
             if (prev_t >= tail_from) look = p.tail_lookahead;
-            if (it >= look) mbar_wait(&empty[(it - look) % kTmaStages], (uint32_t)((it - look) / kTmaStages) & 1u, (uint32_t)p.wait_hint_ns);
+            if (it >= look) mbar_wait(&empty[(it - look) % NS], (uint32_t)((it - look) / NS) & 1u, (uint32_t)p.wait_hint_ns);
             int t;
             if (p.claim_ahead) {
                 t = pending;
@@ -1130,6 +1142,8 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
     const uint32_t ft1 = (uint32_t)((32 + (tid >> 3)) * T::GW + 16 + (tid & 7) * 16);  // tid < 112
     const uint32_t fte = (uint32_t)((((tid - 128) >> 1)) * T::GW + (((tid - 128) & 1) ? 144 : 8));  // 128 <= tid < 220
     const uint32_t ftref = (uint32_t)((T::HALO + TH / 2) * T::GW + T::HX + TW / 2);
+    const int mj0 = tid % 10, mj1 = (tid + 256) % 10, mj2 = (tid + 512) % 10;  // morphology variant: item column of the thread's items
+    (void)mj0, (void)mj1, (void)mj2;
     // zero stores of a flat tile that lies entirely inside the image (element offsets from the tile's first pixel / word)
     const uint32_t so_lab = (uint32_t)((tid >> 5) * W + 4 * (tid & 31)), so_lab_step = (uint32_t)(8 * W);
     const uint32_t so_mask = (uint32_t)((tid >> 3) * W + 16 * (tid & 7));
@@ -1140,10 +1154,10 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
         acc |= d | ((d & 0x7f7f7f7fu) + kq);
     };
     for (int it = 0;; it++) {
-        const int st = it % kTmaStages;
+        const int st = it % NS;
         unsigned long long t_a = 0, t_b = 0;
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
-        mbar_wait(&full[st], (uint32_t)(it / kTmaStages) & 1u, (uint32_t)p.wait_hint_ns);
+        mbar_wait(&full[st], (uint32_t)(it / NS) & 1u, (uint32_t)p.wait_hint_ns);
         if (b.phase_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
         const int4 cur = s_tile[st];
         if (cur.x >= total) break;
@@ -1158,13 +1172,29 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
             // morphology variant: every 16-byte item of the box that lies inside the image (the image is 16-px aligned, so an
             // item is inside or outside as a whole).  The mask of the tile + MR ring depends on columns [5, 155) of the box:
             // the outer four columns on either side are ignored.
-            if (try_flat) {
+            if (try_flat && box_inside) {
+                // the box is one contiguous run of GH * 10 sixteen-byte items: items tid, tid + 256, tid + 512; which of them
+                // is a row's first / last item (outer four columns ignored) is known per thread (mj0..2, hoisted)
+                constexpr int NI = T::GH * (T::GW / 16);
+                static_assert(NI > 512 && NI <= 768, "three items per thread");
+                const uint32_t ref4 = 0x01010101u * cur_stage[ftref];
+                uint4 v0 = *reinterpret_cast<const uint4 *>(cur_stage + 16 * tid);
+                uint4 v1 = *reinterpret_cast<const uint4 *>(cur_stage + 16 * (tid + 256));
+                uint4 v2 = make_uint4(ref4, ref4, ref4, ref4);
+                if (tid + 512 < NI) v2 = *reinterpret_cast<const uint4 *>(cur_stage + 16 * (tid + 512));
+                if (mj0 == 0) v0.x = ref4;
+                if (mj0 == 9) v0.w = ref4;
+                if (mj1 == 0) v1.x = ref4;
+                if (mj1 == 9) v1.w = ref4;
+                if (mj2 == 0) v2.x = ref4;
+                if (mj2 == 9) v2.w = ref4;
+                absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
+                absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
+                absd(v2.x, ref4, acc), absd(v2.y, ref4, acc), absd(v2.z, ref4, acc), absd(v2.w, ref4, acc);
+            } else if (try_flat) {
                 constexpr int IPR = T::GW / 16;
-                int r_lo = 0, r_hi = T::GH, j_lo = 0, j_hi = IPR;
-                if (!box_inside) {
-                    r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
-                    j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
-                }
+                const int r_lo = max(0, T::HALO - y0), r_hi = min(T::GH, H - y0 + T::HALO);
+                const int j_lo = x0 == 0 ? 1 : 0, j_hi = min(IPR, (W - x0 + T::HX) >> 4);
                 const uint32_t ref4 = 0x01010101u * cur_stage[min(T::HALO + TH / 2, r_hi - 1) * T::GW + min(T::HX + TW / 2, 16 * j_hi - 1)];
                 for (int idx = tid; idx < T::GH * IPR; idx += kK1Consumers) {
                     const int r = idx / IPR, j = idx - r * IPR;
@@ -1275,7 +1305,7 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
             if (b.tile_occ && tid == 2) reinterpret_cast<uint32_t *>(b.tile_occ)[cur.x] = 0u;  // (the tile number is its index)
             if (!p.sparse_aux && tid < TH * (TW / 32)) bits_out[row0 * b.ww + (x0 >> 5) + so_bits] = 0u;
         } else if constexpr (MR > 0) {
-            morph_tile_compute_and_store<MR>(b, p, bits_out, cur_stage, sm + kTmaStages * STAGE, f, tx, ty, flat, box_inside, tid,
+            morph_tile_compute_and_store<MR>(b, p, bits_out, cur_stage, sm + NS * STAGE, f, tx, ty, flat, box_inside, tid,
                                              &empty[st]);
         } else {
             tile_compute_and_store<TW, TH, RB, 16, true>(b, p, bits_out, cur_stage, f_raw, u1_raw, bl_raw, f, tx, x0, y0, flat,
@@ -1383,6 +1413,18 @@ cudaError_t configure_preprocess_tma() {
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TmaSmem<128, 32, 2, 4, 3>::BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TmaSmem<128, 32, 2, 0, 3>::BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 0, 3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     // ask for the largest shared-memory carve-out: residency of these kernels is limited by shared memory, not by L1
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -1444,7 +1486,11 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kK1Threads);
-    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES : (morph ? TmaSmem<128, 32, 2, 4>::BYTES : TmaSmem<128, 32, 2>::BYTES);
+    // three stages when the kernel runs at three CTAs per SM next to the per-frame CCL kernel (p.stages, set by hv_api.cu)
+    const bool s3 = !gauss && p.stages == 3;
+    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES
+                                 : (morph ? (s3 ? TmaSmem<128, 32, 2, 4, 3>::BYTES : TmaSmem<128, 32, 2, 4>::BYTES)
+                                          : (s3 ? TmaSmem<128, 32, 2, 0, 3>::BYTES : TmaSmem<128, 32, 2>::BYTES));
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1454,14 +1500,16 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     *used = true;
     PreprocessParams q = p;
     const Tunables &tun = tunables();
-    q.lookahead = std::min(tun.k1_lookahead, kTmaStages);
+    q.lookahead = std::min(s3 ? std::max(tun.k1_lookahead, 3) : tun.k1_lookahead, s3 ? 3 : kTmaStages);
     q.tail_lookahead = std::min(tun.k1_tail_lookahead, q.lookahead);
     q.tail_tiles = tun.k1_tail_rounds * grid;
     q.prefetch_tiles = tun.k1_prefetch;
     q.claim_ahead = tun.k1_claim_ahead;
     q.wait_hint_ns = tun.k1_wait_hint_ns;
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
+    if (morph && s3) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 4, 3>, tmap, b, q, bits_out, sched);
     if (morph) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 4>, tmap, b, q, bits_out, sched);
+    if (s3) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 0, 3>, tmap, b, q, bits_out, sched);
     return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2>, tmap, b, q, bits_out, sched);
 }
 

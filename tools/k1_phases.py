@@ -8,11 +8,13 @@ st = torch.cuda.current_stream().cuda_stream
 grid = 148 * int(os.environ.get('HV_K1_CTAS_PER_SM', '5'))
 det = hc.Detector(0, profile=True, phase_timing=True)
 det.set_stream(st)
-for it in range(4): det.detect_device(pool[it % 8].data_ptr(), n, h, w)
+mk = int(os.environ.get('SWEEP_MORPH', '0'))
+params = hc.make_params(morph_open_k=mk, morph_close_k=mk) if mk else None
+for it in range(4): det.detect_device(pool[it % 8].data_ptr(), n, h, w, 1, params)
 det.profile()
 res = []
 for it in range(10):
-    det.detect_device(pool[it % 8].data_ptr(), n, h, w)
+    det.detect_device(pool[it % 8].data_ptr(), n, h, w, 1, params)
     k1 = det.phase_times()[200:206]; q = det.phase_times()[248:256]
     res.append((k1, q))
 pr = det.profile()
