@@ -277,7 +277,6 @@ struct hv_ctx {
     // CCL path selection: sparse masks go through the fused per-frame kernel; if a batch needed the global-memory
     // fallback the next batches use the global path directly and the fused kernel is re-tried every 8th batch
     bool dense_hint = false;
-    uint32_t dense_batches = 0;
     int sync_cur = 0;  // which of the synchronous slots holds the most recent batch
     // last batch enqueued through the device-resident path (for the programmatic-dependent-launch overlap decision)
     cudaStream_t last_stream = nullptr;
@@ -627,10 +626,10 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     const bool morph = morph_req && !k1_morph;
     // CCL path of this batch (decided before K1 runs: the fused kernel lets K1 skip the all-zero bit-mask words)
     bool fused = !(ctx->cfg.flags & HV_FLAG_GLOBAL_CCL) && ccl_frame_supported(b);
-    if (fused && ctx->dense_hint) {
-        ctx->dense_batches++;
-        if (ctx->dense_batches % 8 != 0) fused = false;  // stay on the global path, re-try the fused kernel now and then
-    }
+    // After a batch that needed the global-memory kernels the context stays on them until the results of a later batch
+    // say that its frames would fit the per-frame kernel again (retire_slot: few components, little foreground).  A probe
+    // that fails costs the whole batch twice, so there is no blind re-try.
+    if (fused && ctx->dense_hint) fused = false;
     // Small build of the per-frame kernel (co-resident with K1 CTAs): box-blur path, with or without the fused morphology.  After a frame did
     // not fit, the big build takes over until it reports (frame_flags bit 1) that a whole batch would have fitted again.
     const bool morph_fused_plan = morph && morph_expand_supported(pr.morph_open_k, pr.morph_close_k) && !tun.no_fused_morph;
@@ -880,7 +879,6 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
     if (!s.used_small) {  // (after the small build the big one is tried before the global path becomes the default)
         ctx->dense_hint = true;
-        ctx->dense_batches = 0;
     }
     s.used_small = false;
     return HV_OK;
@@ -889,10 +887,24 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
 // A device-resident batch whose results nobody has looked at yet: wait for its read-back, finish the frames the
 // per-frame kernel flagged (global path), update the CCL path selection.  Runs before the slot is reused, before a
 // batch that writes the same caller-owned output planes is enqueued, and when the batch is fetched.
+// CCL path selection from the results of a batch that went through the global-memory kernels: back to the per-frame
+// kernel once every frame of a batch is sparse enough for its big build with a wide margin (components and foreground
+// pixels; the kernel's real limits are non-zero words and word-runs, which the per-frame records do not carry).
+void update_dense_hint(hv_ctx *ctx, const Slot &s) {
+    if (!ctx->dense_hint || s.used_fused || !s.has_batch) return;
+    bool sparse = true;
+    for (int f = 0; f < s.view.n; f++) {
+        const hv_frame_result &r = s.h_results.p[f];
+        sparse &= r.status == HV_OK && r.n_components <= 1024u && r.fg_pixels <= 16384u;
+    }
+    if (sparse) ctx->dense_hint = false;
+}
+
 hv_status retire_slot(hv_ctx *ctx, Slot &s) {
     if (!s.pending) return HV_OK;
     HV_TRY_CUDA(ctx, cudaEventSynchronize(s.copied));
     s.pending = false;
+    update_dense_hint(ctx, s);
     return resolve_fallback(ctx, s, s.batch_stream);
 }
 
@@ -1344,6 +1356,7 @@ hv_status hv_detect_batch(hv_ctx *ctx, const uint8_t *frames, int32_t n, int32_t
     rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    update_dense_hint(ctx, s);
     rs = resolve_fallback(ctx, s, st);
     if (rs != HV_OK) return rs;
     hv_status rc = unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);
@@ -1396,6 +1409,7 @@ hv_status hv_wait(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defe
         if (s.ticket == ticket && ticket > 0) {
             HV_TRY_CUDA(ctx, cudaEventSynchronize(s.done));
             s.ticket = -1;
+            update_dense_hint(ctx, s);
             hv_status rf = resolve_fallback(ctx, s, s.stream);
             if (rf != HV_OK) return rf;
             return unpack_results(ctx, s, results, defects, defects_cap, n_defects_total);

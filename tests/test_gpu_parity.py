@@ -876,3 +876,34 @@ def test_enqueue_refuses_graph_capture():
     finally:
         det.set_stream(None)
         det.close()
+
+
+def test_ccl_path_selection_follows_the_frames(oracle):
+    """Dense frames move the context to the global-memory CCL kernels (after one batch that the per-frame kernel flags);
+    it stays there -- no blind re-tries, which would cost such batches twice -- until the results of a batch show sparse
+    frames again, and then returns to the per-frame kernel.  Results equal the oracle's throughout."""
+    import heimdall_core as hc
+    dense = np.stack([synth.high_contamination_frame(768, 1024, s) for s in (1, 2)])
+    sparse = synth.bottle_batch(2, 768, 1024, start_index=60, contaminants=1)
+    det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=30000, profile=True)
+    try:
+        def run(batch):
+            det.profile()
+            res = det.detect_batch(batch[..., None], debug=["labels"])
+            for f in range(len(batch)):
+                ref = oracle.detect_contamination(batch[f][:, :, None])
+                assert np.array_equal(res.debug["labels"][f], ref.labels)
+                assert [((int(d["y"]), int(d["x"])), float(d["size"])) for d in res.defects_of(f)] == \
+                    [(d["position"], d["size"]) for d in ref.defects]
+            p = det.profile()
+            return p["ccl_frame_fused"]["launches"], p["ccl_merge"]["launches"]
+        assert run(sparse) == (1, 0)
+        f1 = run(dense)
+        assert f1[1] == 1                       # flagged (small and/or big build) and finished by the global kernels
+        for _ in range(9):
+            assert run(dense) in ((1, 1), (0, 1))
+        assert run(dense) == (0, 1)             # settled on the global path: no probing of the per-frame kernel
+        assert run(sparse) == (0, 1)            # still there for one batch: its results say "sparse" ...
+        assert run(sparse) == (1, 0)            # ... and the per-frame kernel is back
+    finally:
+        det.close()
