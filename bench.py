@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import sys
@@ -289,19 +290,48 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     stats_buf = torch.zeros(hv_dist.STATS_WORDS, dtype=torch.int64, device=dev)
     side = torch.cuda.Stream(device=dev)
 
+    # The snapshot + all-reduce pair costs about 50 us of host time (a copy and an NCCL call), which a 40 us step cannot hide
+    # when the thread that issues it is the one that feeds the pipeline: a helper thread issues it instead (torch releases
+    # the GIL inside both calls), on a side stream.  The launching thread only posts a request.
+    import queue
+    stats_q = queue.Queue()
+
+    def stats_worker():
+        torch.cuda.set_device(local_rank)
+        while True:
+            item = stats_q.get()
+            if item is None:
+                return
+            with torch.cuda.stream(side):
+                stats_buf.copy_(stats_view)
+                dist.all_reduce(stats_buf)
+            stats_q.task_done()
+
+    stats_thread = None
+    if world > 1:
+        with torch.cuda.stream(side):
+            stats_buf.copy_(stats_view)
+            dist.all_reduce(stats_buf)          # communicator set-up outside any timed region
+        torch.cuda.synchronize()
+        stats_thread = threading.Thread(target=stats_worker, daemon=True)
+        stats_thread.start()
+
     def reduce_stats(final=False):
         """Snapshot of the running line counters -> all-reduce, entirely on the side stream.  The counters are 64-bit
         atomics that only grow, so a report may be a few microseconds stale but every counter in it is consistent; the
         launching stream is never touched (an event between two kernels there would serialise K1 behind the per-frame
-        CCL kernel and undo the programmatic-dependent-launch overlap).  final=True orders the snapshot after everything
-        enqueued so far: the totals reported at the end."""
+        CCL kernel and undo the programmatic-dependent-launch overlap).  final=True waits for the requests posted so far
+        and orders the snapshot after everything enqueued on the launching stream: the totals reported at the end."""
         if world == 1:
             return
         if final:
+            stats_q.join()
             side.wait_stream(stream)
-        with torch.cuda.stream(side):
-            stats_buf.copy_(stats_view)
-            dist.all_reduce(stats_buf)
+            with torch.cuda.stream(side):
+                stats_buf.copy_(stats_view)
+                dist.all_reduce(stats_buf)
+            return
+        stats_q.put(1)
 
     # Streaming loop: one step = enqueue one batch + collect the results of the batch depth-1 steps back, which the copy
     # engine has meanwhile delivered to pinned host memory (hv_fetch_ticket).  EVERY batch's per-frame records and defect
@@ -314,16 +344,31 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             self.res = [np.zeros(nf, RESULT_DTYPE) for _ in range(depth)]
             self.dfx = [np.zeros(nf * det.defect_cap, DEFECT_DTYPE) for _ in range(depth)]
             self.i = 0
-            self.frames = self.rejected = self.defects = 0
+            self.cstep = 0
+            self.batches = 0
+            # per-frame records of everything collected so far, summed field by field (one vectorised add per batch: the
+            # launching thread has 40 us per step for two library calls and this)
+            self.views = [r.view(np.uint32).reshape(nf, 6) for r in self.res]
+            self.acc = np.zeros((nf, 6), np.uint64)
             self.last = None
 
+        @property
+        def frames(self):
+            return self.batches * nf
+
+        @property
+        def rejected(self):
+            return int(self.acc[:, 3].sum())
+
+        @property
+        def defects(self):
+            return int(self.acc[:, 1].sum())
+
         def collect(self, slot):
-            r = det.fetch_into(self.tickets[slot], self.res[slot], self.dfx[slot])
-            self.frames += nf
-            self.rejected += int(r.frames["rejected"].sum())
-            self.defects += int(r.frames["n_defects"].sum())
+            self.last = det.fetch_into(self.tickets[slot], self.res[slot], self.dfx[slot])
+            np.add(self.acc, self.views[slot], out=self.acc)
+            self.batches += 1
             self.tickets[slot] = 0
-            self.last = r
 
         def step(self, collective=True):
             i = self.i
@@ -333,8 +378,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             nxt = (i + 1) % depth
             if self.tickets[nxt]:
                 self.collect(nxt)
-            if collective and args.stats_every > 0 and (i + 1) % args.stats_every == 0:
-                reduce_stats()
+            if collective and args.stats_every > 0:
+                self.cstep += 1     # counted from the start of the timed region: every rank issues the same number
+                if self.cstep % args.stats_every == 0:
+                    reduce_stats()
             self.i = i + 1
 
         def drain(self):
@@ -351,7 +398,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             dist.barrier()
         torch.cuda.synchronize()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(repeats + 1)]
+        S.cstep = 0
         l0 = det.launch_count()
+        gc.collect()
+        gc.disable()  # a collection pause of the launching thread would show up as a pipeline bubble
         t0 = time.perf_counter()
         evs[0].record(stream)
         for r in range(repeats):
@@ -359,8 +409,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                 S.step(collective)
             evs[r + 1].record(stream)
         S.drain()
+        if world > 1:
+            stats_q.join()   # every rank has issued the same number of all-reduces before anybody moves on
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        gc.enable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -377,7 +430,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     S.drain()
     torch.cuda.synchronize()
     for _ in range(W):
-        S.step()
+        S.step(collective=False)
     S.drain()
 
     # ---- timed region -----------------------------------------------------------------------------------------------------
@@ -422,11 +475,14 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     #      next K1 wait for everything before it: one pipeline drain + fill per window) ----------------------------------------
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    S.cstep = 0
     e0.record(stream)
     for _ in range(R * K):
         S.step()
     e1.record(stream)
     S.drain()
+    if world > 1:
+        stats_q.join()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / (R * K)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -520,6 +576,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     else:
         total_stats = {k: v for k, v in det.stats().items() if k != "area_hist"}
 
+    if world > 1:
+        stats_q.put(None)
+        stats_thread.join(timeout=10)
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
         det.close()
         if world > 1:
@@ -569,7 +630,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                      f"> 126 MB L2); each step also writes {5 * batch_bytes / 1e6:.0f} MB of mask+labels",
         "output_memory": out_mem,
         "parallelism": f"dp{world} (frames sharded, no data-path collective; 256 B all-reduce of the running line statistics "
-                       f"every {args.stats_every} steps = {args.stats_every * nf} frames per GPU, on a side stream)",
+                       f"every {args.stats_every} steps = {args.stats_every * nf} frames per GPU, issued by a helper thread on a side stream)",
         "timed": f"{R} windows of K = {K} steps back to back, a CUDA event on the launching stream at every window boundary; "
                  f"ms_per_step = median window / K (max over ranks of the per-rank medians).  One step = hv_enqueue_device "
                  f"of one batch + hv_fetch_ticket of the batch {depth - 1} steps back: the per-frame records and defect "
@@ -658,7 +719,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--no-compress", action="store_true", help="output planes in plain cudaMalloc memory")
-    ap.add_argument("--stats-every", type=int, default=8,
+    ap.add_argument("--stats-every", type=int, default=20,
                     help="all-reduce the running line statistics every this many steps (N > 1)")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -216,10 +216,17 @@ hv_status hv_frameset_push(hv_frameset *fs, const hv_camera_frame *fr, const hv_
         fs->st.duplicates++;
         return HV_OK;
     }
-    std::memcpy(s.slab + fs->frame_bytes * fr->camera, fr->data, fs->frame_bytes);
+    // zero-copy: a frame that already lies in page-locked memory is referenced where it is
+    bool referenced = false;
+    if (fs->ctx && (fs->cfg.flags & HV_FRAMESET_ZERO_COPY)) {
+        cudaPointerAttributes at{};
+        referenced = cudaPointerGetAttributes(&at, fr->data) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
+    if (!referenced) std::memcpy(s.slab + fs->frame_bytes * fr->camera, fr->data, fs->frame_bytes);
     s.have[fr->camera] = 1;
     s.meta[fr->camera] = *fr;
-    s.meta[fr->camera].data = s.slab + fs->frame_bytes * fr->camera;
+    if (!referenced) s.meta[fr->camera].data = s.slab + fs->frame_bytes * fr->camera;
     s.meta[fr->camera].size = fs->frame_bytes;
     s.meta[fr->camera].frame_id = id;
     s.t_min = std::min(s.t_min, fr->timestamp_ns);

@@ -31,6 +31,7 @@ HV_FLAG_PHASE_TIMING = 32
 
 HV_BLUR_BOX, HV_BLUR_GAUSSIAN, HV_BLUR_NONE = 0, 1, 2
 HV_ALLOC_COMPRESSIBLE = 1
+HV_FRAMESET_ZERO_COPY = 1
 HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION = 0, 1
 HV_STATS_AREA_BINS = 16
 HV_K_COUNT = 9
@@ -103,7 +104,7 @@ HV_SYNC_FREERUN, HV_SYNC_SOFTWARE, HV_SYNC_HARDWARE = 0, 1, 2
 
 class hv_frameset_config(C.Structure):
     _fields_ = [("n_cameras", C.c_int32), ("sets_per_batch", C.c_int32), ("sync_mode", C.c_int32),
-                ("max_pending_sets", C.c_int32)]
+                ("max_pending_sets", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class hv_frameset_stats(C.Structure):

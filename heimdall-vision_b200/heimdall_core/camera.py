@@ -101,13 +101,16 @@ class FrameSetBatcher:
     dry mode: the batching rules run, nothing is submitted (CPU tests)."""
 
     def __init__(self, detector, n_cameras: int, sets_per_batch: int = 1, sync_mode: SyncMode = SyncMode.Hardware,
-                 max_pending_sets: int = 0, params=None):
+                 max_pending_sets: int = 0, params=None, zero_copy: bool = False):
         import ctypes as C
         self._C = C
         self._det = detector
         self._params = params
         self.n_cameras, self.sets_per_batch = int(n_cameras), int(sets_per_batch)
-        cfg = A.hv_frameset_config(self.n_cameras, self.sets_per_batch, int(sync_mode), int(max_pending_sets))
+        # zero_copy: frames that already lie in page-locked memory (Detector.host_alloc) are referenced, not copied; the
+        # caller keeps them unchanged until wait() has returned for their batch
+        cfg = A.hv_frameset_config(self.n_cameras, self.sets_per_batch, int(sync_mode), int(max_pending_sets),
+                                   A.HV_FRAMESET_ZERO_COPY if zero_copy else 0, 0)
         h = C.c_void_p()
         st = A.lib.hv_frameset_create(detector._ctx if detector is not None else None, C.byref(cfg), C.byref(h))
         if st != A.HV_OK:

@@ -312,7 +312,14 @@ typedef struct {
     int32_t sets_per_batch;   /* complete sets per detector batch */
     int32_t sync_mode;        /* HV_SYNC_*: Freerun matches the k-th frame of every camera, the others match frame_id */
     int32_t max_pending_sets; /* incomplete sets kept while cameras are late; the oldest is dropped beyond (0 -> 8) */
+    int32_t flags;            /* HV_FRAMESET_* */
+    int32_t reserved;
 } hv_frameset_config;
+/* Frames whose data already lies in page-locked host memory (hv_host_alloc / cudaHostAlloc / cudaHostRegister) are
+ * referenced instead of copied into a slab: the caller keeps such a buffer valid and unchanged until hv_frameset_wait has
+ * returned for the batch the frame went into (or the batcher reports the frame's set as dropped).  Pageable frames are
+ * still copied.  Saves one pass over every frame on the host: 8 GB/s per thread for the copy against 55 GB/s of PCIe. */
+#define HV_FRAMESET_ZERO_COPY 1
 typedef struct {
     uint64_t frames_pushed;
     uint64_t sets_completed;
