@@ -308,7 +308,7 @@ struct hv_ctx {
     DevBuf<uint8_t> u_a, u_b, u_c;
     DevBuf<hv_center> u_centers;
     DevBuf<hv_contour> u_contours;
-    DevBuf<uint32_t> u_count;
+    DevBuf<uint32_t> u_count, u_owner;
     // buffers handed out by hv_device_alloc through the virtual-memory API (compressible memory)
     std::map<void *, VmmRec> vmm;
 };
@@ -1137,7 +1137,7 @@ void hv_destroy(hv_ctx *ctx) {
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->d_phase_ns) cudaFree(ctx->d_phase_ns);
     ctx->u_a.release(), ctx->u_b.release(), ctx->u_c.release();
-    ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release();
+    ctx->u_centers.release(), ctx->u_contours.release(), ctx->u_count.release(), ctx->u_owner.release();
     while (!ctx->vmm.empty()) hv_device_free(ctx, ctx->vmm.begin()->first);  // buffers the caller did not return
     delete ctx;
 }
@@ -1805,6 +1805,60 @@ hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w
     s.has_batch = false;
     if (n_contours) *n_contours = n_out;
     return rc;
+}
+
+// ---- result side (N4) ---------------------------------------------------------------------------------------------------
+hv_status hv_export_results(const hv_frame_result *results, int32_t n, double timestamp, double processing_time,
+                            uint64_t first_sequence, hv_inspection_record *records, hv_dashboard_stats *stats) {
+    if (!results || n < 0 || (!records && !stats)) return HV_ERR_INVALID_ARGUMENT;
+    for (int f = 0; f < n; f++) {
+        const hv_frame_result &r = results[f];
+        if (records) {
+            hv_inspection_record &q = records[f];
+            q.sequence = first_sequence + (uint64_t)f;
+            q.timestamp = timestamp;
+            q.processing_time = processing_time;
+            q.success = r.status == HV_OK ? 1u : 0u;
+            q.has_defects = r.n_defects > 0 ? 1u : 0u;  // base_inspector.py:40-42
+            q.defect_count = r.n_defects;
+            q.defects_offset = r.defects_offset;
+        }
+        if (stats) {  // dashboard.py:483-500, one image at a time, the reference's expression order
+            stats->total_images += 1;
+            stats->total_defects += r.n_defects;
+            if (stats->avg_processing_time_ms == 0)
+                stats->avg_processing_time_ms = processing_time * 1000;
+            else
+                stats->avg_processing_time_ms = 0.9 * stats->avg_processing_time_ms + 0.1 * processing_time * 1000;
+            if (stats->total_images > 0)
+                stats->defect_rate = (double)stats->total_defects / (double)stats->total_images * 100;
+        }
+    }
+    return HV_OK;
+}
+
+hv_status hv_draw_overlays(hv_ctx *ctx, uint8_t *img, int32_t h, int32_t w, const hv_overlay *items, int32_t n) {
+    if (!ctx || !img || h <= 0 || w <= 0 || n < 0 || (n > 0 && !items)) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    for (int i = 0; i < n; i++)
+        if (items[i].kind < HV_OVERLAY_CROSS || items[i].kind > HV_OVERLAY_MARKER) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "unknown overlay kind");
+    if (n == 0) return HV_OK;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    const size_t px = (size_t)h * w;
+    HV_TRY_CUDA(ctx, ctx->u_a.reserve(px * 3));
+    HV_TRY_CUDA(ctx, ctx->u_b.reserve(sizeof(hv_overlay) * (size_t)n));
+    if (px > ctx->u_owner.cap) {  // all zero between calls: the kernels release what they claim
+        HV_TRY_CUDA(ctx, ctx->u_owner.reserve(px));
+        HV_TRY_CUDA(ctx, cudaMemsetAsync(ctx->u_owner.p, 0, px * sizeof(uint32_t), st));
+    }
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->u_a.p, img, px * 3, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(ctx->u_b.p, items, sizeof(hv_overlay) * (size_t)n, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, launch_overlays(reinterpret_cast<const hv_overlay *>(ctx->u_b.p), n, h, w, ctx->u_a.p, ctx->u_owner.p, st));
+    ctx->launches += 3;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(img, ctx->u_a.p, px * 3, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    return HV_OK;
 }
 
 // ---- line statistics ----------------------------------------------------------------------------------------------

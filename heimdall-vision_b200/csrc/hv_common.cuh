@@ -197,6 +197,7 @@ cudaError_t launch_collect_centers(const BatchView &b, uint32_t min_area, hv_cen
 cudaError_t launch_bayer(const uint8_t *d_src, int n, int h, int w, int pattern, bool to_gray, uint8_t *d_dst,
                          cudaStream_t s);
 cudaError_t launch_yuyv(const uint8_t *d_src, int n, int h, int w, bool to_gray, uint8_t *d_dst, cudaStream_t s);
+cudaError_t launch_overlays(const hv_overlay *d_items, int n, int h, int w, uint8_t *d_img, unsigned int *d_owner, cudaStream_t s);
 cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
                                     uint32_t *d_count, int cap, cudaStream_t s);
 

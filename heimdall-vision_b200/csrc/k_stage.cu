@@ -541,6 +541,75 @@ __global__ void __launch_bounds__(256) k_crosses(const hv_center *centers, int n
     q[2] = 255;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// N4: overlays (crosses, boxes, markers) drawn in list order.  Three passes over the items' pixels: claim (the highest
+// item index that touches a pixel owns it -- what sequential drawing leaves behind), paint, release the claims.
+// ---------------------------------------------------------------------------------------------------------
+// footprint of cv2.circle(img, c, 10, color, 2) around its centre, offsets -11..11, bit dx + 11 of row dy + 11
+// (opencv-python 4.13; tests/test_result_side.py compares with committed cv2 output)
+__constant__ uint32_t kMarkerRows[23] = {0x7f00, 0x1ff80, 0x7fff0, 0xf81f8, 0x1f007c, 0x1e003c, 0x3c001e, 0x38000e,
+                                         0x78000f, 0x700007, 0x700007, 0x700007, 0x700007, 0x700007, 0x700007, 0x38000e,
+                                         0x3c001e, 0x1e003c, 0x1f007c, 0xf81f8, 0x7fff0, 0x1ff80, 0x7f00};
+
+// pixel k of an item, or false when k is beyond the item / not part of it
+__device__ __forceinline__ bool overlay_pixel(const hv_overlay &it, int k, int *py, int *px) {
+    if (it.kind == HV_OVERLAY_CROSS) {  // processing.rs:371-401: rows y-3..y+3 at x, then columns x-3..x+3 at y
+        if (k >= 14) return false;
+        *py = k < 7 ? it.y + k - 3 : it.y;
+        *px = k < 7 ? it.x : it.x + k - 10;
+        return true;
+    }
+    if (it.kind == HV_OVERLAY_MARKER) {
+        if (k >= 23 * 23) return false;
+        const int r = k / 23, c = k - 23 * r;
+        if (!((kMarkerRows[r] >> c) & 1u)) return false;
+        *py = it.y + r - 11;
+        *px = it.x + c - 11;
+        return true;
+    }
+    const int ya = min(it.y, it.y1), yb = max(it.y, it.y1), xa = min(it.x, it.x1), xb = max(it.x, it.x1);
+    const int bw = xb - xa + 1, bh = yb - ya + 1;
+    if (k < bw) return *py = ya, *px = xa + k, true;
+    k -= bw;
+    if (k < bw) return *py = yb, *px = xa + k, true;
+    k -= bw;
+    if (k < bh) return *py = ya + k, *px = xa, true;
+    k -= bh;
+    if (k < bh) return *py = ya + k, *px = xb, true;
+    return false;
+}
+
+__device__ __forceinline__ int overlay_extent(const hv_overlay &it) {
+    if (it.kind == HV_OVERLAY_CROSS) return 14;
+    if (it.kind == HV_OVERLAY_MARKER) return 23 * 23;
+    const long long e = 2ll * (llabs((long long)it.y1 - it.y) + 1) + 2ll * (llabs((long long)it.x1 - it.x) + 1);
+    return (int)min(e, 2000000000ll);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(128) k_overlays(const hv_overlay *items, int n, int h, int w, uint8_t *img, unsigned int *owner) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const hv_overlay it = items[i];
+        const int ext = overlay_extent(it);
+        for (int k = threadIdx.x; k < ext; k += blockDim.x) {
+            int y, x;
+            if (!overlay_pixel(it, k, &y, &x) || y < 0 || y >= h || x < 0 || x >= w) continue;
+            const size_t p = (size_t)y * w + x;
+            if (PASS == 0) {
+                atomicMax(owner + p, (unsigned int)i + 1u);
+            } else if (PASS == 1) {
+                if (owner[p] == (unsigned int)i + 1u) {
+                    img[3 * p] = it.color[0];
+                    img[3 * p + 1] = it.color[1];
+                    img[3 * p + 2] = it.color[2];
+                }
+            } else {
+                owner[p] = 0u;
+            }
+        }
+    }
+}
+
 int grid_for(size_t work_items, int per_block) {
     size_t g = (work_items + per_block - 1) / per_block;
     const size_t cap = 148 * 32;
@@ -667,4 +736,15 @@ cudaError_t launch_visualise(const uint8_t *mask, int h, int w, const hv_center 
     return cudaGetLastError();
 }
 
+}  // namespace hv
+
+namespace hv {
+cudaError_t launch_overlays(const hv_overlay *d_items, int n, int h, int w, uint8_t *d_img, unsigned int *d_owner, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int grid = n < 148 * 8 ? n : 148 * 8;
+    k_overlays<0><<<grid, 128, 0, s>>>(d_items, n, h, w, d_img, d_owner);
+    k_overlays<1><<<grid, 128, 0, s>>>(d_items, n, h, w, d_img, d_owner);
+    k_overlays<2><<<grid, 128, 0, s>>>(d_items, n, h, w, d_img, d_owner);
+    return cudaGetLastError();
+}
 }  // namespace hv

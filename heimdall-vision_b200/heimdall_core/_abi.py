@@ -112,6 +112,24 @@ class hv_frameset_stats(C.Structure):
                                           "duplicates", "batches_submitted", "max_skew_ns", "sets_pending")]
 
 
+class hv_inspection_record(C.Structure):
+    _fields_ = [("sequence", C.c_uint64), ("timestamp", C.c_double), ("processing_time", C.c_double),
+                ("success", C.c_uint32), ("has_defects", C.c_uint32), ("defect_count", C.c_uint32),
+                ("defects_offset", C.c_uint32)]
+
+
+class hv_dashboard_stats(C.Structure):
+    _fields_ = [("total_images", C.c_uint64), ("total_defects", C.c_uint64), ("avg_processing_time_ms", C.c_double),
+                ("defect_rate", C.c_double), ("start_time", C.c_double)]
+
+
+class hv_overlay(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("y", C.c_int32), ("x", C.c_int32), ("y1", C.c_int32), ("x1", C.c_int32),
+                ("color", C.c_uint8 * 3), ("reserved", C.c_uint8)]
+
+
+HV_OVERLAY_CROSS, HV_OVERLAY_BOX, HV_OVERLAY_MARKER = 0, 1, 2
+
 assert C.sizeof(hv_camera_frame) == 48
 assert C.sizeof(hv_defect) == 48 and C.sizeof(hv_frame_result) == 24 and C.sizeof(hv_blob) == 40
 assert C.sizeof(hv_line_stats) == 256
@@ -164,6 +182,9 @@ PROTOTYPES = {
     "hv_morphology": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hv_find_contours": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _f64, _P(hv_contour), _sz, _P(_sz), _vp]),
     "hv_process_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _P(hv_center), _sz, _P(_sz)]),
+    "hv_export_results": (_i32, [_P(hv_frame_result), _i32, _f64, _f64, C.c_uint64, _P(hv_inspection_record),
+                                 _P(hv_dashboard_stats)]),
+    "hv_draw_overlays": (_i32, [_vp, _vp, _i32, _i32, _P(hv_overlay), _i32]),
     "hv_stats_get": (_i32, [_vp, _P(hv_line_stats)]),
     "hv_stats_reset": (_i32, [_vp]),
     "hv_stats_device_ptr": (_vp, [_vp]),

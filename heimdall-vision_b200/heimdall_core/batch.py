@@ -24,7 +24,7 @@ class HeimdallCudaError(RuntimeError):
 
 
 def _raise(status: int, ctx) -> None:
-    msg = _lib.hv_last_error(ctx) if ctx else _lib.hv_last_error(None)
+    msg = _lib.hv_last_error(ctx) if ctx else b""
     text = (msg or b"").decode() or _lib.hv_status_string(status).decode()
     # same mapping as the reference: its Result errors become ValueError (processing.rs:23-27, detection.rs:29-33)
     if status in (A.HV_ERR_INVALID_DIMENSIONS, A.HV_ERR_CHANNELS, A.HV_ERR_UNSUPPORTED, A.HV_ERR_INVALID_ARGUMENT):

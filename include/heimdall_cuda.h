@@ -390,6 +390,53 @@ HV_API hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, in
                                   int32_t pipeline, uint8_t *out_hw3, hv_center *contours, size_t cap,
                                   size_t *n_contours);
 
+/* ---- result side (next-row N4) ---------------------------------------------------------------------------------
+ * What the reference does with a frame's defect list once the detector has returned.
+ *
+ * hv_export_results: per-frame records in the shape of `InspectionResult` (heimdall/inspection/base_inspector.py:11-64:
+ * inspection_id, timestamp, success, has_defects = len(defects) > 0, defect_count, processing_time) from the results of a
+ * batch, and the dashboard's running statistics (dashboard.py:38-46 `processing_stats`, updated per image at :483-500:
+ * total_images, total_defects, an exponential moving average of the processing time in milliseconds -- first sample
+ * taken as is, then 0.9 * avg + 0.1 * t * 1000 -- and defect_rate = total_defects / total_images * 100).  Host-side
+ * marshalling, no device work. */
+typedef struct {
+    uint64_t sequence;        /* running inspection number: inspection_id = "<inspector_id>_<sequence>" (base_inspector.py:109) */
+    double timestamp;         /* seconds since the epoch, as given */
+    double processing_time;   /* seconds, as given (per frame) */
+    uint32_t success;         /* 1 unless the frame's status reports an error */
+    uint32_t has_defects;     /* the reject predicate (base_inspector.py:40-42) */
+    uint32_t defect_count;
+    uint32_t defects_offset;  /* first defect of the frame in the batch's defect array */
+} hv_inspection_record;
+typedef struct {
+    uint64_t total_images;
+    uint64_t total_defects;
+    double avg_processing_time_ms;
+    double defect_rate;       /* per cent */
+    double start_time;        /* untouched by the library (dashboard.py:45) */
+} hv_dashboard_stats;
+HV_API hv_status hv_export_results(const hv_frame_result *results, int32_t n, double timestamp, double processing_time,
+                                   uint64_t first_sequence, hv_inspection_record *records, hv_dashboard_stats *stats);
+
+/* Overlays on an (h, w, 3) u8 image in host memory, drawn on the device in list order (a later item paints over an earlier
+ * one).  Kinds:
+ *   HV_OVERLAY_CROSS  the 7-pixel cross of process_image("contamination") at (y, x): vertical bar then horizontal bar,
+ *                     clipped at the image border (rust/heimdall-core/src/processing.rs:371-401);
+ *   HV_OVERLAY_BOX    cv2.rectangle(img, (x, y), (x1, y1), color, 1): the one-pixel outline of the bounding box
+ *                     (the box of heimdall/detectors/contamination_detector.py:249 with thickness 1);
+ *   HV_OVERLAY_MARKER the dashboard's defect marker cv2.circle(img, (x, y), 10, color, 2) (dashboard.py:462; the same call
+ *                     at base_inspector.py:186): OpenCV's footprint of that circle, identical to cv2 wherever the marker
+ *                     lies inside the image and the clipped footprint otherwise (OpenCV re-rasterises clipped arcs). */
+enum { HV_OVERLAY_CROSS = 0, HV_OVERLAY_BOX = 1, HV_OVERLAY_MARKER = 2 };
+typedef struct {
+    int32_t kind;
+    int32_t y, x;      /* cross / marker centre; box: first corner */
+    int32_t y1, x1;    /* box: opposite corner (inclusive) */
+    uint8_t color[3];  /* in the image's channel order; the reference draws (0, 0, 255) */
+    uint8_t reserved;
+} hv_overlay;
+HV_API hv_status hv_draw_overlays(hv_ctx *ctx, uint8_t *img_hw3, int32_t h, int32_t w, const hv_overlay *items, int32_t n);
+
 /* ---- line statistics ------------------------------------------------------------------------------------ */
 HV_API hv_status hv_stats_get(hv_ctx *ctx, hv_line_stats *out);
 HV_API hv_status hv_stats_reset(hv_ctx *ctx);

@@ -88,7 +88,33 @@ def morph_pipeline():
     np.savez_compressed(os.path.join(HERE, "cv2_morph_pipeline.npz"), **d)
 
 
+def overlays():
+    """cv2_overlays.npz: what opencv-python draws for the result-side overlays (next-row N4): cv2.rectangle thickness 1 for
+    boxes (any corner order, partly outside the image), cv2.circle(c, 10, color, 2) for the dashboard's defect marker
+    (dashboard.py:462) at centres whose marker lies inside the image.  Items are (kind, y, x, y1, x1, b, g, r)."""
+    rng = np.random.default_rng(20261020)
+    h, w = 96, 140
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    items = []
+    img = base.copy()
+    for _ in range(14):
+        x, y = int(rng.integers(-6, w + 6)), int(rng.integers(-6, h + 6))
+        x1, y1 = x + int(rng.integers(-30, 40)), y + int(rng.integers(-30, 40))
+        col = [int(c) for c in rng.integers(0, 256, 3)]
+        cv2.rectangle(img, (x, y), (x1, y1), col, 1)
+        items.append([1, y, x, y1, x1] + col)
+    for _ in range(10):
+        x, y = int(rng.integers(12, w - 12)), int(rng.integers(12, h - 12))
+        col = [int(c) for c in rng.integers(0, 256, 3)]
+        cv2.circle(img, (x, y), 10, col, 2)
+        items.append([2, y, x, 0, 0] + col)
+    np.savez_compressed(os.path.join(HERE, "cv2_overlays.npz"), base=base, items=np.array(items, np.int32), out=img)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "overlays":
+        overlays()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "pixfmt":
         pixfmt()
         return
@@ -97,6 +123,7 @@ def main():
         return
     pixfmt()
     morph_pipeline()
+    overlays()
     rng = np.random.default_rng(20261018)
     meta = {"opencv": cv2.__version__, "numpy": np.__version__}
 
