@@ -1807,6 +1807,102 @@ hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w
     return rc;
 }
 
+// ---- Python-detector parity mode (N3) --------------------------------------------------------------------------------------
+void hv_pydet_params_default(hv_pydet_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->contrast_threshold = 25.0;  // contamination_detector.py:36
+    p->blur_ksize = 5;             // :66
+    p->block_size = 11;            // :75
+    p->morph_open_k = 3;           // :81-84
+    p->morph_close_k = 3;          // :87
+}
+
+hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                    const hv_pydet_params *params, uint8_t *gray, uint8_t *blurred, uint8_t *binary,
+                                    int32_t *labels8, hv_blob *comps, size_t cap, size_t *n_comps) {
+    if (!ctx || !img || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
+    if (c != 1 && c != 3) return fail(ctx, HV_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: expected 3D array");
+    if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
+    hv_pydet_params pr;
+    if (params)
+        pr = *params;
+    else
+        hv_pydet_params_default(&pr);
+    if (pr.block_size < 3 || pr.block_size > 31 || !(pr.block_size & 1))
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "block_size must be odd and in [3, 31]");
+    if (pr.morph_open_k < 0 || pr.morph_open_k > 31 || pr.morph_close_k < 0 || pr.morph_close_k > 31)
+        return fail(ctx, HV_ERR_INVALID_ARGUMENT, "morphology kernel size must be in [0, 31]");
+    uint16_t gk[32];
+    if (!gaussian_kernel_q8(pr.blur_ksize, 0.0, gk)) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "Gaussian kernel size must be odd and in [1, 31]");
+    // cv2.getGaussianKernel(block_size, 0, CV_32F): sigma = 0.3 * ((n - 1) * 0.5 - 1) + 0.8, computed in double, stored as float
+    float fk[31];
+    {
+        const int n = pr.block_size;
+        static const double t3[] = {0.25, 0.5, 0.25}, t5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625},
+                            t7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
+        const double *fixed = n == 3 ? t3 : n == 5 ? t5 : n == 7 ? t7 : nullptr;  // OpenCV's small_gaussian_tab
+        if (fixed) {
+            for (int i = 0; i < n; i++) fk[i] = (float)fixed[i];
+        } else {
+            const double sigma = ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+            const double scale2x = -0.5 / (sigma * sigma);
+            double kd[31], sum = 0;
+            for (int i = 0; i < n; i++) {
+                const double x = i - (n - 1) * 0.5;
+                kd[i] = std::exp(scale2x * x * x);
+                sum += kd[i];
+            }
+            for (int i = 0; i < n; i++) fk[i] = (float)(kd[i] / sum);
+        }
+    }
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    if (retire_slot(ctx, s) != HV_OK) return HV_ERR_CUDA;
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    hv_status rs = reserve_slot(ctx, s, 1, h, w, true, px * c, true, true, true, true, true);
+    if (rs != HV_OK) return rs;
+    HV_TRY_CUDA(ctx, ctx->u_a.reserve(px * sizeof(float)));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(s.in.p, img, px * c, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_gray = s.in.p;
+    if (c == 3) {
+        HV_TRY_CUDA(ctx, launch_gray_bgr_cv(s.in.p, h, w, s.gray.p, st));
+        ctx->launches++;
+        d_gray = s.gray.p;
+    }
+    HV_TRY_CUDA(ctx, launch_gaussian_blur(d_gray, 1, h, w, gk, pr.blur_ksize, s.blur.p, s.gauss_tmp.p, st));
+    const double cf = std::floor(pr.contrast_threshold);  // THRESH_BINARY_INV: idelta = cvFloor(C)
+    const int idelta = cf > 1e9 ? 1000000000 : (cf < -1e9 ? -1000000000 : (int)cf);
+    HV_TRY_CUDA(ctx, launch_adaptive_gaussian(s.blur.p, h, w, fk, pr.block_size, idelta, reinterpret_cast<float *>(ctx->u_a.p),
+                                              s.mask.p, st));
+    BatchView b{};
+    fill_view(ctx, s, b, h, w);
+    b.rowflags = s.rowflags.p, b.tiles_x = (w + 127) / 128, b.rf_stride = (size_t)((h + 31) / 32) * b.tiles_x * 32;
+    b.conn8 = 1;
+    HV_TRY_CUDA(ctx, launch_bits_from_gt127(s.mask.p, 1, h, w, b.ww, b.bits, st));
+    int nl = 0;
+    HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
+    HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b, st));
+    ctx->launches += 6 + nl;
+    rs = run_ccl_only(ctx, s, st, b);
+    if (rs != HV_OK) return rs;
+    uint32_t ncomp = 0;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(&ncomp, b.ncomp, sizeof(ncomp), cudaMemcpyDeviceToHost, st));
+    if (gray) HV_TRY_CUDA(ctx, cudaMemcpyAsync(gray, d_gray, px, cudaMemcpyDeviceToHost, st));
+    if (blurred) HV_TRY_CUDA(ctx, cudaMemcpyAsync(blurred, s.blur.p, px, cudaMemcpyDeviceToHost, st));
+    if (binary) HV_TRY_CUDA(ctx, cudaMemcpyAsync(binary, b.mask, px, cudaMemcpyDeviceToHost, st));
+    if (labels8) HV_TRY_CUDA(ctx, cudaMemcpyAsync(labels8, b.labels, px * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    s.has_batch = false;
+    const size_t ncopy = std::min<size_t>(std::min<size_t>(ncomp, cap), (size_t)b.blob_cap);
+    if (comps && ncopy) HV_TRY_CUDA(ctx, cudaMemcpy(comps, b.blobs, sizeof(hv_blob) * ncopy, cudaMemcpyDeviceToHost));
+    if (n_comps) *n_comps = ncopy;
+    if (ncomp > (uint32_t)b.blob_cap || (comps && ncomp > cap))
+        return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more components than max_blobs_per_frame / cap");
+    return HV_OK;
+}
+
 // ---- result side (N4) ---------------------------------------------------------------------------------------------------
 hv_status hv_export_results(const hv_frame_result *results, int32_t n, double timestamp, double processing_time,
                             uint64_t first_sequence, hv_inspection_record *records, hv_dashboard_stats *stats) {

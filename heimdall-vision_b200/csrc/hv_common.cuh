@@ -57,6 +57,7 @@ struct BatchView {
     unsigned int *ccl_wait_flag[4];
     unsigned int ccl_wait_val[4];
     const uint32_t *frame_select;  // n or NULL: when set, the global-path kernels only touch frames with a non-zero entry
+    int conn8;                     // global-memory CCL kernels: 8-connectivity (the Python detector's contours) instead of 4
 };
 
 struct PreprocessParams {
@@ -197,6 +198,9 @@ cudaError_t launch_collect_centers(const BatchView &b, uint32_t min_area, hv_cen
 cudaError_t launch_bayer(const uint8_t *d_src, int n, int h, int w, int pattern, bool to_gray, uint8_t *d_dst,
                          cudaStream_t s);
 cudaError_t launch_yuyv(const uint8_t *d_src, int n, int h, int w, bool to_gray, uint8_t *d_dst, cudaStream_t s);
+cudaError_t launch_gray_bgr_cv(const uint8_t *d_img, int h, int w, uint8_t *d_gray, cudaStream_t s);
+cudaError_t launch_adaptive_gaussian(const uint8_t *d_src, int h, int w, const float *k_host, int ksize, int idelta,
+                                     float *d_rows, uint8_t *d_mask, cudaStream_t s);
 cudaError_t launch_overlays(const hv_overlay *d_items, int n, int h, int w, uint8_t *d_img, unsigned int *d_owner, cudaStream_t s);
 cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
                                     uint32_t *d_count, int cap, cudaStream_t s);

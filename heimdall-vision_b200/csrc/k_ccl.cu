@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
             const uint32_t left = b.bits[i - 1];
             if (left >> 31) uf_union(L, row, row - 32 + run_start(left, 31));
         }
-        if (y > 0) {
+        if (y > 0 && !b.conn8) {
             const uint32_t up = b.bits[i - b.ww];
             const uint32_t o = m & up;
             uint32_t starts = o & ~(o << 1);
@@ -102,6 +102,29 @@ __global__ void __launch_bounds__(256) k_ccl_merge(BatchView b) {
                 const int bit = __ffs(starts) - 1;
                 starts &= starts - 1;
                 uf_union(L, row + run_start(m, bit), row - b.w + run_start(up, bit));
+            }
+        } else if (y > 0) {
+            // 8-connectivity: a run touches every run of the row above that meets it widened by one pixel on either side,
+            // which may reach into the neighbouring words of that row
+            const uint32_t up = b.bits[i - b.ww];
+            const uint32_t upl = wx > 0 ? b.bits[i - b.ww - 1] : 0u, upr = wx + 1 < b.ww ? b.bits[i - b.ww + 1] : 0u;
+            uint32_t rest = m;
+            while (rest) {
+                const int bit = __ffs(rest) - 1;
+                const uint32_t shifted = ~(rest >> bit);
+                const int len = shifted ? __ffs(shifted) - 1 : 32 - bit;
+                const uint32_t runmask = (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << bit;
+                rest &= ~runmask;
+                const int node = row + bit;
+                const uint32_t touch = (runmask | (runmask << 1) | (runmask >> 1)) & up;
+                uint32_t starts = touch & ~(touch << 1);
+                while (starts) {
+                    const int tb = __ffs(starts) - 1;
+                    starts &= starts - 1;
+                    uf_union(L, node, row - b.w + run_start(up, tb));
+                }
+                if (bit == 0 && (upl >> 31)) uf_union(L, node, row - b.w - 32 + run_start(upl, 31));
+                if (bit + len == 32 && (upr & 1u)) uf_union(L, node, row - b.w + 32);
             }
         }
     }

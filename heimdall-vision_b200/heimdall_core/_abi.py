@@ -112,6 +112,11 @@ class hv_frameset_stats(C.Structure):
                                           "duplicates", "batches_submitted", "max_skew_ns", "sets_pending")]
 
 
+class hv_pydet_params(C.Structure):
+    _fields_ = [("contrast_threshold", C.c_double), ("blur_ksize", C.c_int32), ("block_size", C.c_int32),
+                ("morph_open_k", C.c_int32), ("morph_close_k", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
 class hv_inspection_record(C.Structure):
     _fields_ = [("sequence", C.c_uint64), ("timestamp", C.c_double), ("processing_time", C.c_double),
                 ("success", C.c_uint32), ("has_defects", C.c_uint32), ("defect_count", C.c_uint32),
@@ -182,6 +187,9 @@ PROTOTYPES = {
     "hv_morphology": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hv_find_contours": (_i32, [_vp, _vp, _i32, _i32, _i32, _f64, _f64, _P(hv_contour), _sz, _P(_sz), _vp]),
     "hv_process_image": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _P(hv_center), _sz, _P(_sz)]),
+    "hv_pydet_params_default": (None, [_P(hv_pydet_params)]),
+    "hv_python_detector_stages": (_i32, [_vp, _vp, _i32, _i32, _i32, _P(hv_pydet_params), _vp, _vp, _vp, _vp, _P(hv_blob), _sz,
+                                         _P(_sz)]),
     "hv_export_results": (_i32, [_P(hv_frame_result), _i32, _f64, _f64, C.c_uint64, _P(hv_inspection_record),
                                  _P(hv_dashboard_stats)]),
     "hv_draw_overlays": (_i32, [_vp, _vp, _i32, _i32, _P(hv_overlay), _i32]),

@@ -346,6 +346,33 @@ class Detector:
                 _raise(st, self._ctx)
         return out
 
+    def python_detector_stages(self, img: np.ndarray, contrast_threshold: float = 25.0, *, blur_ksize: int = 5,
+                               block_size: int = 11, morph_open_k: int = 3, morph_close_k: int = 3) -> dict:
+        """The stages of the reference's Python detector (contamination_detector.py:58-90) with OpenCV's arithmetic
+        (hv_python_detector_stages): {"gray", "blurred", "binary", "labels8", "components"}; components = BLOB_DTYPE rows of
+        the 8-connected components of `binary` in raster order of their first pixel."""
+        a = np.ascontiguousarray(img, np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        h, w, c = a.shape
+        p = A.hv_pydet_params()
+        _lib.hv_pydet_params_default(C.byref(p))
+        p.contrast_threshold, p.blur_ksize, p.block_size = float(contrast_threshold), int(blur_ksize), int(block_size)
+        p.morph_open_k, p.morph_close_k = int(morph_open_k), int(morph_close_k)
+        out = {"gray": np.empty((h, w), np.uint8), "blurred": np.empty((h, w), np.uint8), "binary": np.empty((h, w), np.uint8),
+               "labels8": np.empty((h, w), np.int32)}
+        cap = h * w // 2 + 1
+        comps = np.zeros(min(cap, 131072), BLOB_DTYPE)
+        n = C.c_size_t(0)
+        with self._lock:
+            st = _lib.hv_python_detector_stages(self._ctx, a.ctypes.data, h, w, c, C.byref(p), out["gray"].ctypes.data,
+                                                out["blurred"].ctypes.data, out["binary"].ctypes.data, out["labels8"].ctypes.data,
+                                                comps.ctypes.data_as(C.POINTER(A.hv_blob)), len(comps), C.byref(n))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        out["components"] = comps[:n.value]
+        return out
+
     def find_contours(self, img: np.ndarray, min_area: float, max_area: float, want_labels: bool = True):
         h, w, c = img.shape
         cap = h * w // 2 + 1

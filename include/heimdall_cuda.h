@@ -390,6 +390,34 @@ HV_API hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, in
                                   int32_t pipeline, uint8_t *out_hw3, hv_center *contours, size_t cap,
                                   size_t *n_contours);
 
+/* ---- Python-detector parity mode (next-row N3) ------------------------------------------------------------------
+ * The stages of the reference's Python detector, `ContaminationDetector.detect` (heimdall/detectors/
+ * contamination_detector.py:58-90; the fallback behind heimdall/rust_bridge.py:139-161), with OpenCV's arithmetic:
+ *   gray     cv2.cvtColor(BGR2GRAY) for c == 3 (15-bit fixed point), the image itself for c == 1          (:58-62)
+ *   blurred  cv2.GaussianBlur(gray, (blur_ksize, blur_ksize), 0)                                             (:66)
+ *   binary   cv2.adaptiveThreshold(blurred, 255, ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY_INV, block_size, C) (:70-77)
+ *            then MORPH_OPEN and MORPH_CLOSE with k x k rectangles                                             (:81-87)
+ *   comps    the 8-connected components of `binary` in raster order of their first pixel (area in pixels, bounding box,
+ *            coordinate sums) and their label plane: the regions whose outer borders cv2.findContours(RETR_EXTERNAL)
+ *            (:90) traces -- RETR_EXTERNAL additionally drops components that lie inside a hole of another one.
+ * gray / blurred / binary are bit-exact with opencv-python 4.13 on the committed golden vectors (the float32 mean of
+ * adaptiveThreshold follows OpenCV's AVX2/FMA summation order, see k_pydet.cu).  NOT reproduced: the contour polygons and
+ * what the detector derives from them (cv2.contourArea, cv2.moments, the filled-polygon masks behind the intensity and
+ * colour scores, :96-160) -- polygon quantities of traced borders, not pixel counts.  Any output pointer may be NULL. */
+typedef struct {
+    double contrast_threshold; /* C (contamination_detector.py:36 default 25) */
+    int32_t blur_ksize;        /* 5 */
+    int32_t block_size;        /* 11: odd, 3..31 */
+    int32_t morph_open_k;      /* 3 */
+    int32_t morph_close_k;     /* 3 */
+    int32_t reserved[4];
+} hv_pydet_params;
+HV_API void hv_pydet_params_default(hv_pydet_params *p);
+HV_API hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                           const hv_pydet_params *params, uint8_t *gray, uint8_t *blurred,
+                                           uint8_t *binary, int32_t *labels8, hv_blob *comps, size_t cap,
+                                           size_t *n_comps);
+
 /* ---- result side (next-row N4) ---------------------------------------------------------------------------------
  * What the reference does with a frame's defect list once the detector has returned.
  *

@@ -111,7 +111,56 @@ def overlays():
     np.savez_compressed(os.path.join(HERE, "cv2_overlays.npz"), base=base, items=np.array(items, np.int32), out=img)
 
 
+def python_detector():
+    """cv2_python_detector.npz (next-row N3): the stages of the reference's Python detector
+    (heimdall/detectors/contamination_detector.py:58-90) run through opencv-python itself on seeded frames:
+    cvtColor(BGR2GRAY) -> GaussianBlur(5,5,0) -> adaptiveThreshold(GAUSSIAN_C, BINARY_INV, 11, C) -> MORPH_OPEN 3x3 ->
+    MORPH_CLOSE 3x3 -> findContours(RETR_EXTERNAL); plus the 8-connected components of the final mask
+    (connectedComponentsWithStats, relabelled in raster order of each component's first pixel)."""
+    rng = np.random.default_rng(20261021)
+    frames = {}
+    fr = synth.bottle_frame(240, 320, 3, contaminants=2)
+    frames["bottle_bgr"] = (np.dstack([fr, fr, fr]), 25)
+    tex = rng.integers(0, 256, (72, 100, 3), dtype=np.uint8)
+    frames["texture_bgr"] = (tex, 10)
+    blem = synth.near_threshold_frame(200, 260, 7, spots=8)
+    frames["blemish_gray"] = (blem, 5)
+    col = np.dstack([synth.bottle_frame(160, 208, 9, contaminants=3), synth.bottle_frame(160, 208, 10, contaminants=1),
+                     synth.bottle_frame(160, 208, 11, contaminants=2)])
+    frames["colour_bgr"] = (col, 12.7)
+    d = {}
+    for name, (img, C) in frames.items():
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) if img.ndim == 3 else img
+        blurred = cv2.GaussianBlur(gray, (5, 5), 0)
+        binary = cv2.adaptiveThreshold(blurred, 255, cv2.ADAPTIVE_THRESH_GAUSSIAN_C, cv2.THRESH_BINARY_INV, 11, C)
+        ker = cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3))
+        m = cv2.morphologyEx(cv2.morphologyEx(binary, cv2.MORPH_OPEN, ker), cv2.MORPH_CLOSE, ker)
+        n, lab, st, _ = cv2.connectedComponentsWithStats(m, connectivity=8, ltype=cv2.CV_32S)
+        flat = lab.ravel()
+        _, first = np.unique(flat, return_index=True)          # first raster index of every label (0 = background)
+        order = np.argsort(first[1:]) + 1                        # labels by first pixel
+        remap = np.zeros(n, np.int32)
+        remap[order] = np.arange(1, n)
+        canon = remap[lab]
+        stats = st[order]                                        # x, y, w, h, area in canonical order
+        contours, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        rects = sorted(cv2.boundingRect(c) for c in contours)
+        d[f"{name}_img"] = img
+        d[f"{name}_C"] = np.float64(C)
+        d[f"{name}_gray"], d[f"{name}_blurred"] = gray, blurred
+        d[f"{name}_binary"], d[f"{name}_morphed"] = np.packbits(binary > 0), np.packbits(m > 0)
+        d[f"{name}_labels8"] = canon.astype(np.int32)
+        d[f"{name}_stats8"] = stats.astype(np.int32)
+        d[f"{name}_ext_rects"] = np.array(rects, np.int32).reshape(-1, 4)
+    np.savez_compressed(os.path.join(HERE, "cv2_python_detector.npz"), **d)
+    for name in frames:
+        print(name, "components", len(d[f"{name}_stats8"]), "external contours", len(d[f"{name}_ext_rects"]))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "python_detector":
+        python_detector()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "overlays":
         overlays()
         return
@@ -124,6 +173,7 @@ def main():
     pixfmt()
     morph_pipeline()
     overlays()
+    python_detector()
     rng = np.random.default_rng(20261018)
     meta = {"opencv": cv2.__version__, "numpy": np.__version__}
 
