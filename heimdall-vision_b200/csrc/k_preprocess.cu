@@ -289,8 +289,9 @@ __device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const Prepro
     uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
     const int ks = p.gauss_ksize, R = ks >> 1;
     const int H = b.h, W = b.w;
-    for (int idx = tid; idx < T::GH * (T::BW / 4); idx += 256) {
-        const int r = idx / (T::BW / 4), i = 4 * (idx - r * (T::BW / 4));
+    const int r_skip = kGaussRB - R;  // the column pass reads row-filtered rows r_skip .. GH - 1 - r_skip only
+    for (int idx = tid; idx < (T::GH - 2 * r_skip) * (T::BW / 4); idx += 256) {
+        const int r = r_skip + idx / (T::BW / 4), i = 4 * (idx % (T::BW / 4));
         const uint8_t *src = &s_g[r][T::GOFF + i - R];  // tap t of output j reads src[j + t]
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
@@ -329,6 +330,68 @@ __device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const Prepro
     tile_sync<NAMED>();
 }
 
+// cv2.GaussianBlur(5, 5, 0) -- the reference's own setting (heimdall/detectors/contamination_detector.py:66) -- on interior
+// tiles, in packed u16x2 arithmetic like the box blur.  OpenCV's 8.8 taps are [16, 64, 96, 64, 16] = 16 * [1, 4, 6, 4, 1]
+// per axis and its result is (sum + 32768) >> 16; both passes are exact integer sums, so the order of the passes is free and
+// the common factor 256 can be taken out: v = (g0 + g4) + 4 (g1 + g3) + 6 g2 over rows (<= 4080), h likewise over columns
+// (<= 65280: fits a 16-bit lane), blur = (h + 128) >> 8.  Blur row r (image row y0 - 5 + r) is centred on stage row r + 7.
+template <int TW, int TH, int HXP, bool NAMED>
+__device__ __forceinline__ void gauss5_fast_blur(uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid, uint64_t *empty_bar) {
+    using T = Tile<TW, TH, kGaussRB, HXP>;
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(u1_raw);
+    uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
+    static_assert(TW == 128 && TH == 32 && T::GOFF == 8 && T::BH == 42 && T::VP >= 152, "thread mappings below");
+    // A. vertical taps: thread = (quad q of 38 over logical columns -4 .. 147, segment of 7 blur rows) -> 228 threads.
+    //    Logical column i sits at stage column 8 + i and is stored at s_v index i + 4.
+    if (tid < 38 * 6) {
+        const int q = tid % 38, seg = tid / 38;
+        const int r0 = seg * 7;
+        uint32_t lo[11], hi[11];
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + 5 + k][4 + 4 * q]);
+            lo[k] = prmt(v, 0, 0x4140);
+            hi[k] = prmt(v, 0, 0x4342);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const uint32_t vlo = (lo[k] + lo[k + 4]) + ((lo[k + 1] + lo[k + 3]) << 2) + lo[k + 2] * 6u;
+            const uint32_t vhi = (hi[k] + hi[k + 4]) + ((hi[k + 1] + hi[k + 3]) << 2) + hi[k + 2] * 6u;
+            *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q]) = make_uint2(vlo, vhi);
+        }
+    }
+    tile_sync<NAMED>();
+    if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // the gray stage is dead: the producer may refill it
+    // B. horizontal taps + rounding: thread = (row, group of 36 columns) -> 42 x 4 = 168 threads; output i = 36g + j reads
+    //    s_v indices i + 2 .. i + 6
+    if (tid < 42 * 4) {
+        const int g = tid & 3, r = tid >> 2;
+        const uint16_t *vrow = &s_v[r][36 * g];
+        uint32_t pk[22];
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const uint2 t = *reinterpret_cast<const uint2 *>(vrow + 4 * k);
+            pk[2 * k] = t.x;
+            pk[2 * k + 1] = t.y;
+        }
+        auto el = [&](int e) -> uint32_t { return (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xffffu); };
+        uint32_t *brow = reinterpret_cast<uint32_t *>(&s_bl[r][36 * g]);
+#pragma unroll
+        for (int j4 = 0; j4 < 9; j4++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = 4 * j4 + u;
+                const uint32_t hsum = (el(j + 2) + el(j + 6)) + ((el(j + 3) + el(j + 5)) << 2) + el(j + 4) * 6u;
+                o[u] = (hsum + 128u) >> 8;
+            }
+            brow[j4] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+        }
+    }
+    tile_sync<NAMED>();
+}
+
 // Everything after the gray tile (+ halo, zero outside the image) sits in shared memory and the flat decision is known:
 // blur + threshold (fast or generic path) and the three outputs.  Block-uniform control flow; contains barriers.
 template <int TW, int TH, int RB, int HXP, bool NAMED>
@@ -353,7 +416,14 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
     if (!flat) {
         const bool fast_thr = TW == 128 && TH == 32 && interior && p.inverse && cth >= 0 && cth <= 255 && !p.force_generic;
         if (RB == kGaussRB && p.gauss_ksize > 0) {
-            gauss_blur_tile<TW, TH, HXP, NAMED>(b, p, g_raw, u1_raw, bl_raw, f, x0, y0, tid, empty_bar);
+            bool done5 = false;
+            if constexpr (RB == kGaussRB && HXP == 16) {
+                if (fast_thr && !p.write_blur && p.gauss_ksize == 5 && p.gk[0] == 16 && p.gk[1] == 64 && p.gk[2] == 96) {
+                    gauss5_fast_blur<TW, TH, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
+                    done5 = true;
+                }
+            }
+            if (!done5) gauss_blur_tile<TW, TH, HXP, NAMED>(b, p, g_raw, u1_raw, bl_raw, f, x0, y0, tid, empty_bar);
             if (fast_thr) fast_threshold<128, 32, T::BW, NAMED>(f_raw, u1_raw, bl_raw, tid, cth);
         } else if (RB == 2 && fast_thr && !p.write_blur) {
             fast_blur_rb2<128, 32, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
@@ -1239,13 +1309,19 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
                 }
                 if (n_cols) tile_sync<true>();
             }
-            if (try_flat) {  // every row of the box, all its 16-byte items (4 px more than needed on either side)
+            if (try_flat) {  // the rows within reach of the filters (RB + 5 of the 12 halo rows for small kernels), all their
+                             // 16-byte items (4 px more than needed on either side): one contiguous run of items
                 const uint32_t ref4 = 0x01010101u * s_g[T::HALO + TH / 2][T::HX + TW / 2];
-                constexpr int NV = T::GH * (T::GW / 16);
-                for (int idx = tid; idx < NV; idx += kK1Consumers) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(cur_stage + 16 * idx);
-                    absd(v.x, ref4, acc), absd(v.y, ref4, acc), absd(v.z, ref4, acc), absd(v.w, ref4, acc);
-                }
+                const int r_skip = kGaussRB - (p.gauss_ksize >> 1);
+                const int nv = (T::GH - 2 * r_skip) * (T::GW / 16);  // <= 560
+                const uint8_t *base = cur_stage + r_skip * T::GW;
+                const uint4 fill = make_uint4(ref4, ref4, ref4, ref4);
+                const uint4 v0 = tid < nv ? *reinterpret_cast<const uint4 *>(base + 16 * tid) : fill;
+                const uint4 v1 = tid + 256 < nv ? *reinterpret_cast<const uint4 *>(base + 16 * (tid + 256)) : fill;
+                const uint4 v2 = tid + 512 < nv ? *reinterpret_cast<const uint4 *>(base + 16 * (tid + 512)) : fill;
+                absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
+                absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
+                absd(v2.x, ref4, acc), absd(v2.y, ref4, acc), absd(v2.z, ref4, acc), absd(v2.w, ref4, acc);
             }
         } else if (try_flat) {
             if (box_inside) {

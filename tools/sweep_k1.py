@@ -4,10 +4,13 @@ process, so run one process per variant:  HV_K1_LOOKAHEAD=2 python tools/sweep_k
 import os, sys, numpy as np, torch
 sys.path.insert(0, 'heimdall-vision_b200'); sys.path.insert(0, '.')
 import heimdall_core as hc, synth
-n, h, w = 25, 1024, 1280
+n, h, w = int(os.environ.get('SWEEP_N', 25)), int(os.environ.get('SWEEP_H', 1024)), int(os.environ.get('SWEEP_W', 1280))
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 st = torch.cuda.current_stream().cuda_stream
-pool = [torch.from_numpy(synth.bottle_batch(n, h, w, start_index=100 * i)).cuda() for i in range(8)]
+npool = int(os.environ.get('SWEEP_POOL', 8))
+_distinct = min(n, 8)
+_base = [synth.bottle_batch(_distinct, h, w, start_index=100 * i) for i in range(npool)]
+pool = [torch.from_numpy(np.ascontiguousarray(np.resize(b, (n, h, w)))).cuda() for b in _base]
 det = hc.Detector(0); det.set_stream(st)
 comp = os.environ.get('SWEEP_COMPRESS', '1') == '1'
 nout = int(os.environ.get('SWEEP_OUTS', str(det.pipeline_depth())))
@@ -15,7 +18,10 @@ outs = [(det.device_alloc((n, h, w), np.uint8, comp), det.device_alloc((n, h, w)
 print('outputs compressed:', outs[0][0].compressed, outs[0][1].compressed)
 mk = int(os.environ.get('SWEEP_MORPH', '0'))
 params = hc.make_params(morph_open_k=mk, morph_close_k=mk) if mk else None
-def step(i): det.enqueue_device(pool[i % 8].data_ptr(), n, h, w, 1, params, outs[i % nout][0].data_ptr(), outs[i % nout][1].data_ptr())
+if os.environ.get('SWEEP_GAUSS'):
+    gk, gs = os.environ['SWEEP_GAUSS'].split(',')
+    params = hc.make_params(blur_mode=hc._abi.HV_BLUR_GAUSSIAN, blur_ksize=int(gk), gauss_sigma=float(gs))
+def step(i): det.enqueue_device(pool[i % npool].data_ptr(), n, h, w, 1, params, outs[i % nout][0].data_ptr(), outs[i % nout][1].data_ptr())
 for i in range(10): step(i)
 torch.cuda.synchronize()
 best = 1e9; tot = 0
