@@ -33,6 +33,7 @@ hv::Tunables read_tunables() {
     t.pipeline_depth = env_int("HV_PIPELINE_DEPTH", t.pipeline_depth, 2, 8);
     t.k1_ctas_per_sm = env_int("HV_K1_CTAS_PER_SM", t.k1_ctas_per_sm, 1, 5);
     t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
+    t.ccl_small_max_tiles = env_int("HV_CCL_SMALL_MAX_TILES", t.ccl_small_max_tiles, 0, 1 << 30);
     t.k1_stages_coresident = env_int("HV_K1_STAGES", t.k1_stages_coresident, 2, 3);
     t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
@@ -641,6 +642,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                              (size_t)n * ((h + 31) / 32) * ((w + 127) / 128) <= 16384;
     bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !tun.ccl_big;
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
+    // Long kernels (many tiles per launch) do not need the gapless chain -- launch gaps and the drain of the per-frame kernel
+    // are a small part of the step -- and K1 is faster with all its CTAs: the big build behind a full-occupancy K1.
+    // Measured with open + close 3x3 folded into K1: 64 x 5 MP 466 -> 428 us per step; 25 x 1.3 MP 50.6 (small) vs 53.9 us;
+    // plain pipeline on 1.3 MP frames: 250 frames 519 -> 415 us, 100 frames 172 vs 174, 64 frames 107 (small) vs 115.
+    if ((size_t)n * ((h + 31) / 32) * ((w + 127) / 128) > (size_t)tun.ccl_small_max_tiles) ccl_small = false;
     // resident K1 CTAs per SM (0 = the kernel's default, 5).  Next to the small CCL build: 3.  Four would fit beside one CTA
     // of it, but those CTAs often land two to an SM, and two of them leave room for two K1 CTAs whatever K1 asked for --
     // with three the loss is one CTA instead of two (measured in one call: 41.9 us per step with 4, 41.1 with 3, although

@@ -130,6 +130,7 @@ struct Tunables {
     int k1_prefetch = 0;          // HV_K1_PREFETCH: L2 tensor prefetch distance in tiles (0 = off)
     int k1_claim_ahead = 0;       // HV_K1_CLAIM_AHEAD
     int k1_wait_hint_ns = 10000000;  // HV_K1_WAIT_HINT_NS
+    int ccl_small_max_tiles = 32768;  // HV_CCL_SMALL_MAX_TILES: batches with more 128x32 tiles use the big per-frame CCL build
     int morph_tiles_per_sm = 2;   // HV_MORPH_TILES_PER_SM
     int phase_frame = 0;          // HV_PHASE_FRAME (with HV_FLAG_PHASE_TIMING)
     bool k1_static = false;       // HV_K1_STATIC
