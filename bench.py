@@ -209,15 +209,18 @@ def workload_config(args, world: int) -> dict:
             "params": "reference defaults min_size=10 max_size=3000 threshold=25"}
 
 
+# the sources of the two kernels whose DRAM traffic profiles/traffic.json records (K1 and the per-frame CCL kernel)
+TRAFFIC_SOURCES = ("expand_tile.cuh", "hv_common.cuh", "k_ccl_frame.cu", "k_preprocess.cu", "score_device.cuh")
+
+
 def csrc_sha16() -> str:
     """Fingerprint of the kernel sources: the ncu-measured DRAM traffic in profiles/ is only quoted for the code it was
     captured from."""
     import hashlib
     hsh = hashlib.sha256()
     d = os.path.join(PKG, "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            hsh.update(open(os.path.join(d, f), "rb").read())
+    for f in TRAFFIC_SOURCES:
+        hsh.update(open(os.path.join(d, f), "rb").read())
     return hsh.hexdigest()[:16]
 
 
