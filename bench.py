@@ -213,6 +213,81 @@ def workload_config(args, world: int) -> dict:
 TRAFFIC_SOURCES = ("expand_tile.cuh", "hv_common.cuh", "k_ccl_frame.cu", "k_preprocess.cu", "score_device.cuh")
 
 
+def peak_gbs() -> float:
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def other_configs(hc, synth, torch, stream, peak, skip_parity):
+    """BASELINE.json configs[2] and [3] at their frame sizes, device-resident, with the streaming loop of the headline
+    (enqueue + fetch of the batch depth-1 back).  Batches are smaller than the configs' 256 / full-line counts to keep the
+    default run short; frac = 6 B/px x pixels / time / measured HBM peak."""
+    from oracle import oracle as O
+    out = {}
+    G = hc._abi.HV_BLUR_GAUSSIAN
+    cases = [("c2_5mp_box", (64, 2048, 2448), hc.make_params(), {}, "bottle"),
+             ("c2_5mp_gauss_k5", (64, 2048, 2448), hc.make_params(blur_mode=G, blur_ksize=5, gauss_sigma=0.0), dict(gauss_ksize=5, gauss_sigma=0.0), "bottle"),
+             ("c2_5mp_gauss_k15_s3", (64, 2048, 2448), hc.make_params(blur_mode=G, blur_ksize=15, gauss_sigma=3.0), dict(gauss_ksize=15, gauss_sigma=3.0), "bottle"),
+             ("c2_5mp_open_close_3", (64, 2048, 2448), hc.make_params(morph_open_k=3, morph_close_k=3), dict(morph_open_k=3, morph_close_k=3), "bottle"),
+             ("c2_5mp_open_close_15", (64, 2048, 2448), hc.make_params(morph_open_k=15, morph_close_k=15), dict(morph_open_k=15, morph_close_k=15), "bottle"),
+             ("c3_12mp_10k_blobs", (16, 3000, 4096), hc.make_params(), {}, "dense")]
+    cache = {}
+    for name, (n, h, w), prm, okw, kind in cases:
+        key = (kind, n, h, w)
+        if key not in cache:
+            cache.clear()
+            gen = (lambda i: synth.bottle_frame(h, w, 500 + i, contaminants=i % 4)) if kind == "bottle" else \
+                (lambda i: synth.high_contamination_frame(h, w, i))
+            distinct = [gen(i) for i in range(4 if kind == "bottle" else 2)]
+            host = np.stack([distinct[i % len(distinct)] for i in range(n)])
+            cache[key] = (host, torch.from_numpy(host).cuda())
+        host, d_in = cache[key]
+        det = hc.Detector(torch.cuda.current_device(), max_defects_per_frame=512 if kind == "bottle" else 32768)
+        det.set_stream(stream.cuda_stream)
+        depth = det.pipeline_depth()
+        n_out = 2                     # two sets of output planes (the batch that last wrote a set is retired before it is reused)
+        outs = [(det.device_alloc((n, h, w), np.uint8), det.device_alloc((n, h, w), np.int32)) for _ in range(n_out)]
+        res = det.detect_device(d_in.data_ptr(), n, h, w, 1, prm, outs[0][0].ptr, outs[0][1].ptr)
+        ok = None
+        if not skip_parity:
+            ref = O.detect_contamination(host[0][:, :, None], **okw)
+            ok = bool(np.array_equal(outs[0][0].get(0, 1)[0], ref.mask) and np.array_equal(outs[0][1].get(0, 1)[0], ref.labels) and
+                      [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in res.defects_of(0)] ==
+                      [(d["position"], d["size"], d["confidence"]) for d in ref.defects])
+            if not ok:
+                raise SystemExit(f"{name}: results differ from the oracle; refusing to report a number")
+        tickets = []
+
+        def step(i):
+            tickets.append(det.enqueue_device(d_in.data_ptr(), n, h, w, 1, prm, outs[i % n_out][0].ptr, outs[i % n_out][1].ptr))
+            if len(tickets) >= n_out:
+                det.fetch(tickets.pop(0), n)
+        for i in range(2 * depth):
+            step(i)
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evs[0].record(stream)
+        for r in range(3):
+            for i in range(5):
+                step(i)
+            evs[r + 1].record(stream)
+        while tickets:
+            det.fetch(tickets.pop(0), n)
+        torch.cuda.synchronize()
+        ms = float(np.median([evs[r].elapsed_time(evs[r + 1]) for r in range(3)])) / 5
+        gbs = ALG_BYTES_PER_PX * n * h * w / (ms * 1e-3) / 1e9
+        out[name] = {"batch": f"{n} x {w}x{h}", "ms_per_step": ms, "frames_per_s": n / (ms * 1e-3), "achieved_gbs": gbs,
+                     "frac": gbs / peak, "parity_checked": ok}
+        for a, b in outs:
+            a.free(), b.free()
+        det.close()
+    cache.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
 def csrc_sha16() -> str:
     """Fingerprint of the kernel sources: the ncu-measured DRAM traffic in profiles/ is only quoted for the code it was
     captured from."""
@@ -526,6 +601,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         morph = {"ms_per_step": float(t.item()) / K, "windows": len(wm), "launches_per_step": lm / (len(wm) * K),
                  "parity_checked": bool(okm) and not args.skip_parity}
 
+    # ---- the other BASELINE configs at their stated frame sizes (rank 0 at N = 1): parity of one frame against the oracle,
+    #      then a short timed run (3 windows of 5 steps, median) -- the full tables are tools/bench_configs.py's ----------------
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(hc, synth, torch, stream, peak_gbs(), args.skip_parity)
+
     # ---- end to end: pinned host frames -> H2D -> pipeline -> D2H of the results, through hv_submit / hv_wait -----------------
     n_pin = min(pool_n, max(args.slots, 3))
     pins = []
@@ -594,12 +675,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     k1 = prof["preprocess_mask"]
     k1_ms = k1["ms"] / max(k1["launches"], 1)
     alg_bytes = ALG_BYTES_PER_PX * h * w * nf
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        pass
+    peak = peak_gbs()
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) \
+        else "fallback (B200_PROFILING.md)"
     # DRAM bytes per launch from the ncu --set full capture of THIS code (profiles/traffic.json carries the fingerprint of
     # the kernel sources it was taken from; a capture of other code is not quoted)
     traffic, traffic_note = None, "no ncu capture of the current kernel sources under profiles/"
@@ -682,6 +760,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     }
     if nocoll is not None:
         line["ms_per_step_no_collective"] = nocoll
+    if other is not None:
+        line["other_configs"] = other
     if morph is not None:
         m_ach = alg_bytes / (morph["ms_per_step"] * 1e-3) / 1e9
         line["roofline_morph"] = {"pipeline": "blur -> adaptive threshold -> open 3x3 -> close 3x3 -> CCL -> stats -> reject "
@@ -711,6 +791,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--repeats", type=int, default=15, help="timed windows of --steps steps, back to back; the median counts")
     ap.add_argument("--no-morph", action="store_true", help="skip the roofline_morph sub-record")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other_configs sub-record (BASELINE configs[2], [3])")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=25)
     ap.add_argument("--height", type=int, default=1024)
