@@ -1824,9 +1824,21 @@ void hv_pydet_params_default(hv_pydet_params *p) {
     p->morph_close_k = 3;          // :87
 }
 
-hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
-                                    const hv_pydet_params *params, uint8_t *gray, uint8_t *blurred, uint8_t *binary,
-                                    int32_t *labels8, hv_blob *comps, size_t cap, size_t *n_comps) {
+}  // extern "C"
+
+namespace {
+
+struct PyStages {
+    BatchView b{};           // slot 0: bits / mask / labels (8-connected) / blobs of the final mask
+    const uint8_t *d_gray = nullptr;
+    const uint8_t *d_img = nullptr;
+    uint32_t ncomp = 0;
+};
+
+// gray -> blur -> adaptive Gaussian threshold -> open / close -> 8-connected components, everything left on the device in
+// slot 0 (the stream is synchronised on return)
+hv_status pydet_run_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, const hv_pydet_params *params,
+                           PyStages *out) {
     if (!ctx || !img || h <= 0 || w <= 0) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "bad argument");
     if (c != 1 && c != 3) return fail(ctx, HV_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: expected 3D array");
     if ((long long)h * w >= 2147483647LL) return fail(ctx, HV_ERR_INVALID_ARGUMENT, "frame too large");
@@ -1895,17 +1907,216 @@ hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, 
     if (rs != HV_OK) return rs;
     uint32_t ncomp = 0;
     HV_TRY_CUDA(ctx, cudaMemcpyAsync(&ncomp, b.ncomp, sizeof(ncomp), cudaMemcpyDeviceToHost, st));
-    if (gray) HV_TRY_CUDA(ctx, cudaMemcpyAsync(gray, d_gray, px, cudaMemcpyDeviceToHost, st));
-    if (blurred) HV_TRY_CUDA(ctx, cudaMemcpyAsync(blurred, s.blur.p, px, cudaMemcpyDeviceToHost, st));
-    if (binary) HV_TRY_CUDA(ctx, cudaMemcpyAsync(binary, b.mask, px, cudaMemcpyDeviceToHost, st));
-    if (labels8) HV_TRY_CUDA(ctx, cudaMemcpyAsync(labels8, b.labels, px * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
     s.has_batch = false;
-    const size_t ncopy = std::min<size_t>(std::min<size_t>(ncomp, cap), (size_t)b.blob_cap);
-    if (comps && ncopy) HV_TRY_CUDA(ctx, cudaMemcpy(comps, b.blobs, sizeof(hv_blob) * ncopy, cudaMemcpyDeviceToHost));
+    if (ncomp > (uint32_t)b.blob_cap) return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more components than max_blobs_per_frame");
+    out->b = b;
+    out->d_gray = d_gray;
+    out->d_img = s.in.p;
+    out->ncomp = ncomp;
+    return HV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                    const hv_pydet_params *params, uint8_t *gray, uint8_t *blurred, uint8_t *binary,
+                                    int32_t *labels8, hv_blob *comps, size_t cap, size_t *n_comps) {
+    PyStages ps;
+    hv_status rs = pydet_run_stages(ctx, img, h, w, c, params, &ps);
+    if (rs != HV_OK) return rs;
+    Slot &s = ctx->slots[0];
+    cudaStream_t st = s.stream;
+    const size_t px = (size_t)h * w;
+    if (gray) HV_TRY_CUDA(ctx, cudaMemcpyAsync(gray, ps.d_gray, px, cudaMemcpyDeviceToHost, st));
+    if (blurred) HV_TRY_CUDA(ctx, cudaMemcpyAsync(blurred, s.blur.p, px, cudaMemcpyDeviceToHost, st));
+    if (binary) HV_TRY_CUDA(ctx, cudaMemcpyAsync(binary, ps.b.mask, px, cudaMemcpyDeviceToHost, st));
+    if (labels8) HV_TRY_CUDA(ctx, cudaMemcpyAsync(labels8, ps.b.labels, px * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const size_t ncopy = std::min<size_t>(ps.ncomp, cap);
+    if (comps && ncopy) HV_TRY_CUDA(ctx, cudaMemcpyAsync(comps, ps.b.blobs, sizeof(hv_blob) * ncopy, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
     if (n_comps) *n_comps = ncopy;
-    if (ncomp > (uint32_t)b.blob_cap || (comps && ncomp > cap))
-        return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more components than max_blobs_per_frame / cap");
+    if (comps && ps.ncomp > cap) return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more components than cap");
+    return HV_OK;
+}
+
+void hv_pydet_score_params_default(hv_pydet_score_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->min_size = 10.0;         // contamination_detector.py:26
+    p->max_size = 3000.0;       // :29
+    p->min_confidence = 0.25;   // :35
+    p->use_color = 1;           // :38
+}
+
+hv_status hv_python_detect(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c, const hv_pydet_params *stage_params,
+                           const hv_pydet_score_params *score_params, hv_pydefect *defects, size_t cap, size_t *n_defects,
+                           size_t *n_contours) {
+    if (n_defects) *n_defects = 0;
+    if (n_contours) *n_contours = 0;
+    hv_pydet_score_params sp;
+    if (score_params)
+        sp = *score_params;
+    else
+        hv_pydet_score_params_default(&sp);
+    PyStages ps;
+    hv_status rs = pydet_run_stages(ctx, img, h, w, c, stage_params, &ps);
+    if (rs != HV_OK) return rs;
+    const int n8 = (int)ps.ncomp;
+    if (n8 == 0) return HV_OK;
+    Slot &s0 = ctx->slots[0];
+    Slot &s1 = ctx->slots[1];
+    if (retire_slot(ctx, s1) != HV_OK) return HV_ERR_CUDA;
+    cudaStream_t st = s0.stream;
+    const size_t px = (size_t)h * w;
+    // 4-connected components of the background (complement of the final mask), in the second scratch set
+    rs = reserve_slot(ctx, s1, 1, h, w, false, 0, false, false, false, true, true);
+    if (rs != HV_OK) return rs;
+    s1.has_batch = false;
+    BatchView b4{};
+    fill_view(ctx, s1, b4, h, w);
+    b4.rowflags = s1.rowflags.p, b4.tiles_x = (w + 127) / 128, b4.rf_stride = (size_t)((h + 31) / 32) * b4.tiles_x * 32;
+    HV_TRY_CUDA(ctx, launch_invert_bits(ps.b.bits, b4.bits, h, b4.ww, w, st));
+    HV_TRY_CUDA(ctx, launch_bits_to_mask_labels(b4, st));
+    ctx->launches += 2;
+    rs = run_ccl_only(ctx, s1, st, b4);
+    if (rs != HV_OK) return rs;
+    uint32_t n4u = 0;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(&n4u, b4.ncomp, sizeof(n4u), cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n4u > (uint32_t)b4.blob_cap) return fail(ctx, HV_ERR_CAPACITY, "capacity exceeded: more background regions than max_blobs_per_frame");
+    const int n4 = (int)n4u;
+    // device scratch: first8 | first4 | above8 | above4 | root8 | root4 | ext | sums | trace
+    const size_t o_first8 = 0, o_first4 = o_first8 + 4u * n8, o_above8 = o_first4 + 4u * n4, o_above4 = o_above8 + 4u * n8,
+                 o_root8 = o_above4 + 4u * n4, o_root4 = o_root8 + 4u * n8, o_ext = o_root4 + 4u * n4,
+                 o_sums = (o_ext + 4u * n8 + 15) & ~(size_t)15, o_trace = o_sums + 80u * n8, o_end = o_trace + 32u * n8;
+    HV_TRY_CUDA(ctx, ctx->u_c.reserve(o_end + 64));
+    uint8_t *base = ctx->u_c.p;
+    auto u32p = [&](size_t o) { return reinterpret_cast<uint32_t *>(base + o); };
+    auto i32p = [&](size_t o) { return reinterpret_cast<int32_t *>(base + o); };
+    HV_TRY_CUDA(ctx, cudaMemsetAsync(base + o_first8, 0xff, 4u * (n8 + n4), st));
+    HV_TRY_CUDA(ctx, launch_first_pixel(ps.b.labels, h, w, u32p(o_first8), st));
+    HV_TRY_CUDA(ctx, launch_first_pixel(b4.labels, h, w, u32p(o_first4), st));
+    HV_TRY_CUDA(ctx, launch_label_above(u32p(o_first8), n8, w, b4.labels, i32p(o_above8), st));
+    HV_TRY_CUDA(ctx, launch_label_above(u32p(o_first4), n4, w, ps.b.labels, i32p(o_above4), st));
+    ctx->launches += 4;
+    std::vector<hv_blob> comps8(n8), comps4(n4);
+    std::vector<uint32_t> first8(n8), first4(n4);
+    std::vector<int32_t> above8(n8), above4(n4);
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(comps8.data(), ps.b.blobs, sizeof(hv_blob) * n8, cudaMemcpyDeviceToHost, st));
+    if (n4) HV_TRY_CUDA(ctx, cudaMemcpyAsync(comps4.data(), b4.blobs, sizeof(hv_blob) * n4, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(first8.data(), base + o_first8, 4u * n8, cudaMemcpyDeviceToHost, st));
+    if (n4) HV_TRY_CUDA(ctx, cudaMemcpyAsync(first4.data(), base + o_first4, 4u * n4, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(above8.data(), base + o_above8, 4u * n8, cudaMemcpyDeviceToHost, st));
+    if (n4) HV_TRY_CUDA(ctx, cudaMemcpyAsync(above4.data(), base + o_above4, 4u * n4, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    // Enclosure: a background region that does not reach the image border is a hole of the foreground component above its
+    // first pixel; a foreground component whose first pixel lies below a hole is nested in that hole's owner.  Everything
+    // that encloses a component has an earlier first pixel, so one pass in raster order of the first pixels resolves it.
+    std::vector<char> border4(n4);
+    for (int j = 0; j < n4; j++)
+        border4[j] = comps4[j].xmin == 0 || comps4[j].ymin == 0 || comps4[j].xmax == (uint32_t)w - 1 || comps4[j].ymax == (uint32_t)h - 1;
+    std::vector<int32_t> root8(n8, 0), root4(n4, 0);
+    {
+        int i8 = 0, i4 = 0;  // labels of both planes are numbered in raster order of their first pixels
+        while (i8 < n8 || i4 < n4) {
+            const bool take8 = i4 >= n4 || (i8 < n8 && first8[i8] < first4[i4]);
+            if (take8) {
+                const int a = above8[i8];  // background label above the first pixel, 0 in the first row
+                root8[i8] = (a <= 0 || border4[a - 1]) ? i8 + 1 : root4[a - 1];
+                if (root8[i8] == 0) root8[i8] = i8 + 1;
+                i8++;
+            } else {
+                const int a = above4[i4];  // foreground label above the hole's first pixel
+                root4[i4] = (border4[i4] || a <= 0) ? 0 : root8[a - 1];
+                i4++;
+            }
+        }
+    }
+    std::vector<int32_t> ext;
+    for (int k = 0; k < n8; k++)
+        if (root8[k] == k + 1) ext.push_back(k + 1);
+    const int n_ext = (int)ext.size();
+    if (n_contours) *n_contours = (size_t)n_ext;
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(base + o_root8, root8.data(), 4u * n8, cudaMemcpyHostToDevice, st));
+    if (n4) HV_TRY_CUDA(ctx, cudaMemcpyAsync(base + o_root4, root4.data(), 4u * n4, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(base + o_ext, ext.data(), 4u * n_ext, cudaMemcpyHostToDevice, st));
+    HV_TRY_CUDA(ctx, launch_region_sums(i32p(o_ext), n_ext, ps.b.blobs, ps.b.labels, b4.labels, i32p(o_root8), i32p(o_root4), h, w,
+                                        ps.d_gray, c == 3 ? ps.d_img : nullptr, base + o_sums, st));
+    HV_TRY_CUDA(ctx, launch_trace_contours(i32p(o_ext), n_ext, u32p(o_first8), ps.b.labels, b4.labels, i32p(o_root8), i32p(o_root4), h,
+                                           w, base + o_trace, st));
+    ctx->launches += 2;
+    struct Sums {
+        unsigned long long cnt_in, cnt_out, gray_in, gray_out, ch_in[3], ch_out[3];
+    };
+    struct Trace {
+        double a00, a10, a01;
+        uint32_t chain_len, reserved;
+    };
+    static_assert(sizeof(Sums) == 80 && sizeof(Trace) == 32, "device records");
+    std::vector<Sums> sums(n_ext);
+    std::vector<Trace> tr(n_ext);
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(sums.data(), base + o_sums, sizeof(Sums) * n_ext, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaMemcpyAsync(tr.data(), base + o_trace, sizeof(Trace) * n_ext, cudaMemcpyDeviceToHost, st));
+    HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
+    // contamination_detector.py:96-176, in cv2.findContours' order (the component found last comes first), in the
+    // reference's expression order (doubles, no contraction)
+    size_t nd = 0;
+    hv_status rc = HV_OK;
+    for (int e = n_ext - 1; e >= 0; e--) {
+        const hv_blob &q = comps8[ext[e] - 1];
+        const Trace &t = tr[e];
+        const double area = std::fabs(t.a00 * 0.5);  // cv2.contourArea
+        if (area < sp.min_size || area > sp.max_size) continue;
+        const int bx = (int)q.xmin, by = (int)q.ymin, bw = (int)(q.xmax - q.xmin + 1), bh = (int)(q.ymax - q.ymin + 1);
+        // cv2.moments of the contour: m00 = a00 * (+-0.5), m10 = a10 * (+-1/6), m01 = a01 * (+-1/6)
+        double m00 = 0, m10 = 0, m01 = 0;
+        if (std::fabs(t.a00) > 1.1920928955078125e-07) {
+            const double h2 = t.a00 > 0 ? 0.5 : -0.5, h6 = t.a00 > 0 ? 0.16666666666666666666666666666667 : -0.16666666666666666666666666666667;
+            m00 = t.a00 * h2, m10 = t.a10 * h6, m01 = t.a01 * h6;
+        }
+        if (!(m00 > 0)) continue;
+        const int cx = (int)(m10 / m00), cy = (int)(m01 / m00);
+        const Sums &u = sums[e];
+        const double background = u.cnt_out ? (double)u.gray_out / (double)u.cnt_out : 127.0;
+        const double foreground = u.cnt_in ? (double)u.gray_in / (double)u.cnt_in : 127.0;
+        const double intensity_diff = std::fabs(background - foreground);
+        const double intensity_score = std::min(1.0, intensity_diff / 30.0);
+        const long long rect_area = (long long)bw * bh;
+        const double area_ratio = rect_area > 0 ? area / (double)rect_area : 0.0;
+        const double shape_score = 1.0 - area_ratio;
+        double color_score = 0.5;
+        if (sp.use_color && c == 3) {
+            double color_diff = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const double fg = u.cnt_in ? (double)u.ch_in[k] / (double)u.cnt_in : 127.0;
+                const double bg = u.cnt_out ? (double)u.ch_out[k] / (double)u.cnt_out : 127.0;
+                const double d = std::fabs(fg - bg);
+                if (k == 0 || d > color_diff) color_diff = d;
+            }
+            color_score = std::min(1.0, color_diff / 30.0);
+        }
+        const double t1 = intensity_score * 0.5, t2 = shape_score * 0.2, t3 = color_score * 0.3;
+        const double confidence = (t1 + t2) + t3;
+        if (!(confidence >= sp.min_confidence)) continue;
+        if (nd < cap && defects) {
+            hv_pydefect &d = defects[nd];
+            d.x = cx, d.y = cy;
+            d.size = area, d.confidence = confidence;
+            d.intensity_diff = intensity_diff, d.shape_score = shape_score, d.color_score = color_score;
+            d.bx = bx, d.by = by, d.bw = bw, d.bh = bh;
+            d.label8 = (uint32_t)ext[e];
+            d.chain_len = t.chain_len;
+        } else {
+            rc = HV_ERR_CAPACITY;
+        }
+        nd++;
+    }
+    if (n_defects) *n_defects = std::min(nd, cap);
+    if (rc != HV_OK) return fail(ctx, rc, "capacity exceeded: defects array too small");
+    (void)px;
     return HV_OK;
 }
 

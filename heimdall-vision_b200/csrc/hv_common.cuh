@@ -202,6 +202,16 @@ cudaError_t launch_yuyv(const uint8_t *d_src, int n, int h, int w, bool to_gray,
 cudaError_t launch_gray_bgr_cv(const uint8_t *d_img, int h, int w, uint8_t *d_gray, cudaStream_t s);
 cudaError_t launch_adaptive_gaussian(const uint8_t *d_src, int h, int w, const float *k_host, int ksize, int idelta,
                                      float *d_rows, uint8_t *d_mask, cudaStream_t s);
+cudaError_t launch_invert_bits(const uint32_t *in, uint32_t *out, int h, int ww, int w, cudaStream_t s);
+cudaError_t launch_first_pixel(const int32_t *labels, int h, int w, uint32_t *first, cudaStream_t s);
+cudaError_t launch_label_above(const uint32_t *first, int n, int w, const int32_t *other, int32_t *above, cudaStream_t s);
+// out: n_ext records of 14 x u64 {cnt_in, cnt_out, gray_in, gray_out, ch_in[3], ch_out[3]} (k_pydet.cu RegionSums)
+cudaError_t launch_region_sums(const int32_t *ext, int n_ext, const hv_blob *comps8, const int32_t *l8, const int32_t *l4,
+                               const int32_t *root8, const int32_t *root4, int h, int w, const uint8_t *gray, const uint8_t *bgr,
+                               void *out, cudaStream_t s);
+// out: n_ext records {double a00, a10, a01; u32 chain_len, reserved} (k_pydet.cu TraceOut)
+cudaError_t launch_trace_contours(const int32_t *ext, int n_ext, const uint32_t *first8, const int32_t *l8, const int32_t *l4,
+                                  const int32_t *root8, const int32_t *root4, int h, int w, void *out, cudaStream_t s);
 cudaError_t launch_overlays(const hv_overlay *d_items, int n, int h, int w, uint8_t *d_img, unsigned int *d_owner, cudaStream_t s);
 cudaError_t launch_collect_contours(const BatchView &b, double min_area, double max_area, hv_contour *d_out,
                                     uint32_t *d_count, int cap, cudaStream_t s);

@@ -117,6 +117,18 @@ class hv_pydet_params(C.Structure):
                 ("morph_open_k", C.c_int32), ("morph_close_k", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class hv_pydet_score_params(C.Structure):
+    _fields_ = [("min_size", C.c_double), ("max_size", C.c_double), ("min_confidence", C.c_double),
+                ("use_color", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class hv_pydefect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("size", C.c_double), ("confidence", C.c_double),
+                ("intensity_diff", C.c_double), ("shape_score", C.c_double), ("color_score", C.c_double),
+                ("bx", C.c_int32), ("by", C.c_int32), ("bw", C.c_int32), ("bh", C.c_int32),
+                ("label8", C.c_uint32), ("chain_len", C.c_uint32)]
+
+
 class hv_inspection_record(C.Structure):
     _fields_ = [("sequence", C.c_uint64), ("timestamp", C.c_double), ("processing_time", C.c_double),
                 ("success", C.c_uint32), ("has_defects", C.c_uint32), ("defect_count", C.c_uint32),
@@ -190,6 +202,9 @@ PROTOTYPES = {
     "hv_pydet_params_default": (None, [_P(hv_pydet_params)]),
     "hv_python_detector_stages": (_i32, [_vp, _vp, _i32, _i32, _i32, _P(hv_pydet_params), _vp, _vp, _vp, _vp, _P(hv_blob), _sz,
                                          _P(_sz)]),
+    "hv_pydet_score_params_default": (None, [_P(hv_pydet_score_params)]),
+    "hv_python_detect": (_i32, [_vp, _vp, _i32, _i32, _i32, _P(hv_pydet_params), _P(hv_pydet_score_params), _P(hv_pydefect), _sz,
+                                _P(_sz), _P(_sz)]),
     "hv_export_results": (_i32, [_P(hv_frame_result), _i32, _f64, _f64, C.c_uint64, _P(hv_inspection_record),
                                  _P(hv_dashboard_stats)]),
     "hv_draw_overlays": (_i32, [_vp, _vp, _i32, _i32, _P(hv_overlay), _i32]),

@@ -373,6 +373,33 @@ class Detector:
         out["components"] = comps[:n.value]
         return out
 
+    def python_detect(self, img: np.ndarray, min_size: float = 10.0, max_size: float = 3000.0,
+                      contrast_threshold: float = 15.0, min_confidence: float = 0.25, use_color: bool = True) -> List[dict]:
+        """`ContaminationDetector.detect` of the reference's Python path (contamination_detector.py:44-216; defaults :26-38)
+        on the GPU (hv_python_detect): a list of the reference's `Defect.to_dict()` dictionaries -- type, position (x, y),
+        size (cv2.contourArea), confidence, intensity_diff, shape_score, color_score, bounding_box -- in cv2.findContours'
+        order.  `img`: (h, w) gray or (h, w, 3) BGR uint8.  The metadata entry "contour" is not produced."""
+        a = np.ascontiguousarray(img, np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        h, w, c = a.shape
+        sp = A.hv_pydet_params()
+        _lib.hv_pydet_params_default(C.byref(sp))
+        sp.contrast_threshold = float(contrast_threshold)
+        qp = A.hv_pydet_score_params()
+        _lib.hv_pydet_score_params_default(C.byref(qp))
+        qp.min_size, qp.max_size, qp.min_confidence, qp.use_color = float(min_size), float(max_size), float(min_confidence), int(use_color)
+        cap = 4096
+        out = (A.hv_pydefect * cap)()
+        n, nc = C.c_size_t(0), C.c_size_t(0)
+        with self._lock:
+            st = _lib.hv_python_detect(self._ctx, a.ctypes.data, h, w, c, C.byref(sp), C.byref(qp), out, cap, C.byref(n), C.byref(nc))
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
+        return [{"type": "contamination", "position": (int(d.x), int(d.y)), "size": float(d.size), "confidence": float(d.confidence),
+                 "intensity_diff": float(d.intensity_diff), "shape_score": float(d.shape_score), "color_score": float(d.color_score),
+                 "bounding_box": (int(d.bx), int(d.by), int(d.bw), int(d.bh))} for d in out[:n.value]]
+
     def find_contours(self, img: np.ndarray, min_area: float, max_area: float, want_labels: bool = True):
         h, w, c = img.shape
         cap = h * w // 2 + 1

@@ -401,9 +401,8 @@ HV_API hv_status hv_process_image(hv_ctx *ctx, const uint8_t *img, int32_t h, in
  *            coordinate sums) and their label plane: the regions whose outer borders cv2.findContours(RETR_EXTERNAL)
  *            (:90) traces -- RETR_EXTERNAL additionally drops components that lie inside a hole of another one.
  * gray / blurred / binary are bit-exact with opencv-python 4.13 on the committed golden vectors (the float32 mean of
- * adaptiveThreshold follows OpenCV's AVX2/FMA summation order, see k_pydet.cu).  NOT reproduced: the contour polygons and
- * what the detector derives from them (cv2.contourArea, cv2.moments, the filled-polygon masks behind the intensity and
- * colour scores, :96-160) -- polygon quantities of traced borders, not pixel counts.  Any output pointer may be NULL. */
+ * adaptiveThreshold follows OpenCV's AVX2/FMA summation order, see k_pydet.cu).  The contour quantities and the scores:
+ * hv_python_detect below.  Any output pointer may be NULL. */
 typedef struct {
     double contrast_threshold; /* C (contamination_detector.py:36 default 25) */
     int32_t blur_ksize;        /* 5 */
@@ -417,6 +416,35 @@ HV_API hv_status hv_python_detector_stages(hv_ctx *ctx, const uint8_t *img, int3
                                            const hv_pydet_params *params, uint8_t *gray, uint8_t *blurred,
                                            uint8_t *binary, int32_t *labels8, hv_blob *comps, size_t cap,
                                            size_t *n_comps);
+
+/* The whole `ContaminationDetector.detect` (contamination_detector.py:44-216) on top of those stages: the external contours'
+ * polygon area (cv2.contourArea), bounding rectangle, centre from the polygon moments (int(m10/m00), int(m01/m00)), the
+ * filled-contour masks behind the intensity and colour scores, confidence = 0.5 intensity + 0.2 shape + 0.3 colour, the size
+ * and confidence filters, in cv2.findContours' order.  How: the outer border of an 8-connected component with everything it
+ * encloses is traced on the device (Moore tracing = cv2's CHAIN_APPROX_NONE chain; the moment accumulators are integer-valued
+ * doubles, so area and moments are bit-identical with cv2's); cv2.drawContours(..., -1) of that contour is the component plus
+ * the regions of its complement that do not reach the image border (checked against cv2 on thousands of random contours,
+ * tests/golden/make_golden.py); RETR_EXTERNAL's nesting rule comes from the 4-connected components of the background.
+ * position = (x, y) as the Python `Defect` has it.  Not returned: metadata["contour"] (the CHAIN_APPROX_SIMPLE point list). */
+typedef struct {
+    double min_size, max_size;   /* contour-area limits (contamination_detector.py:26-30: 10, 3000) */
+    double min_confidence;       /* :36 default 0.25; heimdall/rust_bridge.py:148 passes 0.3 */
+    int32_t use_color;           /* :38 default 1; only with a 3-channel image */
+    int32_t reserved[3];
+} hv_pydet_score_params;
+typedef struct {
+    int32_t x, y;                /* Defect.position = (cx, cy) */
+    double size;                 /* cv2.contourArea */
+    double confidence;
+    double intensity_diff, shape_score, color_score; /* metadata */
+    int32_t bx, by, bw, bh;      /* metadata["bounding_box"] = cv2.boundingRect */
+    uint32_t label8;             /* 1-based label of the component in the labels8 plane of hv_python_detector_stages */
+    uint32_t chain_len;          /* points of the CHAIN_APPROX_NONE contour */
+} hv_pydefect;
+HV_API void hv_pydet_score_params_default(hv_pydet_score_params *p);
+HV_API hv_status hv_python_detect(hv_ctx *ctx, const uint8_t *img, int32_t h, int32_t w, int32_t c,
+                                  const hv_pydet_params *stage_params, const hv_pydet_score_params *score_params,
+                                  hv_pydefect *defects, size_t cap, size_t *n_defects, size_t *n_contours);
 
 /* ---- result side (next-row N4) ---------------------------------------------------------------------------------
  * What the reference does with a frame's defect list once the detector has returned.

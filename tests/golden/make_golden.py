@@ -157,7 +157,53 @@ def python_detector():
         print(name, "components", len(d[f"{name}_stats8"]), "external contours", len(d[f"{name}_ext_rects"]))
 
 
+def python_detect():
+    """reference_python_detect.json (next-row N3): results of the UNMODIFIED reference detector
+    (heimdall/detectors/contamination_detector.py `ContaminationDetector.detect`, imported from /root/reference) on seeded
+    frames that do contain contamination it finds: every defect's to_dict() without the contour point list."""
+    sys.path.insert(0, "/root/reference")
+    import logging
+    logging.disable(logging.CRITICAL)
+    from heimdall.detectors.contamination_detector import ContaminationDetector
+    rng = np.random.default_rng(20261022)
+    frames = {}
+    blem = synth.near_threshold_frame(200, 260, 7, spots=8)
+    frames["blemish_gray"] = (blem, dict(contrast_threshold=5))
+    frames["blemish_bgr"] = (np.dstack([blem, np.roll(blem, 3, 1), np.roll(blem, 5, 0)]), dict(contrast_threshold=5, min_confidence=0.3))
+    col = np.dstack([synth.bottle_frame(160, 208, 9, contaminants=3), synth.bottle_frame(160, 208, 10, contaminants=1),
+                     synth.bottle_frame(160, 208, 11, contaminants=2)])
+    frames["colour_bgr"] = (col, dict(contrast_threshold=12.7))
+    frames["colour_bgr_nocolor"] = (col, dict(contrast_threshold=12.7, use_color=False, min_contaminant_size=4, max_contaminant_size=500))
+    tex = rng.integers(0, 256, (72, 100, 3), dtype=np.uint8)
+    frames["texture_bgr"] = (tex, dict(contrast_threshold=10, min_contaminant_size=2))
+    rings = np.full((120, 160), 200, np.uint8)   # nested shapes: a ring with an island in its hole, a blob with two holes
+    cv2.circle(rings, (40, 60), 30, 60, 6)
+    cv2.circle(rings, (40, 60), 8, 50, -1)
+    cv2.rectangle(rings, (90, 30), (150, 90), 40, -1)
+    cv2.rectangle(rings, (100, 40), (115, 55), 200, -1)
+    cv2.circle(rings, (135, 72), 7, 210, -1)
+    frames["nested_gray"] = (rings, dict(contrast_threshold=15, max_contaminant_size=100000))
+    out = {}
+    for name, (img, cfg) in frames.items():
+        det = ContaminationDetector(config=cfg)
+        defects = det.detect(img)
+        recs = []
+        for d in defects:
+            dd = d.to_dict()
+            recs.append({"position": [int(v) for v in dd["position"]], "size": float(dd["size"]), "confidence": float(dd["confidence"]),
+                         "intensity_diff": float(dd["intensity_diff"]), "shape_score": float(dd["shape_score"]),
+                         "color_score": float(dd["color_score"]), "bounding_box": [int(v) for v in dd["bounding_box"]]})
+        out[name] = {"config": cfg, "defects": recs}
+        print(name, len(recs), "defects")
+    np.savez_compressed(os.path.join(HERE, "reference_python_detect_frames.npz"), **{k: v[0] for k, v in frames.items()})
+    json.dump(out, open(os.path.join(HERE, "reference_python_detect.json"), "w"), indent=1)
+    logging.disable(logging.NOTSET)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "python_detect":
+        python_detect()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "python_detector":
         python_detector()
         return
@@ -174,6 +220,8 @@ def main():
     morph_pipeline()
     overlays()
     python_detector()
+    if os.path.isdir("/root/reference/heimdall"):
+        python_detect()
     rng = np.random.default_rng(20261018)
     meta = {"opencv": cv2.__version__, "numpy": np.__version__}
 

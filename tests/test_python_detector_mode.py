@@ -64,3 +64,27 @@ def test_eight_connectivity_differs_from_four_on_diagonals():
     if diag.any():
         ys, xs = np.nonzero(diag)
         assert (lab[ys + 1, xs + 1] == lab[ys, xs]).all()
+
+
+REF_CASES = ["blemish_gray", "blemish_bgr", "colour_bgr", "colour_bgr_nocolor", "texture_bgr", "nested_gray"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", REF_CASES)
+def test_python_detect_equals_the_unmodified_reference_detector(detector, golden_dir, case):
+    """hv_python_detect against tests/golden/reference_python_detect.json: what the reference's own
+    `ContaminationDetector.detect` (imported unmodified from /root/reference by tests/golden/make_golden.py) returned for
+    the same frames and configurations -- every defect, in its order, with exact equality of the integer fields and of
+    the doubles (contour area, confidence, the three scores).  Covers gray and BGR input, the colour score on and off,
+    non-default size limits, nested shapes (a ring with an island in its hole: RETR_EXTERNAL keeps the ring only)."""
+    ref = json.load(open(os.path.join(golden_dir, "reference_python_detect.json")))[case]
+    img = np.load(os.path.join(golden_dir, "reference_python_detect_frames.npz"))[case]
+    cfg = ref["config"]
+    got = detector.python_detect(img, cfg.get("min_contaminant_size", 10), cfg.get("max_contaminant_size", 3000),
+                                 cfg.get("contrast_threshold", 15), cfg.get("min_confidence", 0.25), cfg.get("use_color", True))
+    exp = ref["defects"]
+    assert len(exp) > 0
+    assert [list(d["position"]) for d in got] == [d["position"] for d in exp]
+    assert [list(d["bounding_box"]) for d in got] == [d["bounding_box"] for d in exp]
+    for key in ("size", "confidence", "intensity_diff", "shape_score", "color_score"):
+        assert [d[key] for d in got] == [d[key] for d in exp], key
