@@ -19,12 +19,12 @@ from typing import Any, Dict, Optional
 import numpy as np
 
 from . import _abi
-from . import acquisition, batch, camera, detection, processing, results
+from . import acquisition, batch, camera, detection, detectors, processing, results
 from ._abi import HV_PIPELINE_BASIC, HV_PIPELINE_CONTAMINATION
 from .batch import Detector, HeimdallCudaError, default_detector, make_params, with_capacity_retry
 
 __all__ = ["process_image", "detect_contamination", "benchmark_processing", "acquisition", "processing", "detection",
-           "batch", "camera", "results", "Detector", "HeimdallCudaError", "make_params"]
+           "batch", "camera", "results", "detectors", "Detector", "HeimdallCudaError", "make_params"]
 
 __version__ = _abi.lib.hv_version().decode()
 

@@ -88,3 +88,32 @@ def test_python_detect_equals_the_unmodified_reference_detector(detector, golden
     assert [list(d["bounding_box"]) for d in got] == [d["bounding_box"] for d in exp]
     for key in ("size", "confidence", "intensity_diff", "shape_score", "color_score"):
         assert [d[key] for d in got] == [d[key] for d in exp], key
+
+
+def test_detector_mirror_has_the_reference_contract():
+    """heimdall_core.detectors.ContaminationDetector: constructor defaults of contamination_detector.py:26-38 and the
+    detect() / __call__ contract of heimdall/detectors/base.py:41-84 (no GPU needed for this part)."""
+    import inspect
+
+    from heimdall_core import detectors as D
+    d = D.ContaminationDetector()
+    assert (d.name, d.min_contaminant_size, d.max_contaminant_size, d.contrast_threshold, d.min_confidence, d.use_color) == \
+        ("contamination_detector", 10, 3000, 15, 0.25, True)
+    d2 = D.ContaminationDetector(config={"contrast_threshold": 25, "min_confidence": 0.3})   # what rust_bridge.py:143-149 passes
+    assert (d2.contrast_threshold, d2.min_confidence, d2.min_contaminant_size) == (25, 0.3, 10)
+    assert list(inspect.signature(d.detect).parameters) == ["image", "context"]
+    assert issubclass(D.ContaminationDetector, D.DefectDetector) and callable(d)
+    with pytest.raises(ValueError):
+        d.detect(np.zeros((4, 4, 2), np.uint8))
+
+
+@pytest.mark.gpu
+def test_detector_mirror_returns_the_reference_defects(detector, golden_dir):
+    from heimdall_core import detectors as D
+    ref = json.load(open(os.path.join(golden_dir, "reference_python_detect.json")))["blemish_bgr"]
+    img = np.load(os.path.join(golden_dir, "reference_python_detect_frames.npz"))["blemish_bgr"]
+    got = D.ContaminationDetector(config=ref["config"], detector=detector)(img)
+    assert [(list(d.position), d.size, d.confidence, d.defect_type) for d in got] == \
+        [(e["position"], e["size"], e["confidence"], "contamination") for e in ref["defects"]]
+    dd = got[0].to_dict()
+    assert set(dd) == {"type", "position", "size", "confidence", "intensity_diff", "shape_score", "color_score", "bounding_box"}
