@@ -34,6 +34,7 @@ hv::Tunables read_tunables() {
     t.k1_ctas_per_sm = env_int("HV_K1_CTAS_PER_SM", t.k1_ctas_per_sm, 1, 5);
     t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
     t.ccl_small_max_tiles = env_int("HV_CCL_SMALL_MAX_TILES", t.ccl_small_max_tiles, 0, 1 << 30);
+    t.k1_ctas_coresident = env_int("HV_K1_CTAS_CORESIDENT", t.k1_ctas_coresident, 1, 5);
     t.k1_stages_coresident = env_int("HV_K1_STAGES", t.k1_stages_coresident, 2, 3);
     t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
@@ -46,6 +47,7 @@ hv::Tunables read_tunables() {
     t.k1_static = env_flag("HV_K1_STATIC");
     t.k1_no_tma = env_flag("HV_K1_NO_TMA");
     t.ccl_big = env_flag("HV_CCL_BIG");
+    t.ccl_no_tiny = env_flag("HV_CCL_NO_TINY");
     t.no_k1_flag = env_flag("HV_NO_K1_FLAG");
     t.no_early_k1 = env_flag("HV_NO_EARLY_K1");
     t.no_pdl = env_flag("HV_NO_PDL");
@@ -217,6 +219,7 @@ struct Slot {
     PinBuf<uint8_t> h_stage;  // pinned staging for camera frames that arrive in pageable memory
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
     bool used_small = false;  // ... its small build
+    bool used_tiny = false;   // ... its tiny build
     bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
     DevBuf<int32_t> labels;
@@ -297,6 +300,9 @@ struct hv_ctx {
     // which build of the per-frame CCL kernel: the small one (co-resident with K1) until a frame did not fit in it
     bool ccl_small_ok = true;
     uint32_t ccl_small_retry = 0;
+    // ... and the tiny one once a batch has reported (frame flags) that all its frames would fit it
+    bool ccl_tiny_ok = false;
+    uint32_t ccl_tiny_cooldown = 0;
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -651,7 +657,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // of it, but those CTAs often land two to an SM, and two of them leave room for two K1 CTAs whatever K1 asked for --
     // with three the loss is one CTA instead of two (measured in one call: 41.9 us per step with 4, 41.1 with 3, although
     // K1 alone is slower with 3: 53.5 vs 50.4 us).  The morphology tiles kernel needs the room as well.
-    pp.ctas_per_sm = ccl_small ? 3 : 0;
+    pp.ctas_per_sm = ccl_small ? (k1_morph ? std::max(tun.k1_ctas_coresident, 4) : tun.k1_ctas_coresident) : 0;
     pp.stages = ccl_small ? tun.k1_stages_coresident : 2;
     pp.sparse_aux = (fused && !morph) ? 1 : 0;
     if (k1_morph) pp.morph_open_k = pr.morph_open_k, pp.morph_close_k = pr.morph_close_k;
@@ -776,9 +782,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         // right before it on the stream; the kernel waits for K1 itself (griddepcontrol.wait)
         const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !tun.no_pdl &&
                               !tun.no_pdl_tail;
-        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, ccl_small, st));
+        const bool ccl_tiny = ccl_small && ctx->ccl_tiny_ok && !tun.ccl_no_tiny;
+        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, ccl_tiny ? 2 : (ccl_small ? 1 : 0), st));
         s.ccl_expected += (uint32_t)n;
-        s.used_small = ccl_small;
+        s.used_small = ccl_small && !ccl_tiny;
+        s.used_tiny = ccl_tiny;
         ctx->launches += 1;
     } else {
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
@@ -855,18 +863,26 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     if (!s.used_fused) return HV_OK;
     const uint32_t *h_flags = flags_after(s.h_results.p, s.view.n);
     bool any = false;
-    bool all_fit_small = true;
+    bool all_fit_small = true, all_fit_tiny = true;
     for (int f = 0; f < s.view.n; f++) {
         any |= (h_flags[f] & 1u) != 0;
-        all_fit_small &= h_flags[f] == 0;
+        all_fit_small &= (h_flags[f] & 3u) == 0;
+        all_fit_tiny &= h_flags[f] == 0;
     }
     if (!any) {
         ctx->dense_hint = false;
-        if (!s.used_small && all_fit_small) ctx->ccl_small_ok = true;  // the big build reports that the small one would do
+        if (!s.used_small && !s.used_tiny && all_fit_small) ctx->ccl_small_ok = true;  // the big build reports that the small one would do
+        // every build reports whether the tiny one would do; after a batch that overflowed it, it stays off for a while so
+        // that a line whose frames hover around its capacity does not pay the fallback again and again
+        if (ctx->ccl_tiny_cooldown > 0) ctx->ccl_tiny_cooldown--;
+        ctx->ccl_tiny_ok = all_fit_tiny && ctx->ccl_tiny_cooldown == 0;
         return HV_OK;
     }
-    if (s.used_small) {  // too much foreground for the small build: the big one takes over (the global path below
-        ctx->ccl_small_ok = false;  // finishes the flagged frames of this batch)
+    if (s.used_tiny) {  // too much foreground for the tiny build: back to the small one (the global path below finishes the
+        ctx->ccl_tiny_ok = false;  // flagged frames of this batch)
+        ctx->ccl_tiny_cooldown = 64;
+    } else if (s.used_small) {  // ... for the small build: the big one takes over
+        ctx->ccl_small_ok = false;
         ctx->ccl_small_retry = 0;
     }
     ctx->last_valid = false;  // kernels that are not part of the K1 / per-frame chain go onto the stream
@@ -883,10 +899,11 @@ hv_status resolve_fallback(hv_ctx *ctx, Slot &s, cudaStream_t st) {
     rs = enqueue_readback(ctx, s, st);
     if (rs != HV_OK) return rs;
     HV_TRY_CUDA(ctx, cudaStreamSynchronize(st));
-    if (!s.used_small) {  // (after the small build the big one is tried before the global path becomes the default)
+    if (!s.used_small && !s.used_tiny) {  // (after the smaller builds the big one is tried before the global path becomes the default)
         ctx->dense_hint = true;
     }
     s.used_small = false;
+    s.used_tiny = false;
     return HV_OK;
 }
 

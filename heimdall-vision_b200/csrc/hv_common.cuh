@@ -122,6 +122,7 @@ __device__ __forceinline__ uint8_t gray_f64(uint32_t c0, uint32_t c1, uint32_t c
 struct Tunables {
     int pipeline_depth = 6;       // HV_PIPELINE_DEPTH: scratch sets in rotation = batches in flight on the device (2..8)
     int k1_ctas_per_sm = 5;       // HV_K1_CTAS_PER_SM (1..5)
+    int k1_ctas_coresident = 3;   // HV_K1_CTAS_CORESIDENT: K1 CTAs per SM next to the small per-frame CCL build (1..5)
     int k1_stages_coresident = 2; // HV_K1_STAGES: TMA stages of K1 when it runs at three CTAs per SM next to the CCL kernel (2 | 3)
     int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4)
     int k1_lookahead = 2;         // HV_K1_LOOKAHEAD: tiles the TMA producer runs ahead
@@ -136,6 +137,7 @@ struct Tunables {
     bool k1_static = false;       // HV_K1_STATIC
     bool k1_no_tma = false;       // HV_K1_NO_TMA
     bool ccl_big = false;         // HV_CCL_BIG
+    bool ccl_no_tiny = false;     // HV_CCL_NO_TINY: never use the tiny per-frame CCL build
     bool no_k1_flag = false;      // HV_NO_K1_FLAG
     bool no_early_k1 = false;     // HV_NO_EARLY_K1
     bool no_pdl = false;          // HV_NO_PDL
@@ -178,7 +180,7 @@ cudaError_t launch_ccl_flatten(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_scan(const BatchView &b, cudaStream_t s);
 cudaError_t launch_ccl_label(const BatchView &b, cudaStream_t s);
 cudaError_t launch_score(const BatchView &b, const ScoreParams &p, cudaStream_t s);
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, bool small, cudaStream_t s);
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, int level, cudaStream_t s);
 bool ccl_frame_supported(const BatchView &b);
 cudaError_t configure_ccl_frame();
 cudaError_t configure_preprocess_tma();

@@ -46,6 +46,10 @@ struct CclCfg {
 };
 using CclBig = CclCfg<512, 4096, 8192, 2048, 4096>;
 using CclSmall = CclCfg<256, 2048, 4096, 512, 1024>;
+// Tiny: 128 threads, 768 / 1024 / 256, 22 KB -- for frames that are sparse after morphology (300-460 non-zero words on the
+// headline frames with open + close 3x3).  It needs less than one K1 CTA does of everything (shared memory, registers,
+// threads), so it can take the place of any single K1 CTA that retires.
+using CclTiny = CclCfg<128, 768, 1024, 256, 512>;
 
 template <typename C>
 struct FrameSmem {
@@ -74,6 +78,7 @@ struct FrameSmem {
 };
 static_assert(sizeof(FrameSmem<CclBig>) <= 227 * 1024, "FrameSmem must fit the 227 KB per-CTA shared memory of sm_100");
 static_assert(sizeof(FrameSmem<CclSmall>) <= 71 * 1024, "the small build must fit next to four K1 CTAs");
+static_assert(sizeof(FrameSmem<CclTiny>) <= 24 * 1024, "the tiny build must fit into the room one K1 CTA leaves");
 static_assert(CclBig::kCapN <= 65536 && CclBig::kCapE <= 65536, "16-bit node ids in rnk / edges");
 
 // exclusive scan of one value per thread across the CTA; returns the exclusive prefix, *total_out gets the block sum.
@@ -151,7 +156,7 @@ __device__ __forceinline__ uint32_t run_index(uint32_t starts, int bit) {
 // Registers: the small build shares an SM with four K1 CTAs (4 x 288 threads x 40 registers = 46080 of 65536), which
 // leaves 256 threads x 72 registers.
 template <typename C>
-__global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) k_ccl_frame(BatchView b, ScoreParams sp) {
+__global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::kFT == 128 ? 80 : 128)) k_ccl_frame(BatchView b, ScoreParams sp) {
     constexpr int kFT = C::kFT, kNW = C::kNW, kCapW = C::kCapW, kCapN = C::kCapN, kCapB = C::kCapB, kCapE = C::kCapE;
     constexpr int kMaxEPT = C::kMaxEPT;
     using FrameSmem = hv::FrameSmem<C>;
@@ -529,10 +534,12 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : 128) 
         b.fgcount[f] = fg;
         // bit 0 = "not done, needs the global path" (set on the early exits); bit 1 = done, but would not have fitted the
         // small build: the host uses it to decide when to go back to that build
-        b.frame_flags[f] = (nw <= (uint32_t)CclSmall::kCapW && nn <= (uint32_t)CclSmall::kCapN && ne <= (uint32_t)CclSmall::kCapE &&
-                            ncomp <= (uint32_t)CclSmall::kCapB)
-                               ? 0u
-                               : 2u;
+        // bit 2 likewise for the tiny build
+        const bool fits_small = nw <= (uint32_t)CclSmall::kCapW && nn <= (uint32_t)CclSmall::kCapN && ne <= (uint32_t)CclSmall::kCapE &&
+                                ncomp <= (uint32_t)CclSmall::kCapB;
+        const bool fits_tiny = nw <= (uint32_t)CclTiny::kCapW && nn <= (uint32_t)CclTiny::kCapN && ne <= (uint32_t)CclTiny::kCapE &&
+                               ncomp <= (uint32_t)CclTiny::kCapB;
+        b.frame_flags[f] = (fits_small ? 0u : 2u) | (fits_tiny ? 0u : 4u);
         unsigned long long *st = reinterpret_cast<unsigned long long *>(b.stats);
         atomicAdd(st + 0, 1ull);
         atomicAdd(st + 1, (unsigned long long)r.rejected);
@@ -569,21 +576,25 @@ cudaError_t configure_ccl_frame() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ccl_frame<CclSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrameSmem<CclSmall>));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ccl_frame<CclTiny>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_ccl_frame<CclSmall>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, bool small, cudaStream_t s) {
+// level: 0 = big build, 1 = small, 2 = tiny
+cudaError_t launch_ccl_frame(const BatchView &b, const ScoreParams &p, bool pdl, int level, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(b.n);
-    cfg.blockDim = dim3(small ? CclSmall::kFT : CclBig::kFT);
-    cfg.dynamicSmemBytes = small ? sizeof(FrameSmem<CclSmall>) : sizeof(FrameSmem<CclBig>);
+    cfg.blockDim = dim3(level == 2 ? CclTiny::kFT : (level == 1 ? CclSmall::kFT : CclBig::kFT));
+    cfg.dynamicSmemBytes = level == 2 ? sizeof(FrameSmem<CclTiny>) : (level == 1 ? sizeof(FrameSmem<CclSmall>) : sizeof(FrameSmem<CclBig>));
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (small) return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclSmall>, b, p);
+    if (level == 2) return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclTiny>, b, p);
+    if (level == 1) return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclSmall>, b, p);
     return cudaLaunchKernelEx(&cfg, k_ccl_frame<CclBig>, b, p);
 }
 
