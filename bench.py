@@ -328,7 +328,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         b = base[perm].astype(np.int16) + rng.integers(-1, 2, size=base.shape, dtype=np.int16)
         pool_host.append(np.clip(b, 0, 255).astype(np.uint8))
     pool_dev = [torch.from_numpy(b).to(dev) for b in pool_host]
-    det = hc.Detector(local_rank, num_slots=args.slots)
+    det = hc.Detector(local_rank, num_slots=args.slots, defer_tail=not args.no_defer_tail)
     # The output planes come from the library's allocator (hv_device_alloc): memory with L2 compute-data compression, so
     # the almost entirely zero mask / label planes cost less DRAM write time.  --no-compress: plain cudaMalloc memory.
     depth = det.pipeline_depth()  # output sets in rotation = batches the library keeps in flight on the device
@@ -718,7 +718,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                  f"lists of EVERY batch reach pinned host memory inside the timed region (copy stream ordered by the "
                  f"slot's device-side completion counter) and their sums are checked against the device's line statistics; "
                  f"K1 of step i+1 overlaps the per-frame CCL kernels of the previous steps (programmatic dependent launch, "
-                 f"{depth} output sets in rotation)"})
+                 f"{depth} output sets in rotation)",
+        "defer_tail": (None if args.no_defer_tail else
+                       "HV_FLAG_DEFER_TAIL: a call enqueues the per-frame kernel of the PREVIOUS batch, then K1 of this one, so the "
+                       "window-boundary event sits between a batch's K1 and its own per-frame kernel (a full dependency anyway) "
+                       "instead of draining the K1 / per-frame overlap; every window still holds K K1 launches and K per-frame "
+                       "launches (shifted by one batch), results are fetched by ticket as before.  --no-defer-tail measures "
+                       "the plain order (DESIGN.md section 5)")})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": R,
         "ms_per_step": step_ms, "ms_per_step_min": min(p[1] for p in per_rank) / K,
@@ -790,6 +796,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--repeats", type=int, default=15, help="timed windows of --steps steps, back to back; the median counts")
+    ap.add_argument("--no-defer-tail", action="store_true",
+                    help="enqueue every batch's per-frame kernel with the batch itself (without HV_FLAG_DEFER_TAIL)")
     ap.add_argument("--no-morph", action="store_true", help="skip the roofline_morph sub-record")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the other_configs sub-record (BASELINE configs[2], [3])")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")

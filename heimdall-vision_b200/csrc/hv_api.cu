@@ -303,6 +303,17 @@ struct hv_ctx {
     // ... and the tiny one once a batch has reported (frame flags) that all its frames would fit it
     bool ccl_tiny_ok = false;
     uint32_t ccl_tiny_cooldown = 0;
+    // HV_FLAG_DEFER_TAIL: the per-frame kernel (and the read-back behind it) of the latest hv_enqueue_device batch, not yet
+    // on the stream (flush_deferred)
+    struct DeferredTail {
+        bool valid = false;
+        int slot = -1;
+        BatchView b;
+        ScoreParams sp;
+        int level = 0;
+        bool pdl = false;
+        cudaStream_t st = nullptr;
+    } deferred;
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -528,11 +539,36 @@ hv_status enqueue_global_ccl(hv_ctx *ctx, const BatchView &b, const ScoreParams 
     return HV_OK;
 }
 
+hv_status enqueue_async_readback(hv_ctx *ctx, Slot &s, cudaStream_t st);
+
+// HV_FLAG_DEFER_TAIL.  The stream sequence of a streaming loop is K1(i), CCL(i), K1(i+1), CCL(i+1), ...: K1(i+1) is released
+// by the per-frame kernel of batch i the moment that kernel is resident (programmatic launch), and that is what keeps the
+// device busy while the per-frame kernel works through its latency.  Whatever the caller puts onto the stream between two
+// calls -- an event, a copy -- lands between CCL(i) and K1(i+1) and turns that hand-over into plain stream order: K1(i+1)
+// then waits for the whole per-frame kernel (about 40 us of mostly idle device for the headline batch).  With the tail
+// deferred a call enqueues CCL(i-1), K1(i) instead: the caller's work lands between K1(i) and CCL(i), where a full
+// dependency exists anyway.  The price: batch i's label plane and results are complete in stream order only after the next
+// call / hv_flush / hv_fetch_ticket -- which is why it is opt-in.  The read-back is enqueued together with the kernel, never
+// ahead of it, so a device-wide synchronize by the caller cannot wait for a kernel that has not been launched.
+hv_status flush_deferred(hv_ctx *ctx) {
+    if (!ctx->deferred.valid) return HV_OK;
+    hv_ctx::DeferredTail d = ctx->deferred;
+    ctx->deferred.valid = false;
+    Slot &s = ctx->slots[d.slot];
+    HV_TRY_CUDA(ctx, launch_ccl_frame(d.b, d.sp, d.pdl, d.level, d.st));
+    ctx->launches += 1;
+    return enqueue_async_readback(ctx, s, d.st);
+}
+
 // Enqueue the whole detect pipeline for frames already on the device.  No host synchronisation.
 hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t *d_frames, int n, int h, int w, int c,
                            size_t row_stride, size_t frame_stride, const hv_params &pr, uint8_t *d_mask,
-                           int32_t *d_labels, bool want_blur) {
+                           int32_t *d_labels, bool want_blur, bool may_defer = false) {
     const Tunables &tun = tunables();
+    {
+        hv_status rf = flush_deferred(ctx);  // the previous batch's tail goes onto the stream ahead of this batch's K1
+        if (rf != HV_OK) return rf;
+    }
     if (row_stride == 0) row_stride = (size_t)w * c;
     if (frame_stride == 0) frame_stride = row_stride * h;
     if (row_stride < (size_t)w * c || frame_stride < row_stride * (size_t)h)
@@ -783,11 +819,20 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         const bool pdl_tail = k1_tma && (!morph || morph_fused) && ctx->prof_mask == 0 && !tun.no_pdl &&
                               !tun.no_pdl_tail;
         const bool ccl_tiny = ccl_small && ctx->ccl_tiny_ok && !tun.ccl_no_tiny;
-        HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, ccl_tiny ? 2 : (ccl_small ? 1 : 0), st));
+        const int level = ccl_tiny ? 2 : (ccl_small ? 1 : 0);
+        // (deferred only in the plain chain K1 -> per-frame kernel, where the kernel waits for K1's launch counter)
+        if (may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && pdl_tail && b.k1_done && !morph && ctx->wait32 && !b.phase_ns) {
+            ctx->deferred.valid = true;
+            ctx->deferred.slot = (int)(&s - ctx->slots.data());
+            ctx->deferred.b = b, ctx->deferred.sp = sp, ctx->deferred.level = level, ctx->deferred.pdl = pdl_tail;
+            ctx->deferred.st = st;
+        } else {
+            HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, level, st));
+            ctx->launches += 1;
+        }
         s.ccl_expected += (uint32_t)n;
         s.used_small = ccl_small && !ccl_tiny;
         s.used_tiny = ccl_tiny;
-        ctx->launches += 1;
     } else {
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
             HV_TRY_CUDA(ctx, launch_densify_bits(b, st));
@@ -925,6 +970,10 @@ void update_dense_hint(hv_ctx *ctx, const Slot &s) {
 
 hv_status retire_slot(hv_ctx *ctx, Slot &s) {
     if (!s.pending) return HV_OK;
+    if (ctx->deferred.valid && &ctx->slots[ctx->deferred.slot] == &s) {
+        hv_status rf = flush_deferred(ctx);
+        if (rf != HV_OK) return rf;
+    }
     HV_TRY_CUDA(ctx, cudaEventSynchronize(s.copied));
     s.pending = false;
     update_dense_hint(ctx, s);
@@ -1149,6 +1198,7 @@ hv_status hv_create(int32_t device, const hv_config *cfg, hv_ctx **out) {
 void hv_destroy(hv_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    flush_deferred(ctx);
     cudaDeviceSynchronize();
     for (auto &s : ctx->slots) s.release();
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1169,6 +1219,11 @@ const char *hv_last_error(const hv_ctx *ctx) { return ctx ? ctx->err.c_str() : g
 
 hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream, int32_t enable) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    if (ctx->deferred.valid) {  // (belongs to the stream that is being replaced)
+        cudaSetDevice(ctx->device);
+        hv_status rf = flush_deferred(ctx);
+        if (rf != HV_OK) return rf;
+    }
     ctx->user_stream = enable ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
     ctx->use_user_stream = enable != 0;
     return HV_OK;
@@ -1281,16 +1336,24 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
     Slot &s = cur_sync_slot(ctx);
     s.has_batch = false;
     rs = enqueue_pipeline(ctx, s, st, d_frames, n, h, w, c, row_stride, frame_stride, pr, d_mask, d_labels,
-                          (ctx->cfg.flags & 4u) != 0);
+                          (ctx->cfg.flags & 4u) != 0, true);
     if (rs != HV_OK) return rs;
     s.batch_stream = st;
     s.ticket = ctx->next_ticket++;
     if (ticket) *ticket = s.ticket;
     if (tunables().exp_k1_only) return HV_OK;  // (experiment builds: nothing computes results)
-    rs = enqueue_async_readback(ctx, s, st);
-    if (rs != HV_OK) return rs;
+    if (!ctx->deferred.valid) {  // (a deferred tail brings its read-back along: flush_deferred)
+        rs = enqueue_async_readback(ctx, s, st);
+        if (rs != HV_OK) return rs;
+    }
     s.pending = true;
     return HV_OK;
+}
+
+hv_status hv_flush(hv_ctx *ctx) {
+    if (!ctx) return HV_ERR_INVALID_ARGUMENT;
+    HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    return flush_deferred(ctx);
 }
 
 hv_status hv_fetch_ticket(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects, size_t defects_cap,
@@ -2195,6 +2258,10 @@ hv_status hv_draw_overlays(hv_ctx *ctx, uint8_t *img, int32_t h, int32_t w, cons
 hv_status hv_stats_get(hv_ctx *ctx, hv_line_stats *out) {
     if (!ctx || !out) return HV_ERR_INVALID_ARGUMENT;
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        hv_status rf = flush_deferred(ctx);  // every enqueued batch counts
+        if (rf != HV_OK) return rf;
+    }
     HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
     HV_TRY_CUDA(ctx, cudaMemcpy(out, ctx->d_stats, sizeof(*out), cudaMemcpyDeviceToHost));
     return HV_OK;
@@ -2203,6 +2270,10 @@ hv_status hv_stats_get(hv_ctx *ctx, hv_line_stats *out) {
 hv_status hv_stats_reset(hv_ctx *ctx) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        hv_status rf = flush_deferred(ctx);  // every enqueued batch counts
+        if (rf != HV_OK) return rf;
+    }
     HV_TRY_CUDA(ctx, cudaDeviceSynchronize());
     HV_TRY_CUDA(ctx, cudaMemset(ctx->d_stats, 0, sizeof(hv_line_stats)));
     return HV_OK;

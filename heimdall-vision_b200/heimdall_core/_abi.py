@@ -25,6 +25,7 @@ HV_ERR_BAD_TICKET = -8
 
 HV_FLAG_PROFILE = 2
 HV_FLAG_KEEP_BLUR = 4
+HV_FLAG_DEFER_TAIL = 64
 HV_FLAG_FORCE_GENERIC = 8
 HV_FLAG_GLOBAL_CCL = 16
 HV_FLAG_PHASE_TIMING = 32
@@ -179,6 +180,7 @@ PROTOTYPES = {
                                       _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
     "hv_enqueue_device": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _vp, _vp, _P(_i64)]),
     "hv_fetch_ticket": (_i32, [_vp, _i64, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
+    "hv_flush": (_i32, [_vp]),
     "hv_fetch_results": (_i32, [_vp, _P(hv_frame_result), _P(hv_defect), _sz, _P(_sz)]),
     "hv_fetch_debug": (_i32, [_vp, _P(hv_debug_outputs)]),
     "hv_submit": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _sz, _sz, _P(hv_params), _P(_i64)]),

@@ -83,7 +83,7 @@ class Detector:
 
     def __init__(self, device: int = 0, *, max_blobs_per_frame: int = 0, max_defects_per_frame: int = 0,
                  num_slots: int = 0, profile: bool = False, keep_blur: bool = False, force_generic: bool = False,
-                 global_ccl: bool = False, phase_timing: bool = False):
+                 global_ccl: bool = False, phase_timing: bool = False, defer_tail: bool = False):
         cfg = A.hv_config()
         _lib.hv_config_default(C.byref(cfg))
         cfg.max_blobs_per_frame = max_blobs_per_frame
@@ -92,7 +92,8 @@ class Detector:
         cfg.flags = ((A.HV_FLAG_PROFILE if profile else 0) | (A.HV_FLAG_KEEP_BLUR if keep_blur else 0) |
                      (A.HV_FLAG_FORCE_GENERIC if force_generic else 0) |
                      (A.HV_FLAG_GLOBAL_CCL if global_ccl else 0) |
-                     (A.HV_FLAG_PHASE_TIMING if phase_timing else 0))
+                     (A.HV_FLAG_PHASE_TIMING if phase_timing else 0) |
+                     (A.HV_FLAG_DEFER_TAIL if defer_tail else 0))
         self._ctx = C.c_void_p()
         self._lock = threading.RLock()
         self._inflight_frames: Dict[int, tuple] = {}  # ticket -> raw camera frames that must outlive their H2D copy
@@ -275,6 +276,13 @@ class Detector:
             if st != A.HV_OK and not (st == A.HV_ERR_CAPACITY and not raise_on_capacity):
                 _raise(st, self._ctx)
         return BatchResult(res, dfx[:total.value], st)
+
+    def flush(self) -> None:
+        """With defer_tail: put the kernel held back for the latest batch onto the stream now (hv_flush)."""
+        with self._lock:
+            st = _lib.hv_flush(self._ctx)
+            if st != A.HV_OK:
+                _raise(st, self._ctx)
 
     def fetch_results(self, n: int, defects_cap: Optional[int] = None, raise_on_capacity: bool = True) -> BatchResult:
         """Results of the most recently enqueued batch."""

@@ -848,6 +848,62 @@ def test_streaming_finishes_flagged_frames_without_fetch(oracle):
         det.close()
 
 
+def test_deferred_tail_streaming_with_work_between_batches(oracle):
+    """HV_FLAG_DEFER_TAIL: the per-frame kernel of a batch goes onto the stream with the next call.  A streaming loop that
+    records an event between every two batches, synchronizes the whole device while a tail is held back, rotates one and
+    several plane sets, contains a frame the per-frame kernel cannot hold, and finally closes a context with a tail still
+    held back: every batch's records, the planes after hv_flush, and the line statistics equal the oracle's."""
+    import torch
+
+    import heimdall_core as hc
+    n, h, w = 2, 512, 640
+    busy = synth.high_contamination_frame(h, w, 3)
+    calm = [synth.bottle_frame(h, w, 140 + i, contaminants=i % 3) for i in range(14)]
+    batches = [np.stack([calm[i], busy if i == 6 else calm[(i + 5) % 14]]) for i in range(14)]
+    refs = [[oracle.detect_contamination(b[f][:, :, None]) for f in range(n)] for b in batches]
+    st = torch.cuda.current_stream().cuda_stream
+    for n_sets in (1, 6):
+        det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=20000, defer_tail=True)
+        try:
+            det.set_stream(st)
+            depth = det.pipeline_depth()
+            d_in = [torch.from_numpy(b).cuda() for b in batches]
+            masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(n_sets)]
+            labels = [det.device_alloc((n, h, w), np.int32) for _ in range(n_sets)]
+            tickets, fetched, events = [], {}, []
+            for i in range(len(batches)):
+                tickets.append(det.enqueue_device(d_in[i].data_ptr(), n, h, w, 1, None, masks[i % n_sets].ptr, labels[i % n_sets].ptr))
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                events.append(ev)
+                if i == 4:
+                    torch.cuda.synchronize()     # (must not wait for a kernel that is not on the stream yet)
+                if i >= depth - 1:
+                    fetched[i - depth + 1] = det.fetch(tickets[i - depth + 1], n)
+            det.flush()
+            torch.cuda.synchronize()
+            k = (len(batches) - 1) % n_sets
+            got_m, got_l = masks[k].get(), labels[k].get()
+            for f in range(n):
+                assert np.array_equal(got_m[f], refs[-1][f].mask) and np.array_equal(got_l[f], refs[-1][f].labels)
+            for i in range(len(batches) - depth + 1, len(batches)):
+                fetched[i] = det.fetch(tickets[i], n)
+            for i in range(len(batches)):
+                for f in range(n):
+                    got = [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in fetched[i].defects_of(f)]
+                    assert got == [(d["position"], d["size"], d["confidence"]) for d in refs[i][f].defects], (n_sets, i, f)
+                    assert int(fetched[i].frames["n_components"][f]) == refs[i][f].ncomp
+            t = det.enqueue_device(d_in[0].data_ptr(), n, h, w, 1, None, masks[0].ptr, labels[0].ptr)
+            s = det.stats()                      # counts the batch whose tail was still held back
+            assert s["frames_inspected"] == n * (len(batches) + 1)
+            assert s["total_defects"] == sum(len(r.defects) for b in refs for r in b) + sum(len(r.defects) for r in refs[0])
+            det.enqueue_device(d_in[1].data_ptr(), n, h, w, 1, None, masks[0].ptr, labels[0].ptr)
+            assert t > 0
+        finally:
+            det.close()                          # with a tail held back
+    torch.cuda.synchronize()
+
+
 def test_enqueue_refuses_graph_capture():
     """The kernels of consecutive batches are ordered by device-side counters whose expected values are kernel arguments:
     replaying a captured graph would replay stale values.  hv_enqueue_device refuses a capturing stream."""
