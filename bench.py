@@ -720,10 +720,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                  f"K1 of step i+1 overlaps the per-frame CCL kernels of the previous steps (programmatic dependent launch, "
                  f"{depth} output sets in rotation)",
         "defer_tail": (None if args.no_defer_tail else
-                       "HV_FLAG_DEFER_TAIL: a call enqueues the per-frame kernel of the PREVIOUS batch, then K1 of this one, so the "
-                       "window-boundary event sits between a batch's K1 and its own per-frame kernel (a full dependency anyway) "
+                       "HV_FLAG_DEFER_TAIL: call i enqueues the per-frame kernel of batch i - 2, then K1 of batch i, so the "
+                       "window-boundary event sits behind a K1 and in front of a per-frame kernel whose input is long complete "
                        "instead of draining the K1 / per-frame overlap; every window still holds K K1 launches and K per-frame "
-                       "launches (shifted by one batch), results are fetched by ticket as before.  --no-defer-tail measures "
+                       "launches (shifted by two batches), results are fetched by ticket as before.  --no-defer-tail measures "
                        "the plain order (DESIGN.md section 5)")})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": R,

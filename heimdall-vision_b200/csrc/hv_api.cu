@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <new>
 #include <string>
@@ -35,6 +36,7 @@ hv::Tunables read_tunables() {
     t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
     t.ccl_small_max_tiles = env_int("HV_CCL_SMALL_MAX_TILES", t.ccl_small_max_tiles, 0, 1 << 30);
     t.k1_ctas_coresident = env_int("HV_K1_CTAS_CORESIDENT", t.k1_ctas_coresident, 1, 5);
+    t.defer_depth = env_int("HV_DEFER_DEPTH", t.defer_depth, 1, 3);
     t.k1_stages_coresident = env_int("HV_K1_STAGES", t.k1_stages_coresident, 2, 3);
     t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
@@ -60,6 +62,7 @@ hv::Tunables read_tunables() {
 #ifdef HV_EXPERIMENTS
     t.exp_k1_only = env_flag("HV_EXP_K1_ONLY");
     t.exp_ccl_noop = env_flag("HV_EXP_CCL_NOOP");
+    t.exp_ccl_stop = env_int("HV_EXP_CCL_STOP", 0, 0, 9);
 #endif
     return t;
 }
@@ -220,6 +223,7 @@ struct Slot {
     bool used_fused = false;  // the batch went through the fused per-frame CCL kernel
     bool used_small = false;  // ... its small build
     bool used_tiny = false;   // ... its tiny build
+    bool tail_deferred = false;  // its per-frame kernel was held back when the batch was enqueued (HV_FLAG_DEFER_TAIL)
     bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
     DevBuf<int32_t> labels;
@@ -306,14 +310,14 @@ struct hv_ctx {
     // HV_FLAG_DEFER_TAIL: the per-frame kernel (and the read-back behind it) of the latest hv_enqueue_device batch, not yet
     // on the stream (flush_deferred)
     struct DeferredTail {
-        bool valid = false;
         int slot = -1;
         BatchView b;
         ScoreParams sp;
         int level = 0;
         bool pdl = false;
         cudaStream_t st = nullptr;
-    } deferred;
+    };
+    std::deque<DeferredTail> deferred;  // oldest first
     // profiling: event pairs recorded around kernels whose bit is set in prof_mask
     struct ProfRec {
         int k;
@@ -545,19 +549,26 @@ hv_status enqueue_async_readback(hv_ctx *ctx, Slot &s, cudaStream_t st);
 // by the per-frame kernel of batch i the moment that kernel is resident (programmatic launch), and that is what keeps the
 // device busy while the per-frame kernel works through its latency.  Whatever the caller puts onto the stream between two
 // calls -- an event, a copy -- lands between CCL(i) and K1(i+1) and turns that hand-over into plain stream order: K1(i+1)
-// then waits for the whole per-frame kernel (about 40 us of mostly idle device for the headline batch).  With the tail
-// deferred a call enqueues CCL(i-1), K1(i) instead: the caller's work lands between K1(i) and CCL(i), where a full
-// dependency exists anyway.  The price: batch i's label plane and results are complete in stream order only after the next
-// call / hv_flush / hv_fetch_ticket -- which is why it is opt-in.  The read-back is enqueued together with the kernel, never
-// ahead of it, so a device-wide synchronize by the caller cannot wait for a kernel that has not been launched.
-hv_status flush_deferred(hv_ctx *ctx) {
-    if (!ctx->deferred.valid) return HV_OK;
-    hv_ctx::DeferredTail d = ctx->deferred;
-    ctx->deferred.valid = false;
-    Slot &s = ctx->slots[d.slot];
-    HV_TRY_CUDA(ctx, launch_ccl_frame(d.b, d.sp, d.pdl, d.level, d.st));
-    ctx->launches += 1;
-    return enqueue_async_readback(ctx, s, d.st);
+// then waits for the whole per-frame kernel (about 40 us of mostly idle device for the headline batch).  With the tails of
+// the last defer_depth batches held back, call i enqueues CCL(i - 2), K1(i): the caller's work lands behind a K1, in front
+// of a per-frame kernel whose own K1 completed a batch earlier, and the next K1 is released as soon as that kernel is
+// resident.  A per-frame kernel enqueued a batch late also finds its input complete: it is resident for its own 40-50 us,
+// not for K1's duration on top (measured, no events between the calls: 40.7 -> 40.2 us per batch; with an event every 20
+// batches: 44.2 -> 43.4 us with one tail held back -> 41.9 with two).  The price: a batch's label plane and results are
+// complete in stream order only defer_depth calls later, or after hv_flush / hv_fetch_ticket -- which is why it is opt-in.
+// The read-back is enqueued together with the kernel, never ahead of it, so a device-wide synchronize by the caller
+// cannot wait for a kernel that has not been launched.
+hv_status flush_deferred(hv_ctx *ctx, size_t keep = 0) {
+    while (ctx->deferred.size() > keep) {
+        hv_ctx::DeferredTail d = ctx->deferred.front();
+        ctx->deferred.pop_front();
+        Slot &s = ctx->slots[d.slot];
+        HV_TRY_CUDA(ctx, launch_ccl_frame(d.b, d.sp, d.pdl, d.level, d.st));
+        ctx->launches += 1;
+        hv_status rs = enqueue_async_readback(ctx, s, d.st);
+        if (rs != HV_OK) return rs;
+    }
+    return HV_OK;
 }
 
 // Enqueue the whole detect pipeline for frames already on the device.  No host synchronisation.
@@ -566,7 +577,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                            int32_t *d_labels, bool want_blur, bool may_defer = false) {
     const Tunables &tun = tunables();
     {
-        hv_status rf = flush_deferred(ctx);  // the previous batch's tail goes onto the stream ahead of this batch's K1
+        // the tails held back go onto the stream ahead of this batch's K1; a streaming call keeps the latest
+        // (defer_depth - 1) of them back
+        const bool streaming = may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && !ctx->deferred.empty() &&
+                               ctx->deferred.back().st == st;
+        hv_status rf = flush_deferred(ctx, streaming ? (size_t)(tun.defer_depth - 1) : 0);
         if (rf != HV_OK) return rf;
     }
     if (row_stride == 0) row_stride = (size_t)w * c;
@@ -646,7 +661,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
                 b.ccl_wait_n++;
             }
     b.phase_ns = (ctx->cfg.flags & HV_FLAG_PHASE_TIMING) ? ctx->d_phase_ns : nullptr;
-    if (tun.exp_ccl_noop) b.phase_frame = -12345;
+    if (tun.exp_ccl_noop) b.phase_frame = -12345 - tun.exp_ccl_stop;
     if (b.phase_ns) {
         cudaMemsetAsync(ctx->d_phase_ns + 192, 0, 64 * sizeof(unsigned long long), st);
         cudaMemsetAsync(ctx->d_phase_ns + 248, 0xff, sizeof(unsigned long long), st);
@@ -810,6 +825,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         }
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
+    bool deferred_now = false;
     if (fused && tun.exp_k1_only) {
         // experiment: K1 chain alone (results are NOT computed)
     } else if (fused) {
@@ -822,10 +838,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         const int level = ccl_tiny ? 2 : (ccl_small ? 1 : 0);
         // (deferred only in the plain chain K1 -> per-frame kernel, where the kernel waits for K1's launch counter)
         if (may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && pdl_tail && b.k1_done && !morph && ctx->wait32 && !b.phase_ns) {
-            ctx->deferred.valid = true;
-            ctx->deferred.slot = (int)(&s - ctx->slots.data());
-            ctx->deferred.b = b, ctx->deferred.sp = sp, ctx->deferred.level = level, ctx->deferred.pdl = pdl_tail;
-            ctx->deferred.st = st;
+            hv_ctx::DeferredTail d;
+            d.slot = (int)(&s - ctx->slots.data());
+            d.b = b, d.sp = sp, d.level = level, d.pdl = pdl_tail, d.st = st;
+            ctx->deferred.push_back(d);
+            deferred_now = true;
         } else {
             HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, level, st));
             ctx->launches += 1;
@@ -841,6 +858,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         hv_status rg = enqueue_global_ccl(ctx, b, sp, st);
         if (rg != HV_OK) return rg;
     }
+    s.tail_deferred = deferred_now;
     s.used_fused = fused;
     s.sparse_bits = pp.sparse_aux != 0 || (morph_fused && fused);  // (fused morphology: tiles out of reach of foreground have no bit words)
     s.score = sp;
@@ -970,10 +988,12 @@ void update_dense_hint(hv_ctx *ctx, const Slot &s) {
 
 hv_status retire_slot(hv_ctx *ctx, Slot &s) {
     if (!s.pending) return HV_OK;
-    if (ctx->deferred.valid && &ctx->slots[ctx->deferred.slot] == &s) {
-        hv_status rf = flush_deferred(ctx);
-        if (rf != HV_OK) return rf;
-    }
+    for (size_t k = 0; k < ctx->deferred.size(); k++)
+        if (&ctx->slots[ctx->deferred[k].slot] == &s) {  // its tail (and the older ones) go onto the stream now
+            hv_status rf = flush_deferred(ctx, ctx->deferred.size() - 1 - k);
+            if (rf != HV_OK) return rf;
+            break;
+        }
     HV_TRY_CUDA(ctx, cudaEventSynchronize(s.copied));
     s.pending = false;
     update_dense_hint(ctx, s);
@@ -1219,7 +1239,7 @@ const char *hv_last_error(const hv_ctx *ctx) { return ctx ? ctx->err.c_str() : g
 
 hv_status hv_set_stream(hv_ctx *ctx, void *cuda_stream, int32_t enable) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
-    if (ctx->deferred.valid) {  // (belongs to the stream that is being replaced)
+    if (!ctx->deferred.empty()) {  // (they belong to the stream that is being replaced)
         cudaSetDevice(ctx->device);
         hv_status rf = flush_deferred(ctx);
         if (rf != HV_OK) return rf;
@@ -1342,7 +1362,7 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
     s.ticket = ctx->next_ticket++;
     if (ticket) *ticket = s.ticket;
     if (tunables().exp_k1_only) return HV_OK;  // (experiment builds: nothing computes results)
-    if (!ctx->deferred.valid) {  // (a deferred tail brings its read-back along: flush_deferred)
+    if (!s.tail_deferred) {  // (a deferred tail brings its read-back along: flush_deferred)
         rs = enqueue_async_readback(ctx, s, st);
         if (rs != HV_OK) return rs;
     }
@@ -1353,7 +1373,9 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
 hv_status hv_flush(hv_ctx *ctx) {
     if (!ctx) return HV_ERR_INVALID_ARGUMENT;
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
-    return flush_deferred(ctx);
+    hv_status rs = flush_deferred(ctx);
+    if (rs != HV_OK) return rs;
+    return HV_OK;
 }
 
 hv_status hv_fetch_ticket(hv_ctx *ctx, int64_t ticket, hv_frame_result *results, hv_defect *defects, size_t defects_cap,

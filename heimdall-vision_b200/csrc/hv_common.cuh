@@ -124,6 +124,7 @@ struct Tunables {
     int k1_ctas_per_sm = 5;       // HV_K1_CTAS_PER_SM (1..5)
     int k1_ctas_coresident = 3;   // HV_K1_CTAS_CORESIDENT: K1 CTAs per SM next to the small per-frame CCL build (1..5)
     int k1_stages_coresident = 2; // HV_K1_STAGES: TMA stages of K1 when it runs at three CTAs per SM next to the CCL kernel (2 | 3)
+    int defer_depth = 2;          // HV_DEFER_DEPTH: with HV_FLAG_DEFER_TAIL, how many batches' per-frame kernels are held back (1..3)
     int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4)
     int k1_lookahead = 2;         // HV_K1_LOOKAHEAD: tiles the TMA producer runs ahead
     int k1_tail_lookahead = 1;    // HV_K1_TAIL_LOOKAHEAD
@@ -148,6 +149,7 @@ struct Tunables {
     bool no_morph_chain = false;  // HV_NO_MORPH_CHAIN
     bool no_k1_morph = false;     // HV_NO_K1_MORPH: never fold 3x3 / 5x5 open+close into K1 (use the tiles kernel)
     bool exp_k1_only = false;     // HV_EXP_K1_ONLY  (-DHV_EXPERIMENTS only): K1 chain alone, NO results
+    int exp_ccl_stop = 0;         // HV_EXP_CCL_STOP (with HV_EXP_CCL_NOOP): the per-frame kernel returns after phase k
     bool exp_ccl_noop = false;    // HV_EXP_CCL_NOOP (-DHV_EXPERIMENTS only): per-frame kernels launched but idle, NO results
 };
 const Tunables &tunables();

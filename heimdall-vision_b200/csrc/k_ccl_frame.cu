@@ -195,6 +195,19 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
         if (threadIdx.x == 0 && b.ccl_done) atomicAdd(b.ccl_done, 1u);
         return;
     }
+#define HV_EXP_STOP(k)                                                       \
+    if (b.phase_frame == -12345 - (k)) {                                     \
+        if (threadIdx.x == 0) {                                              \
+            hv_frame_result r0{};                                            \
+            b.results[blockIdx.x] = r0;                                      \
+            b.frame_flags[blockIdx.x] = 0u;                                  \
+            __threadfence();                                                 \
+            if (b.ccl_done) atomicAdd(b.ccl_done, 1u);                       \
+        }                                                                    \
+        return;                                                              \
+    }
+#else
+#define HV_EXP_STOP(k)
 #endif
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FrameSmem &S = *reinterpret_cast<FrameSmem *>(smem_raw);
@@ -281,6 +294,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     }
     stamp();  // 1
     __syncthreads();
+    HV_EXP_STOP(1)
 
     // ---- phase 1: fetch the words; word-runs become nodes, numbered in raster order -----------------------------------------
     // blocked partition: thread t owns entries [t*ept, (t+1)*ept), so one scan orders the runs of the whole frame
@@ -328,6 +342,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     if (lane == 0) S.warp_fg[wid] = fgpx;
     stamp();  // 2
     __syncthreads();
+    HV_EXP_STOP(2)
 
     // ---- phase 2: unions --------------------------------------------------------------------------------------------------
     // Hooking all the runs of a long vertical line at once would leave a linked list as long as the line.  So the forest is
@@ -405,6 +420,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     }
     stamp();  // 3
     __syncthreads();
+    HV_EXP_STOP(3)
     const uint32_t ne = S.n_edges;
     if (ne > (uint32_t)kCapE) {  // block-uniform
         if (tid == 0) {
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     }
     stamp();  // 5
     __syncthreads();
+    HV_EXP_STOP(5)
 
     // ---- phase 3: flatten, rank the roots ---------------------------------------------------------------------------------
     {
@@ -461,6 +478,7 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     }
     stamp();  // 6
     __syncthreads();
+    HV_EXP_STOP(6)
 
     // ---- phase 4: labels + statistics, one node (run) per thread-iteration ----------------------------------------------
     int32_t *L = b.labels + (size_t)f * H * W;
@@ -477,10 +495,14 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
         atomicMax(&S.b_xmax[rank], xe);
         if (root == v) S.b_ymin[rank] = y;  // the root run holds the raster-first pixel: its row is ymin
         int32_t *dst = L + px;
+#ifdef HV_EXPERIMENTS
+        if (b.phase_frame != -12345 - 9)
+#endif
         for (uint32_t k = 0; k < len; k++) dst[k] = (int32_t)rank + 1;
     }
     stamp();  // 7
     __syncthreads();
+    HV_EXP_STOP(7)
 
     // ---- phase 5: blob table -> global, scoring, ordered compaction, result ----------------------------------------------------
     hv_blob *blobs = b.blobs + (size_t)f * b.blob_cap;

@@ -66,14 +66,14 @@ typedef struct {
 #define HV_FLAG_GLOBAL_CCL 16u   /* always use the global-memory CCL kernels (K2..K6), never the fused per-frame kernel */
 #define HV_FLAG_PHASE_TIMING 32u /* fused CCL kernel records per-phase timestamps of frame 0 (hv_debug_phase_times) */
 #define HV_FLAG_KEEP_BLUR 4u  /* materialise the blurred intermediate for hv_fetch_debug (disables the flat-tile skip) */
-/* hv_enqueue_device keeps the last kernel of a batch (the per-frame labelling + scoring kernel) and the read-back of its
- * results back until the next hv_enqueue_device / hv_flush / hv_fetch_ticket / hv_stats_get on this context.  Whatever the
- * caller enqueues on the stream between two batches (an event, the upload of the next frames) then sits between a batch's
- * preprocess kernel and its per-frame kernel, where a full dependency exists anyway, instead of between the per-frame
+/* hv_enqueue_device holds the last kernel of a batch (the per-frame labelling + scoring kernel) and the read-back of its
+ * results back for two calls: call i enqueues that kernel of batch i - 2, then the preprocess kernel of batch i.  Whatever
+ * the caller enqueues on the stream between two batches (an event, the upload of the next frames) then sits behind a
+ * preprocess kernel and in front of a per-frame kernel whose input has long been complete, instead of between a per-frame
  * kernel and the next batch's preprocess kernel, whose overlap is what keeps the device busy.  For callers that consume
- * the records (tickets), not the label plane in stream order: with this flag the planes and results of the latest batch
- * are complete only after one of the calls above.  Without work between the calls the stream sequence is the same either
- * way. */
+ * the records (tickets), not the label plane in stream order: with this flag the label plane and the results of the last
+ * two batches are complete only after hv_flush / hv_fetch_ticket / hv_stats_get (or two more hv_enqueue_device calls).
+ * The mask plane is written by the preprocess kernel and is complete in stream order either way. */
 #define HV_FLAG_DEFER_TAIL 64u
 
 /* Blur selection for the preprocess stage. */
@@ -249,8 +249,7 @@ HV_API hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, in
 HV_API hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
                                    size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
                                    int32_t *d_labels, int64_t *ticket);
-/* HV_FLAG_DEFER_TAIL: puts the kernel held back for the latest batch (and its read-back) onto the stream now.  A no-op
- * otherwise. */
+/* HV_FLAG_DEFER_TAIL: puts the kernels held back (and their read-backs) onto the stream now.  A no-op otherwise. */
 HV_API hv_status hv_flush(hv_ctx *ctx);
 /* Results of a batch enqueued with hv_enqueue_device, by ticket: blocks until its read-back has arrived.
  * HV_ERR_BAD_TICKET once the batch's scratch set has been reused (more than hv_pipeline_depth() - 1 batches later). */

@@ -11,7 +11,7 @@ npool = int(os.environ.get('SWEEP_POOL', 8))
 _distinct = min(n, 8)
 _base = [synth.bottle_batch(_distinct, h, w, start_index=100 * i) for i in range(npool)]
 pool = [torch.from_numpy(np.ascontiguousarray(np.resize(b, (n, h, w)))).cuda() for b in _base]
-det = hc.Detector(0); det.set_stream(st)
+det = hc.Detector(0, defer_tail=os.environ.get('SWEEP_DEFER', '0') == '1'); det.set_stream(st)
 comp = os.environ.get('SWEEP_COMPRESS', '1') == '1'
 nout = int(os.environ.get('SWEEP_OUTS', str(det.pipeline_depth())))
 outs = [(det.device_alloc((n, h, w), np.uint8, comp), det.device_alloc((n, h, w), np.int32, comp)) for _ in range(nout)]
