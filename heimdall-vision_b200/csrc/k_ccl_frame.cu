@@ -302,14 +302,25 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     const int e0 = min(tid * ept, (int)nw), e1 = min(e0 + ept, (int)nw);
     uint32_t local = 0, fgpx = 0;
     {
+        // the gather itself is striped over the CTA (neighbouring lanes fetch neighbouring compacted words, which are mostly
+        // neighbouring words of one row: a handful of L2 requests per warp instead of 32 per load), all loads of a thread in
+        // flight together; the blocked partition reads the words back from shared memory
         uint32_t wv[kMaxEPT];
 #pragma unroll
-        for (int k = 0; k < kMaxEPT; k++) wv[k] = (e0 + k < e1) ? __ldcg(bits + S.widx[e0 + k]) : 0u;  // one round trip
+        for (int k = 0; k < kMaxEPT; k++) {
+            const int e = tid + k * kFT;
+            wv[k] = e < (int)nw ? __ldcg(bits + S.widx[e]) : 0u;  // one round trip
+        }
 #pragma unroll
         for (int k = 0; k < kMaxEPT; k++) {
-            if (e0 + k < e1) S.wbits[e0 + k] = wv[k];
-            local += __popc(wv[k] & ~(wv[k] << 1));
-            fgpx += __popc(wv[k]);
+            const int e = tid + k * kFT;
+            if (e < (int)nw) S.wbits[e] = wv[k];
+        }
+        __syncthreads();
+        for (int e = e0; e < e1; e++) {
+            const uint32_t wvv = S.wbits[e];
+            local += __popc(wvv & ~(wvv << 1));
+            fgpx += __popc(wvv);
         }
     }
     uint32_t nn = 0;
@@ -481,6 +492,9 @@ __global__ void __launch_bounds__(C::kFT) __maxnreg__(C::kFT == 256 ? 72 : (C::k
     HV_EXP_STOP(6)
 
     // ---- phase 4: labels + statistics, one node (run) per thread-iteration ----------------------------------------------
+    // (Label stores: one thread per run, walking its own pixels.  A pixel-parallel version -- lane t takes pixel t of the
+    // concatenated runs of the warp's 32 nodes, so that a run is one L2 request instead of one per pixel -- made this
+    // kernel 2.4 us longer and the step no shorter: 40.35 vs 40.22 us.)
     int32_t *L = b.labels + (size_t)f * H * W;
     for (uint32_t v = tid; v < nn; v += kFT) {
         const uint32_t px = S.node_px[v], len = S.node_len[v];
