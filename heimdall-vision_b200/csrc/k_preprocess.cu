@@ -279,17 +279,18 @@ __device__ __forceinline__ void fast_threshold(uint8_t *f_raw, uint8_t *u1_raw, 
 // reflection (see the consumer loop), so both passes are uniform.  Row pass over all GH rows and the BW logical columns
 // into u1 (u16), column pass over the BH rows of the blur ring into s_bl; blur pixels outside the image are 0 (the
 // truncated-window threshold test sums them).  4 outputs per thread-iteration share their taps' loads.
-constexpr int kGaussRB = 7;
-template <int TW, int TH, int HXP, bool NAMED>
+constexpr int kGaussRB = 7;       // stage halo of the variant for kernel sizes 9..15
+constexpr int kGaussRBSmall = 3;  // ... for kernel sizes <= 7
+template <int TW, int TH, int RB, int HXP, bool NAMED>
 __device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const PreprocessParams &p, uint8_t *g_raw, uint8_t *u1_raw,
                                                 uint8_t *bl_raw, int f, int x0, int y0, int tid, uint64_t *empty_bar) {
-    using T = Tile<TW, TH, kGaussRB, HXP>;
+    using T = Tile<TW, TH, RB, HXP>;
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
     uint16_t(*s_r)[T::BW] = reinterpret_cast<uint16_t(*)[T::BW]>(u1_raw);
     uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
     const int ks = p.gauss_ksize, R = ks >> 1;
     const int H = b.h, W = b.w;
-    const int r_skip = kGaussRB - R;  // the column pass reads row-filtered rows r_skip .. GH - 1 - r_skip only
+    const int r_skip = RB - R;  // the column pass reads row-filtered rows r_skip .. GH - 1 - r_skip only
     for (int idx = tid; idx < (T::GH - 2 * r_skip) * (T::BW / 4); idx += 256) {
         const int r = r_skip + idx / (T::BW / 4), i = 4 * (idx % (T::BW / 4));
         const uint8_t *src = &s_g[r][T::GOFF + i - R];  // tap t of output j reads src[j + t]
@@ -309,7 +310,7 @@ __device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const Prepro
         const int r = idx / (T::BW / 4), i = 4 * (idx - r * (T::BW / 4));
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (int t = 0; t < ks; t++) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(&s_r[r + kGaussRB - R + t][i]);
+            const uint2 v = *reinterpret_cast<const uint2 *>(&s_r[r + RB - R + t][i]);
             const uint32_t kk = p.gk[t];
             a0 += kk * (v.x & 0xffffu), a1 += kk * (v.x >> 16), a2 += kk * (v.y & 0xffffu), a3 += kk * (v.y >> 16);
         }
@@ -335,9 +336,9 @@ __device__ __forceinline__ void gauss_blur_tile(const BatchView &b, const Prepro
 // per axis and its result is (sum + 32768) >> 16; both passes are exact integer sums, so the order of the passes is free and
 // the common factor 256 can be taken out: v = (g0 + g4) + 4 (g1 + g3) + 6 g2 over rows (<= 4080), h likewise over columns
 // (<= 65280: fits a 16-bit lane), blur = (h + 128) >> 8.  Blur row r (image row y0 - 5 + r) is centred on stage row r + 7.
-template <int TW, int TH, int HXP, bool NAMED>
+template <int TW, int TH, int RB, int HXP, bool NAMED>
 __device__ __forceinline__ void gauss5_fast_blur(uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid, uint64_t *empty_bar) {
-    using T = Tile<TW, TH, kGaussRB, HXP>;
+    using T = Tile<TW, TH, RB, HXP>;
     uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
     uint16_t(*s_v)[T::VP] = reinterpret_cast<uint16_t(*)[T::VP]>(u1_raw);
     uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
@@ -350,7 +351,7 @@ __device__ __forceinline__ void gauss5_fast_blur(uint8_t *g_raw, uint8_t *u1_raw
         uint32_t lo[11], hi[11];
 #pragma unroll
         for (int k = 0; k < 11; k++) {
-            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + 5 + k][4 + 4 * q]);
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + RB - 2 + k][4 + 4 * q]);
             lo[k] = prmt(v, 0, 0x4140);
             hi[k] = prmt(v, 0, 0x4342);
         }
@@ -392,6 +393,112 @@ __device__ __forceinline__ void gauss5_fast_blur(uint8_t *g_raw, uint8_t *u1_raw
     tile_sync<NAMED>();
 }
 
+
+// cv2.GaussianBlur(KS, KS, sigma) for any odd KS in 3..15 whose taps fit a byte, interior tiles.  Both passes of OpenCV's
+// CV_8U path are exact integer sums (8.8 taps, rows into u16, columns into 16.16, one rounding at the end), so their order
+// is free.  Vertical pass first, on the bytes, in packed u16x2 lanes (a lane never exceeds 255 * 256): a thread owns a column
+// quad and seven output rows and streams the 7 + KS - 1 input rows through its fourteen accumulators, fully unrolled.
+// Horizontal pass on the u16 sums with IDP.2A (two taps per instruction, two adjacent columns per 32-bit word): an item is
+// (row, 24 output columns); the outputs whose window starts on an even element use the words as loaded, the others the same
+// words shifted by one element, converted in place between the two halves.  acc starts at 32768: blur = acc >> 16.
+// s_v element index = stage column (logical column + 8), pitch 160.  Blur row r is centred on stage row r + RB.
+template <int TW, int TH, int RB, int HXP, bool NAMED, int KS>
+__device__ __forceinline__ void gauss_fast_blur(const PreprocessParams &p, uint8_t *g_raw, uint8_t *u1_raw, uint8_t *bl_raw, int tid,
+                                                uint64_t *empty_bar) {
+    using T = Tile<TW, TH, RB, HXP>;
+    constexpr int R = KS / 2, VPG = 160, S = 7;
+    static_assert(TW == 128 && TH == 32 && HXP == 16 && T::GW == 160 && T::BH == 42 && T::BW == 144, "thread mappings below");
+    static_assert(R <= RB && R <= 7 && T::BH * VPG * 2 <= T::U1_BYTES, "halo / scratch size");
+    uint8_t(*s_g)[T::GW] = reinterpret_cast<uint8_t(*)[T::GW]>(g_raw);
+    uint16_t(*s_v)[VPG] = reinterpret_cast<uint16_t(*)[VPG]>(u1_raw);
+    uint8_t(*s_bl)[T::BW] = reinterpret_cast<uint8_t(*)[T::BW]>(bl_raw);
+    uint32_t tap[R + 1];  // tap[d] = weight at distance d from the centre
+#pragma unroll
+    for (int d = 0; d <= R; d++) tap[d] = p.gk[R - d];
+    // A. vertical: 40 column quads x 6 segments of 7 blur rows = 240 threads
+    if (tid < 40 * 6) {
+        const int q = tid % 40, seg = tid / 40;
+        const int r0 = seg * S;
+        uint32_t alo[S], ahi[S];
+#pragma unroll
+        for (int k = 0; k < S; k++) alo[k] = 0, ahi[k] = 0;
+#pragma unroll
+        for (int j = 0; j < S + KS - 1; j++) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(&s_g[r0 + RB - R + j][4 * q]);
+            const uint32_t lo = prmt(v, 0, 0x4140), hi = prmt(v, 0, 0x4342);
+#pragma unroll
+            for (int k = 0; k < S; k++) {
+                const int t = j - k;  // tap index of input row j for output row k
+                if (t >= 0 && t < KS) {
+                    const uint32_t wgt = tap[t < R ? R - t : t - R];
+                    alo[k] += wgt * lo;
+                    ahi[k] += wgt * hi;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < S; k++) *reinterpret_cast<uint2 *>(&s_v[r0 + k][4 * q]) = make_uint2(alo[k], ahi[k]);
+    }
+    tile_sync<NAMED>();
+    if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // the gray stage is dead: the producer may refill it
+    // B. horizontal: 42 rows x 6 groups of 24 outputs = 252 threads.  Output j of group g is logical column 24g + j; its
+    //    window starts at element 24g + j + 8 - R.  The group loads elements 24g .. 24g + 47 (24 words).
+    if (tid < 42 * 6) {
+        const int g = tid % 6, r = tid / 6;
+        uint32_t pk[24];
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(&s_v[r][24 * g]);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const uint4 t = src[k];
+                pk[4 * k] = t.x, pk[4 * k + 1] = t.y, pk[4 * k + 2] = t.z, pk[4 * k + 3] = t.w;
+            }
+        }
+        // taps of the window, four to a register: byte m of tw[i] = weight of window element 4i + m (0 beyond KS - 1)
+        constexpr int NT = (KS + 3) / 4;
+        uint32_t tw[NT];
+#pragma unroll
+        for (int i = 0; i < NT; i++) {
+            uint32_t w4 = 0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int t = 4 * i + m;
+                if (t < KS) w4 |= tap[t < R ? R - t : t - R] << (8 * m);
+            }
+            tw[i] = w4;
+        }
+        uint32_t out[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) out[k] = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            if (half == 1) {  // words shifted by one element: pk[i] = elements (2i + 1, 2i + 2)
+#pragma unroll
+                for (int i = 0; i < 23; i++) pk[i] = prmt(pk[i], pk[i + 1], 0x5432);
+            }
+#pragma unroll
+            for (int j = 0; j < 24; j++) {
+                const int s0 = j + 8 - R;  // first window element
+                if ((s0 & 1) != half) continue;
+                const int w0 = s0 >> 1;    // (half == 1: shifted word w0 holds elements s0, s0 + 1)
+                uint32_t acc = 32768u;
+#pragma unroll
+                for (int m = 0; m < (KS + 1) / 2; m++) {
+                    if (m & 1)
+                        acc = __dp2a_hi(pk[w0 + m], tw[m >> 1], acc);
+                    else
+                        acc = __dp2a_lo(pk[w0 + m], tw[m >> 1], acc);
+                }
+                out[j >> 2] |= (acc >> 16) << (8 * (j & 3));
+            }
+        }
+        uint32_t *brow = reinterpret_cast<uint32_t *>(&s_bl[r][24 * g]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) brow[k] = out[k];
+    }
+    tile_sync<NAMED>();
+}
+
 // Everything after the gray tile (+ halo, zero outside the image) sits in shared memory and the flat decision is known:
 // blur + threshold (fast or generic path) and the three outputs.  Block-uniform control flow; contains barriers.
 template <int TW, int TH, int RB, int HXP, bool NAMED>
@@ -415,15 +522,32 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
     if (flat && empty_bar && tid == 0) mbar_arrive(empty_bar);  // every thread is past its flat-test reads of the stage
     if (!flat) {
         const bool fast_thr = TW == 128 && TH == 32 && interior && p.inverse && cth >= 0 && cth <= 255 && !p.force_generic;
-        if (RB == kGaussRB && p.gauss_ksize > 0) {
-            bool done5 = false;
-            if constexpr (RB == kGaussRB && HXP == 16) {
-                if (fast_thr && !p.write_blur && p.gauss_ksize == 5 && p.gk[0] == 16 && p.gk[1] == 64 && p.gk[2] == 96) {
-                    gauss5_fast_blur<TW, TH, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
-                    done5 = true;
+        if (RB > 2 && p.gauss_ksize > 0) {
+            bool done = false;
+            if constexpr (RB > 2 && HXP == 16) {
+                if (fast_thr && !p.write_blur) {
+                    const int ks = p.gauss_ksize;
+                    if (ks == 5 && p.gk[0] == 16 && p.gk[1] == 64 && p.gk[2] == 96) {
+                        gauss5_fast_blur<TW, TH, RB, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
+                        done = true;
+                    } else if (p.gk[ks >> 1] <= 255) {  // (the centre tap is the largest: all of them fit a byte)
+                        done = true;
+                        if constexpr (RB == kGaussRBSmall) {
+                            if (ks == 3) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 3>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else if (ks == 5) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 5>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else if (ks == 7) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 7>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else done = false;
+                        } else {
+                            if (ks == 9) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 9>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else if (ks == 11) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 11>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else if (ks == 13) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 13>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else if (ks == 15) gauss_fast_blur<TW, TH, RB, HXP, NAMED, 15>(p, g_raw, u1_raw, bl_raw, tid, empty_bar);
+                            else done = false;
+                        }
+                    }
                 }
             }
-            if (!done5) gauss_blur_tile<TW, TH, HXP, NAMED>(b, p, g_raw, u1_raw, bl_raw, f, x0, y0, tid, empty_bar);
+            if (!done) gauss_blur_tile<TW, TH, RB, HXP, NAMED>(b, p, g_raw, u1_raw, bl_raw, f, x0, y0, tid, empty_bar);
             if (fast_thr) fast_threshold<128, 32, T::BW, NAMED>(f_raw, u1_raw, bl_raw, tid, cth);
         } else if (RB == 2 && fast_thr && !p.write_blur) {
             fast_blur_rb2<128, 32, HXP, NAMED>(g_raw, u1_raw, bl_raw, tid, empty_bar);
@@ -455,7 +579,7 @@ __device__ __forceinline__ void tile_compute_and_store(const BatchView &b, const
             tile_sync<NAMED>();
             if (empty_bar && tid == 0) mbar_arrive(empty_bar);  // last read of the gray stage is behind us
         }
-        if (!((RB == kGaussRB && p.gauss_ksize > 0) ? fast_thr : (RB == 2 && fast_thr && !p.write_blur))) {
+        if (!((RB > 2 && p.gauss_ksize > 0) ? fast_thr : (RB == 2 && fast_thr && !p.write_blur))) {
             // 3. horizontal 11-sums: output column c uses s_bl columns c + 3 .. c + 13
             for (int idx = tid; idx < T::BH * TW; idx += 256) {
                 const int r = idx / TW, c = idx - r * TW;
@@ -1309,19 +1433,36 @@ __global__ void __launch_bounds__(kK1Threads, (RB == 2 && MR == 0) ? 5 : 4)
                 }
                 if (n_cols) tile_sync<true>();
             }
-            if (try_flat) {  // the rows within reach of the filters (RB + 5 of the 12 halo rows for small kernels), all their
-                             // 16-byte items (4 px more than needed on either side): one contiguous run of items
+            if (try_flat) {  // the rows within reach of the filters (blur radius + 5 of the halo rows)
                 const uint32_t ref4 = 0x01010101u * s_g[T::HALO + TH / 2][T::HX + TW / 2];
-                const int r_skip = kGaussRB - (p.gauss_ksize >> 1);
-                const int nv = (T::GH - 2 * r_skip) * (T::GW / 16);  // <= 560
+                const int r_skip = RB - (p.gauss_ksize >> 1);
+                const int nrows = T::GH - 2 * r_skip;
                 const uint8_t *base = cur_stage + r_skip * T::GW;
-                const uint4 fill = make_uint4(ref4, ref4, ref4, ref4);
-                const uint4 v0 = tid < nv ? *reinterpret_cast<const uint4 *>(base + 16 * tid) : fill;
-                const uint4 v1 = tid + 256 < nv ? *reinterpret_cast<const uint4 *>(base + 16 * (tid + 256)) : fill;
-                const uint4 v2 = tid + 512 < nv ? *reinterpret_cast<const uint4 *>(base + 16 * (tid + 512)) : fill;
-                absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
-                absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
-                absd(v2.x, ref4, acc), absd(v2.y, ref4, acc), absd(v2.z, ref4, acc), absd(v2.w, ref4, acc);
+                if constexpr (RB == kGaussRBSmall) {
+                    // reach <= 8 columns: columns [8, 152), the mapping of the box-blur variant (8 sixteen-byte items per row,
+                    // rows 0..31 one per thread, the rest threads 0..; the two 8-byte edge items of a row: threads 128..)
+                    const uint4 v0 = *reinterpret_cast<const uint4 *>(base + ft0);
+                    absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
+                    if (tid < (nrows - 32) * 8) {
+                        const uint4 v1 = *reinterpret_cast<const uint4 *>(base + ft1);
+                        absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
+                    } else if (tid >= 128 && tid < 128 + 2 * nrows) {
+                        const uint2 v1 = *reinterpret_cast<const uint2 *>(base + fte);
+                        absd(v1.x, ref4, acc), absd(v1.y, ref4, acc);
+                    }
+                } else {  // all 16-byte items of those rows (4 px more than needed on either side): one contiguous run
+                    const int nv = nrows * (T::GW / 16);  // <= 560
+                    const uint4 v0 = *reinterpret_cast<const uint4 *>(base + 16 * tid);  // (nv >= 440)
+                    absd(v0.x, ref4, acc), absd(v0.y, ref4, acc), absd(v0.z, ref4, acc), absd(v0.w, ref4, acc);
+                    if (tid + 256 < nv) {
+                        const uint4 v1 = *reinterpret_cast<const uint4 *>(base + 16 * (tid + 256));
+                        absd(v1.x, ref4, acc), absd(v1.y, ref4, acc), absd(v1.z, ref4, acc), absd(v1.w, ref4, acc);
+                    }
+                    if (tid + 512 < nv) {
+                        const uint4 v2 = *reinterpret_cast<const uint4 *>(base + 16 * (tid + 512));
+                        absd(v2.x, ref4, acc), absd(v2.y, ref4, acc), absd(v2.z, ref4, acc), absd(v2.w, ref4, acc);
+                    }
+                }
             }
         } else if (try_flat) {
             if (box_inside) {
@@ -1483,6 +1624,9 @@ cudaError_t configure_preprocess_tma() {
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TmaSmem<128, 32, kGaussRB>::BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRBSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TmaSmem<128, 32, kGaussRBSmall>::BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TmaSmem<128, 32, 2, 4>::BYTES);
     if (e != cudaSuccess) return e;
@@ -1506,6 +1650,9 @@ cudaError_t configure_preprocess_tma() {
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_tma<128, 32, kGaussRBSmall>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_preprocess<128, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1544,7 +1691,8 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     if (!enc) return cudaSuccess;
     const bool morph = !gauss && (p.morph_open_k > 0 || p.morph_close_k > 0);
     if (morph && !preprocess_tma_morph_supported(b, p, p.morph_open_k, p.morph_close_k)) return cudaSuccess;
-    const int gh = gauss ? Tile<128, 32, kGaussRB, 16>::GH : (morph ? MTile<4>::GH : Tile<128, 32, 2, 16>::GH);
+    const bool gauss_small = gauss && p.gauss_ksize <= 2 * kGaussRBSmall + 1;  // the variant with the smaller halo
+    const int gh = gauss ? (gauss_small ? Tile<128, 32, kGaussRBSmall, 16>::GH : Tile<128, 32, kGaussRB, 16>::GH) : (morph ? MTile<4>::GH : Tile<128, 32, 2, 16>::GH);
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {(cuuint64_t)b.w, (cuuint64_t)b.h, (cuuint64_t)b.n};
     const cuuint64_t strides[2] = {(cuuint64_t)b.gray_row_stride, (cuuint64_t)b.gray_frame_stride};
@@ -1564,7 +1712,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     cfg.blockDim = dim3(kK1Threads);
     // three stages when the kernel runs at three CTAs per SM next to the per-frame CCL kernel (p.stages, set by hv_api.cu)
     const bool s3 = !gauss && p.stages == 3;
-    cfg.dynamicSmemBytes = gauss ? TmaSmem<128, 32, kGaussRB>::BYTES
+    cfg.dynamicSmemBytes = gauss ? (gauss_small ? TmaSmem<128, 32, kGaussRBSmall>::BYTES : TmaSmem<128, 32, kGaussRB>::BYTES)
                                  : (morph ? (s3 ? TmaSmem<128, 32, 2, 4, 3>::BYTES : TmaSmem<128, 32, 2, 4>::BYTES)
                                           : (s3 ? TmaSmem<128, 32, 2, 0, 3>::BYTES : TmaSmem<128, 32, 2>::BYTES));
     cfg.stream = s;
@@ -1582,6 +1730,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
     q.prefetch_tiles = tun.k1_prefetch;
     q.claim_ahead = tun.k1_claim_ahead;
     q.wait_hint_ns = tun.k1_wait_hint_ns;
+    if (gauss_small) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRBSmall>, tmap, b, q, bits_out, sched);
     if (gauss) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, kGaussRB>, tmap, b, q, bits_out, sched);
     if (morph && s3) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 4, 3>, tmap, b, q, bits_out, sched);
     if (morph) return cudaLaunchKernelEx(&cfg, k_preprocess_tma<128, 32, 2, 4>, tmap, b, q, bits_out, sched);

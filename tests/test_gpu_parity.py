@@ -387,6 +387,25 @@ def test_gaussian_fused_into_k1(oracle, detector, k, s, shape):
     check_frame(oracle, detector, tex, min_size=1.0, threshold=5.0, gauss=(k, s), check_blur=(w <= 320))
 
 
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15])
+def test_gaussian_fast_taps_every_kernel_size(oracle, k):
+    """The packed-arithmetic Gaussian of K1's interior tiles (vertical u16x2 pass, horizontal IDP.2A pass; halo 3 for k <= 7,
+    halo 7 above) for every odd kernel size and several sigmas, on a texture where every tile is non-flat and on bottle frames;
+    sigma = 0.1 gives a centre tap of 256, which does not fit a byte and must take the generic taps."""
+    import heimdall_core as hc
+    detector = hc.Detector(0, max_blobs_per_frame=400000, max_defects_per_frame=200000)
+    rng = np.random.default_rng(500 + k)
+    tex = rng.integers(0, 256, (352, 640, 1), dtype=np.uint8)
+    smooth = (rng.integers(0, 256, (44, 80), dtype=np.uint8).repeat(8, 0).repeat(8, 1)[..., None] // 2 + tex // 2).astype(np.uint8)
+    for s in (0.0, 0.7, 2.5):
+        check_frame(oracle, detector, tex, min_size=1.0, threshold=5.0, gauss=(k, s), check_blur=False)
+        check_frame(oracle, detector, smooth, min_size=1.0, threshold=12.0, gauss=(k, s), check_blur=(s == 0.7))
+    fr = synth.bottle_frame(384, 640, 77 + k, contaminants=3)
+    for s in (1.3, 0.1):  # (0.1: the blur is the identity; on the textures that is more components than the detector holds)
+        check_frame(oracle, detector, fr[:, :, None], min_size=1.0, gauss=(k, s), check_blur=False)
+    detector.close()
+
+
 def _gauss_params(k, s):
     import heimdall_core as hc
     return hc.make_params(blur_mode=hc._abi.HV_BLUR_GAUSSIAN, blur_ksize=k, gauss_sigma=s)
