@@ -34,6 +34,7 @@ hv::Tunables read_tunables() {
     t.pipeline_depth = env_int("HV_PIPELINE_DEPTH", t.pipeline_depth, 2, 8);
     t.k1_ctas_per_sm = env_int("HV_K1_CTAS_PER_SM", t.k1_ctas_per_sm, 1, 5);
     t.k1_gauss_ctas = env_int("HV_K1_GAUSS_CTAS", t.k1_gauss_ctas, 1, 4);
+    t.k1_gauss_small_ctas = env_int("HV_K1_GAUSS_SMALL_CTAS", t.k1_gauss_small_ctas, 1, 4);
     t.ccl_small_max_tiles = env_int("HV_CCL_SMALL_MAX_TILES", t.ccl_small_max_tiles, 0, 1 << 30);
     t.k1_ctas_coresident = env_int("HV_K1_CTAS_CORESIDENT", t.k1_ctas_coresident, 1, 5);
     t.defer_depth = env_int("HV_DEFER_DEPTH", t.defer_depth, 1, 3);

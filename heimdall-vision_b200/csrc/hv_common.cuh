@@ -125,7 +125,8 @@ struct Tunables {
     int k1_ctas_coresident = 3;   // HV_K1_CTAS_CORESIDENT: K1 CTAs per SM next to the small per-frame CCL build (1..5)
     int k1_stages_coresident = 2; // HV_K1_STAGES: TMA stages of K1 when it runs at three CTAs per SM next to the CCL kernel (2 | 3)
     int defer_depth = 2;          // HV_DEFER_DEPTH: with HV_FLAG_DEFER_TAIL, how many batches' per-frame kernels are held back (1..3)
-    int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4)
+    int k1_gauss_ctas = 4;        // HV_K1_GAUSS_CTAS (1..4): Gaussian variant, kernel sizes 9..15
+    int k1_gauss_small_ctas = 4;  // HV_K1_GAUSS_SMALL_CTAS (1..4; five with a 40-register build: 0.60 instead of 0.62): Gaussian variant, kernel sizes <= 7
     int k1_lookahead = 2;         // HV_K1_LOOKAHEAD: tiles the TMA producer runs ahead
     int k1_tail_lookahead = 1;    // HV_K1_TAIL_LOOKAHEAD
     int k1_tail_rounds = 0;       // HV_K1_TAIL_ROUNDS

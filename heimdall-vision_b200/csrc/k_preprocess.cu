@@ -1704,7 +1704,7 @@ cudaError_t launch_preprocess_tma(const BatchView &b, const PreprocessParams &p,
         return cudaSuccess;  // fall back to the non-TMA kernel
     const int tiles = b.tiles_x * ((b.h + 31) / 32) * b.n;
     const int gauss_ctas = tunables().k1_gauss_ctas;
-    int grid = num_sms * (gauss ? gauss_ctas : (p.ctas_per_sm > 0 ? std::min(p.ctas_per_sm, k1_ctas_per_sm()) : k1_ctas_per_sm()));
+    int grid = num_sms * (gauss ? (gauss_small ? tunables().k1_gauss_small_ctas : gauss_ctas) : (p.ctas_per_sm > 0 ? std::min(p.ctas_per_sm, k1_ctas_per_sm()) : k1_ctas_per_sm()));
     if (morph) grid = std::min(grid, num_sms * 4);  // 50 KB of shared memory per CTA
     if (grid > tiles) grid = tiles;
     cudaLaunchConfig_t cfg{};
