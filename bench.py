@@ -288,6 +288,31 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
     return out
 
 
+def gpu_numa_affinity(torch, dev_index: int):
+    """Restrict this thread to the CPUs local to the GPU (sysfs local_cpulist of its PCI function); returns what
+    numa_restore needs, or None when the topology is not visible."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        before = os.sched_getaffinity(0)
+        local = cpus & before
+        if not local or local == before:
+            return None
+        os.sched_setaffinity(0, local)
+        return {"before": before, "cpus": len(local), "bdf": bdf}
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
+def numa_restore(state) -> None:
+    if state:
+        os.sched_setaffinity(0, state["before"])
+
+
 def csrc_sha16() -> str:
     """Fingerprint of the kernel sources: the ncu-measured DRAM traffic in profiles/ is only quoted for the code it was
     captured from."""
@@ -601,19 +626,17 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         morph = {"ms_per_step": float(t.item()) / K, "windows": len(wm), "launches_per_step": lm / (len(wm) * K),
                  "parity_checked": bool(okm) and not args.skip_parity}
 
-    # ---- the other BASELINE configs at their stated frame sizes (rank 0 at N = 1): parity of one frame against the oracle,
-    #      then a short timed run (3 windows of 5 steps, median) -- the full tables are tools/bench_configs.py's ----------------
-    other = None
-    if world == 1 and not args.no_other_configs:
-        other = other_configs(hc, synth, torch, stream, peak_gbs(), args.skip_parity)
-
     # ---- end to end: pinned host frames -> H2D -> pipeline -> D2H of the results, through hv_submit / hv_wait -----------------
     n_pin = min(pool_n, max(args.slots, 3))
     pins = []
+    # the staging buffers are allocated and first touched by a thread that runs on the GPU's own NUMA node (first-touch
+    # placement): a ring on the other socket costs a third of the H2D rate on two-socket hosts
+    numa = gpu_numa_affinity(torch, local_rank)
     for p in range(n_pin):
         ptr = det.host_alloc(batch_bytes)
         ctypes.memmove(ptr, pool_host[p].ctypes.data, batch_bytes)
         pins.append(ptr)
+    numa_restore(numa)
     det.set_stream(None)
     inflight = []
 
@@ -647,6 +670,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     for ptr in pins:
         det.host_free(ptr)
     d2h_bytes = nf * (24 + 4 + det.defect_cap * 48)
+
+    # ---- the other BASELINE configs at their stated frame sizes (rank 0 at N = 1): parity of one frame against the oracle,
+    #      then a short timed run (3 windows of 5 steps, median) -- the full tables are tools/bench_configs.py's ----------------
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(hc, synth, torch, stream, peak_gbs(), args.skip_parity)
 
     torch.cuda.synchronize()
     if world > 1:
@@ -734,7 +763,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "how": f"hv_submit/hv_wait, {args.slots} batches in flight, pinned host frames, wall clock, "
                        f"{K * max(1, R // 3)} steps",
-                "h2d_gbs_per_rank": [batch_bytes * K / s / 1e9 for s in e2e_rank]},
+                "h2d_gbs_per_rank": [batch_bytes * K / s / 1e9 for s in e2e_rank],
+                "staging_numa_local": bool(numa)},
         "gpu_launches": int(round(launches / R)),
         # The kernels of consecutive steps overlap (K1 launches follow each other without a gap, the per-frame CCL kernels
         # of the last few steps run beside them), so no kernel's own duration appears in the step: `kernel_ms` is the STEP
