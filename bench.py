@@ -248,10 +248,9 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
         det.set_stream(stream.cuda_stream)
         depth = det.pipeline_depth()
         n_out = 2                     # two sets of output planes (the batch that last wrote a set is retired before it is reused)
-        # (L2-compressible planes pay on sparse masks; the global-memory CCL kernels of the dense case hook with atomics into the
-        #  label plane, which is 1.8x slower on compressible memory: 2.04 vs 1.16 ms per 16 frames -- plain memory there)
-        comp = kind == "bottle"
-        outs = [(det.device_alloc((n, h, w), np.uint8, comp), det.device_alloc((n, h, w), np.int32, comp)) for _ in range(n_out)]
+        outs = [(det.device_alloc((n, h, w), np.uint8), det.device_alloc((n, h, w), np.int32)) for _ in range(n_out)]
+        res_buf, dfx_buf, _ = det._out_arrays(n, None)   # fetched into the same arrays every step (the dense case returns
+                                                         # 180 k defects per batch: allocating 25 MB per fetch is host-bound)
         res = det.detect_device(d_in.data_ptr(), n, h, w, 1, prm, outs[0][0].ptr, outs[0][1].ptr)
         ok = None
         if not skip_parity:
@@ -266,7 +265,7 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
         def step(i):
             tickets.append(det.enqueue_device(d_in.data_ptr(), n, h, w, 1, prm, outs[i % n_out][0].ptr, outs[i % n_out][1].ptr))
             if len(tickets) >= n_out:
-                det.fetch(tickets.pop(0), n)
+                det.fetch_into(tickets.pop(0), res_buf, dfx_buf)
         for i in range(2 * depth):
             step(i)
         torch.cuda.synchronize()
@@ -277,7 +276,7 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
                 step(i)
             evs[r + 1].record(stream)
         while tickets:
-            det.fetch(tickets.pop(0), n)
+            det.fetch_into(tickets.pop(0), res_buf, dfx_buf)
         torch.cuda.synchronize()
         ms = float(np.median([evs[r].elapsed_time(evs[r + 1]) for r in range(3)])) / 5
         gbs = ALG_BYTES_PER_PX * n * h * w / (ms * 1e-3) / 1e9
