@@ -73,7 +73,9 @@ typedef struct {
  * kernel and the next batch's preprocess kernel, whose overlap is what keeps the device busy.  For callers that consume
  * the records (tickets), not the label plane in stream order: with this flag the label plane and the results of the last
  * two batches are complete only after hv_flush / hv_fetch_ticket / hv_stats_get (or two more hv_enqueue_device calls).
- * The mask plane is written by the preprocess kernel and is complete in stream order either way. */
+ * The mask plane is written by the preprocess kernel and is complete in stream order either way.  Rotate at least
+ * hv_pipeline_depth() sets of output planes with it: a batch that writes planes one of the held batches wrote retires that
+ * batch first, which puts its kernel on the stream and waits for it. */
 #define HV_FLAG_DEFER_TAIL 64u
 
 /* Blur selection for the preprocess stage. */
