@@ -247,7 +247,7 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
         det = hc.Detector(torch.cuda.current_device(), max_defects_per_frame=512 if kind == "bottle" else 32768)
         det.set_stream(stream.cuda_stream)
         depth = det.pipeline_depth()
-        n_out = 2                     # two sets of output planes (the batch that last wrote a set is retired before it is reused)
+        n_out = depth                 # as many sets of output planes as the library keeps batches in flight
         outs = [(det.device_alloc((n, h, w), np.uint8), det.device_alloc((n, h, w), np.int32)) for _ in range(n_out)]
         res_buf, dfx_buf, _ = det._out_arrays(n, None)   # fetched into the same arrays every step (the dense case returns
                                                          # 180 k defects per batch: allocating 25 MB per fetch is host-bound)

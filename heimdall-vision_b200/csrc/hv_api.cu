@@ -38,6 +38,7 @@ hv::Tunables read_tunables() {
     t.ccl_small_max_tiles = env_int("HV_CCL_SMALL_MAX_TILES", t.ccl_small_max_tiles, 0, 1 << 30);
     t.k1_ctas_coresident = env_int("HV_K1_CTAS_CORESIDENT", t.k1_ctas_coresident, 1, 5);
     t.defer_depth = env_int("HV_DEFER_DEPTH", t.defer_depth, 1, 3);
+    t.no_side_ccl = env_flag("HV_NO_SIDE_CCL");
     t.k1_stages_coresident = env_int("HV_K1_STAGES", t.k1_stages_coresident, 2, 3);
     t.k1_lookahead = env_int("HV_K1_LOOKAHEAD", t.k1_lookahead, 1, 8);
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
@@ -225,6 +226,8 @@ struct Slot {
     bool used_small = false;  // ... its small build
     bool used_tiny = false;   // ... its tiny build
     bool tail_deferred = false;  // its per-frame kernel was held back when the batch was enqueued (HV_FLAG_DEFER_TAIL)
+    bool tail_on_side = false;   // its global-memory CCL kernels went onto the slot's own stream (HV_FLAG_DEFER_TAIL)
+    cudaStream_t tail_stream = nullptr;  // the stream its last kernel is on
     bool sparse_bits = false; // K1 left the bit-mask words of flat tiles unwritten (densify before any other reader)
     ScoreParams score{};
     DevBuf<int32_t> labels;
@@ -308,6 +311,7 @@ struct hv_ctx {
     // ... and the tiny one once a batch has reported (frame flags) that all its frames would fit it
     bool ccl_tiny_ok = false;
     uint32_t ccl_tiny_cooldown = 0;
+    bool tail_used = false;  // kernels went onto slot streams since the last hv_flush
     // HV_FLAG_DEFER_TAIL: the per-frame kernel (and the read-back behind it) of the latest hv_enqueue_device batch, not yet
     // on the stream (flush_deferred)
     struct DeferredTail {
@@ -827,6 +831,7 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     }
     ScoreParams sp{pr.min_size, pr.max_size, pr.min_confidence};
     bool deferred_now = false;
+    cudaStream_t tail_stream = st;  // the stream the batch's last kernel is on
     if (fused && tun.exp_k1_only) {
         // experiment: K1 chain alone (results are NOT computed)
     } else if (fused) {
@@ -852,14 +857,28 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         s.used_small = ccl_small && !ccl_tiny;
         s.used_tiny = ccl_tiny;
     } else {
+        // HV_FLAG_DEFER_TAIL on the global path (dense frames): the five CCL kernels of a batch go onto the slot's own stream
+        // behind an event on K1, so that K1 of the next batch (issue-bound on such frames) runs beside them (latency- and
+        // atomics-bound) instead of behind them.  Same contract as the deferred per-frame kernel: labels and results are
+        // complete after hv_flush / hv_fetch_ticket.
+        cudaStream_t cs = st;
+        if (may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && ctx->prof_mask == 0 && s.stream != st && !tun.no_side_ccl) {
+            HV_TRY_CUDA(ctx, cudaEventRecord(s.done, st));
+            HV_TRY_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.done, 0));
+            cs = s.stream;
+            s.tail_on_side = true;
+            ctx->tail_used = true;
+        }
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
-            HV_TRY_CUDA(ctx, launch_densify_bits(b, st));
+            HV_TRY_CUDA(ctx, launch_densify_bits(b, cs));
             ctx->launches++;
         }
-        hv_status rg = enqueue_global_ccl(ctx, b, sp, st);
+        hv_status rg = enqueue_global_ccl(ctx, b, sp, cs);
         if (rg != HV_OK) return rg;
+        tail_stream = cs;
     }
     s.tail_deferred = deferred_now;
+    s.tail_stream = tail_stream;
     s.used_fused = fused;
     s.sparse_bits = pp.sparse_aux != 0 || (morph_fused && fused);  // (fused morphology: tiles out of reach of foreground have no bit words)
     s.score = sp;
@@ -1364,7 +1383,7 @@ hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int
     if (ticket) *ticket = s.ticket;
     if (tunables().exp_k1_only) return HV_OK;  // (experiment builds: nothing computes results)
     if (!s.tail_deferred) {  // (a deferred tail brings its read-back along: flush_deferred)
-        rs = enqueue_async_readback(ctx, s, st);
+        rs = enqueue_async_readback(ctx, s, s.tail_stream);
         if (rs != HV_OK) return rs;
     }
     s.pending = true;
@@ -1376,6 +1395,18 @@ hv_status hv_flush(hv_ctx *ctx) {
     HV_TRY_CUDA(ctx, cudaSetDevice(ctx->device));
     hv_status rs = flush_deferred(ctx);
     if (rs != HV_OK) return rs;
+    if (ctx->tail_used) {  // the launching stream waits for the kernels that went onto slot streams
+        cudaStream_t st = sync_stream(ctx);
+        for (int k = 0; k < kSyncSlots; k++) {
+            Slot &q = ctx->slots[k];
+            if (!q.tail_on_side || q.stream == st) continue;
+            HV_TRY_CUDA(ctx, cudaEventRecord(q.done, q.stream));
+            HV_TRY_CUDA(ctx, cudaStreamWaitEvent(st, q.done, 0));
+            q.tail_on_side = false;
+        }
+        ctx->tail_used = false;
+        ctx->last_valid = false;
+    }
     return HV_OK;
 }
 

@@ -148,6 +148,7 @@ struct Tunables {
     bool no_fused_gauss = false;  // HV_NO_FUSED_GAUSS
     bool no_fused_morph = false;  // HV_NO_FUSED_MORPH
     bool no_morph_chain = false;  // HV_NO_MORPH_CHAIN
+    bool no_side_ccl = false;     // HV_NO_SIDE_CCL: with HV_FLAG_DEFER_TAIL, keep the global-memory CCL kernels on the launching stream
     bool no_k1_morph = false;     // HV_NO_K1_MORPH: never fold 3x3 / 5x5 open+close into K1 (use the tiles kernel)
     bool exp_k1_only = false;     // HV_EXP_K1_ONLY  (-DHV_EXPERIMENTS only): K1 chain alone, NO results
     int exp_ccl_stop = 0;         // HV_EXP_CCL_STOP (with HV_EXP_CCL_NOOP): the per-frame kernel returns after phase k

@@ -73,7 +73,10 @@ typedef struct {
  * kernel and the next batch's preprocess kernel, whose overlap is what keeps the device busy.  For callers that consume
  * the records (tickets), not the label plane in stream order: with this flag the label plane and the results of the last
  * two batches are complete only after hv_flush / hv_fetch_ticket / hv_stats_get (or two more hv_enqueue_device calls).
- * The mask plane is written by the preprocess kernel and is complete in stream order either way.  Rotate at least
+ * The mask plane is written by the preprocess kernel and is complete in stream order either way.  The held kernels read
+ * the batch's input frames (the contrast probe of the scoring): the frames must stay unchanged until the batch has been
+ * fetched or flushed.  Batches that take the global-memory CCL kernels (dense frames) run those on a stream of the
+ * context's own, beside the next batch's preprocess kernel, under the same contract.  Rotate at least
  * hv_pipeline_depth() sets of output planes with it: a batch that writes planes one of the held batches wrote retires that
  * batch first, which puts its kernel on the stream and waits for it. */
 #define HV_FLAG_DEFER_TAIL 64u

@@ -867,7 +867,8 @@ def test_streaming_finishes_flagged_frames_without_fetch(oracle):
         det.close()
 
 
-def test_deferred_tail_streaming_with_work_between_batches(oracle):
+@pytest.mark.parametrize("global_ccl", [False, True])
+def test_deferred_tail_streaming_with_work_between_batches(oracle, global_ccl):
     """HV_FLAG_DEFER_TAIL: the per-frame kernel of a batch goes onto the stream with the next call.  A streaming loop that
     records an event between every two batches, synchronizes the whole device while a tail is held back, rotates one and
     several plane sets, contains a frame the per-frame kernel cannot hold, and finally closes a context with a tail still
@@ -882,7 +883,8 @@ def test_deferred_tail_streaming_with_work_between_batches(oracle):
     refs = [[oracle.detect_contamination(b[f][:, :, None]) for f in range(n)] for b in batches]
     st = torch.cuda.current_stream().cuda_stream
     for n_sets in (1, 6):
-        det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=20000, defer_tail=True)
+        # (global_ccl: every batch through the global-memory kernels, which the flag puts onto the slots' own streams)
+        det = hc.Detector(0, max_blobs_per_frame=100000, max_defects_per_frame=20000, defer_tail=True, global_ccl=global_ccl)
         try:
             det.set_stream(st)
             depth = det.pipeline_depth()

@@ -45,11 +45,11 @@ def tile_batch(distinct, n):
 NSETS = int(os.environ.get("BENCH_SETS", "6"))  # output-plane sets in rotation (= hv_pipeline_depth(): no batch waits for another's planes)
 
 
-def run(name, batch, params, okw, steps, check_frames=(0,)):
+def run(name, batch, params, okw, steps, check_frames=(0,), defer=False):
     if only and not any(o in name for o in only):
         return True
     n, h, w = batch.shape
-    det = hc.Detector(0, max_defects_per_frame=512 if h * w < 8_000_000 else 32768, defer_tail=os.environ.get("BENCH_DEFER", "0") == "1")
+    det = hc.Detector(0, max_defects_per_frame=512 if h * w < 8_000_000 else 32768, defer_tail=defer or os.environ.get("BENCH_DEFER", "0") == "1")
     det.set_stream(st)
     d_in = torch.from_numpy(batch).cuda()
     outs = [(torch.empty((n, h, w), dtype=torch.uint8, device="cuda"), torch.empty((n, h, w), dtype=torch.int32, device="cuda"))
@@ -116,6 +116,8 @@ del five
 n12 = 4 if quick else 16
 twelve = tile_batch([synth.high_contamination_frame(3000, 4096, i) for i in range(2)], n12)
 run("C4 12 MP, >10k blobs/frame (global-memory CCL path)", twelve, hc.make_params(), {}, 3 if quick else 6)
+run("C4 12 MP, the same with HV_FLAG_DEFER_TAIL (CCL kernels on the slots' streams beside the next K1)", twelve, hc.make_params(),
+    {}, 3 if quick else 6, defer=True)
 del twelve
 # ---- configs[4] on one GPU: 8 camera streams x 5 MP, one batch per stream round (bench.py --gpus N shards streams) ----
 streams = tile_batch([synth.bottle_frame(2048, 2448, 900 + i, contaminants=i % 3) for i in range(8)], 8)
