@@ -799,18 +799,37 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         b.k1_wait_value = s.k1_expected;
     }
     bool morph_fused = false;
+    // HV_FLAG_DEFER_TAIL, batches whose kernels behind K1 are long (morphology through the tiles kernels without the counter
+    // chain, the global-memory CCL kernels): everything behind K1 goes onto the slot's own stream behind an event on K1, so
+    // that K1 of the next batch runs beside those latency-bound kernels instead of behind them.  Same contract as the
+    // deferred per-frame kernel: labels and results are complete after hv_flush / hv_fetch_ticket.
+    cudaStream_t ts = st;
+    auto to_side_stream = [&]() -> cudaError_t {
+        if (ts != st) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(s.done, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(s.stream, s.done, 0);
+        if (e != cudaSuccess) return e;
+        ts = s.stream;
+        s.tail_on_side = true;
+        ctx->tail_used = true;
+        return cudaSuccess;
+    };
+    const bool side_ok = may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && ctx->prof_mask == 0 && s.stream != st &&
+                         !tun.no_side_ccl;
     if (morph) {
         ProfScope ps(ctx, HV_K_MORPH, st);
+        if (side_ok && !morph_chain) HV_TRY_CUDA(ctx, to_side_stream());
         if (morph_fused_plan) {
             // open + close + expansion in one kernel, launched ahead of K1's completion; its result goes to the other
             // bit plane, which is the one the CCL reads from here on
-            const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !tun.no_pdl;
+            const bool pdl_mid = k1_tma && ctx->prof_mask == 0 && !tun.no_pdl && ts == st;
             // counter chain: the scan waits for K1's launch counter (b.k1_done), the tiles kernel for the scan's, and the
             // per-frame CCL kernel for the tiles kernel's (handed to it in the k1_done fields)
             unsigned int *chain = (b.k1_done && morph_chain) ? s.sched.p + 10 : nullptr;
             if (chain) s.scan_expected++;
             HV_TRY_CUDA(ctx, launch_morph_expand(b, pr.morph_open_k, pr.morph_close_k, b.bits_tmp, s.rowflags_tmp.p,
-                                                 s.tile_list.p, s.sched.p + 4, chain, s.scan_expected, ctx->num_sms, pdl_mid, st));
+                                                 s.tile_list.p, s.sched.p + 4, chain, s.scan_expected, ctx->num_sms, pdl_mid, ts));
             std::swap(b.bits, b.bits_tmp);
             b.rowflags = s.rowflags_tmp.p;
             if (chain) {
@@ -824,8 +843,8 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
             morph_fused = true;
         } else {
             int nl = 0;
-            HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, st));
-            HV_TRY_CUDA(ctx, launch_expand_bits(b, st));
+            HV_TRY_CUDA(ctx, launch_morph(b, pr.morph_open_k, pr.morph_close_k, &nl, ts));
+            HV_TRY_CUDA(ctx, launch_expand_bits(b, ts));
             ctx->launches += nl + 1;
         }
     }
@@ -850,25 +869,16 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
             ctx->deferred.push_back(d);
             deferred_now = true;
         } else {
-            HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, level, st));
+            HV_TRY_CUDA(ctx, launch_ccl_frame(b, sp, pdl_tail, level, ts));
             ctx->launches += 1;
+            tail_stream = ts;
         }
         s.ccl_expected += (uint32_t)n;
         s.used_small = ccl_small && !ccl_tiny;
         s.used_tiny = ccl_tiny;
     } else {
-        // HV_FLAG_DEFER_TAIL on the global path (dense frames): the five CCL kernels of a batch go onto the slot's own stream
-        // behind an event on K1, so that K1 of the next batch (issue-bound on such frames) runs beside them (latency- and
-        // atomics-bound) instead of behind them.  Same contract as the deferred per-frame kernel: labels and results are
-        // complete after hv_flush / hv_fetch_ticket.
-        cudaStream_t cs = st;
-        if (may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && ctx->prof_mask == 0 && s.stream != st && !tun.no_side_ccl) {
-            HV_TRY_CUDA(ctx, cudaEventRecord(s.done, st));
-            HV_TRY_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.done, 0));
-            cs = s.stream;
-            s.tail_on_side = true;
-            ctx->tail_used = true;
-        }
+        if (side_ok) HV_TRY_CUDA(ctx, to_side_stream());  // (dense frames: the five global-memory CCL kernels)
+        cudaStream_t cs = ts;
         if (morph_fused) {  // the global path scans every word: give the tiles the morphology skipped their zero words
             HV_TRY_CUDA(ctx, launch_densify_bits(b, cs));
             ctx->launches++;

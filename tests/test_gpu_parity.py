@@ -925,6 +925,55 @@ def test_deferred_tail_streaming_with_work_between_batches(oracle, global_ccl):
     torch.cuda.synchronize()
 
 
+def test_deferred_tail_long_kernels_on_side_streams(oracle):
+    """HV_FLAG_DEFER_TAIL with batches whose kernels behind K1 are long -- morphology through the tiles kernels on a batch too
+    big for the counter chain (> 16384 tiles), and dense frames through the global-memory CCL kernels: they run on the slot's
+    own stream beside the next batch's K1.  Records of every batch and the planes after hv_flush equal the oracle's."""
+    import torch
+
+    import heimdall_core as hc
+    st = torch.cuda.current_stream().cuda_stream
+    cases = [("morph7", [synth.bottle_frame(2048, 2448, 610 + i, contaminants=2 + i) for i in range(2)], 13,
+              dict(morph_open_k=7, morph_close_k=7)),
+             ("dense", [synth.high_contamination_frame(768, 1024, 5 + i) for i in range(2)], 4, {})]
+    for name, distinct, n, mk in cases:
+        h, w = distinct[0].shape
+        refs = [oracle.detect_contamination(d[:, :, None], **mk) for d in distinct]
+        batch = np.stack([distinct[i % 2] for i in range(n)])
+        det = hc.Detector(0, max_blobs_per_frame=200000, max_defects_per_frame=60000, defer_tail=True,
+                          global_ccl=(name == "dense"))
+        try:
+            det.set_stream(st)
+            depth = det.pipeline_depth()
+            d_in = torch.from_numpy(batch).cuda()
+            masks = [det.device_alloc((n, h, w), np.uint8) for _ in range(depth)]
+            labels = [det.device_alloc((n, h, w), np.int32) for _ in range(depth)]
+            params = hc.make_params(**mk)
+            tickets, fetched = [], []
+            steps = 9
+            for i in range(steps):
+                tickets.append(det.enqueue_device(d_in.data_ptr(), n, h, w, 1, params, masks[i % depth].ptr, labels[i % depth].ptr))
+                torch.cuda.Event().record()
+                if i >= depth - 1:
+                    fetched.append(det.fetch(tickets[i - depth + 1], n))
+            det.flush()
+            torch.cuda.synchronize()
+            k = (steps - 1) % depth
+            for f in (0, 1, n - 1):
+                assert np.array_equal(masks[k].get(f, 1)[0], refs[f % 2].mask), (name, f)
+                assert np.array_equal(labels[k].get(f, 1)[0], refs[f % 2].labels), (name, f)
+            for i in range(steps - depth + 1, steps):
+                fetched.append(det.fetch(tickets[i], n))
+            assert len(fetched) == steps
+            for r in fetched:
+                for f in range(n):
+                    got = [((int(d["y"]), int(d["x"])), float(d["size"]), float(d["confidence"])) for d in r.defects_of(f)]
+                    assert got == [(d["position"], d["size"], d["confidence"]) for d in refs[f % 2].defects], (name, f)
+            assert det.stats()["frames_inspected"] == n * steps
+        finally:
+            det.close()
+
+
 def test_enqueue_refuses_graph_capture():
     """The kernels of consecutive batches are ordered by device-side counters whose expected values are kernel arguments:
     replaying a captured graph would replay stale values.  hv_enqueue_device refuses a capturing stream."""

@@ -111,12 +111,15 @@ for sig in (0.0, 1.0, 2.0, 3.0):
 for k in (3, 7, 11, 15):
     run(f"C3 5 MP, morphology open+close k={k}", five, hc.make_params(morph_open_k=k, morph_close_k=k),
         dict(morph_open_k=k, morph_close_k=k), 3 if quick else 6)
+    if k > 3:  # (tiles kernels behind K1: with the flag they run on the slots' streams beside the next batch's K1)
+        run(f"C3 5 MP, morphology open+close k={k}, HV_FLAG_DEFER_TAIL", five, hc.make_params(morph_open_k=k, morph_close_k=k),
+            dict(morph_open_k=k, morph_close_k=k), 3 if quick else 6, defer=True)
 del five
 # ---- configs[3]: 12 MP 4096x3000 high-contamination frames (10k+ blobs per frame) -------------------------------------
 n12 = 4 if quick else 16
 twelve = tile_batch([synth.high_contamination_frame(3000, 4096, i) for i in range(2)], n12)
 run("C4 12 MP, >10k blobs/frame (global-memory CCL path)", twelve, hc.make_params(), {}, 3 if quick else 6)
-run("C4 12 MP, the same with HV_FLAG_DEFER_TAIL (CCL kernels on the slots' streams beside the next K1)", twelve, hc.make_params(),
+run("C4 12 MP, >10k blobs/frame, HV_FLAG_DEFER_TAIL", twelve, hc.make_params(),
     {}, 3 if quick else 6, defer=True)
 del twelve
 # ---- configs[4] on one GPU: 8 camera streams x 5 MP, one batch per stream round (bench.py --gpus N shards streams) ----
