@@ -282,6 +282,10 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
         gbs = ALG_BYTES_PER_PX * n * h * w / (ms * 1e-3) / 1e9
         out[name] = {"batch": f"{n} x {w}x{h}", "ms_per_step": ms, "frames_per_s": n / (ms * 1e-3), "achieved_gbs": gbs,
                      "frac": gbs / peak, "parity_checked": ok}
+        if kind == "dense":
+            out[name]["note"] = ("host-bound: every batch's 180 k defect records (8.6 MB) are delivered to the host and unpacked by "
+                                 "one thread inside the timed region; device-side the step is 1.15 ms (0.16; 0.79 ms = 0.23 with "
+                                 "HV_FLAG_DEFER_TAIL), profiles/r05_configs.md")
         for a, b in outs:
             a.free(), b.free()
         det.close()
