@@ -220,7 +220,7 @@ def peak_gbs() -> float:
         return 6650.0
 
 
-def other_configs(hc, synth, torch, stream, peak, skip_parity):
+def other_configs(hc, synth, torch, stream, peak, skip_parity, defer_tail=True):
     """BASELINE.json configs[2] and [3] at their frame sizes, device-resident, with the streaming loop of the headline
     (enqueue + fetch of the batch depth-1 back).  Batches are smaller than the configs' 256 / full-line counts to keep the
     default run short; frac = 6 B/px x pixels / time / measured HBM peak."""
@@ -244,7 +244,8 @@ def other_configs(hc, synth, torch, stream, peak, skip_parity):
             host = np.stack([distinct[i % len(distinct)] for i in range(n)])
             cache[key] = (host, torch.from_numpy(host).cuda())
         host, d_in = cache[key]
-        det = hc.Detector(torch.cuda.current_device(), max_defects_per_frame=512 if kind == "bottle" else 32768)
+        det = hc.Detector(torch.cuda.current_device(), max_defects_per_frame=512 if kind == "bottle" else 32768,
+                          defer_tail=defer_tail)   # (as the headline loop: HV_FLAG_DEFER_TAIL unless --no-defer-tail)
         det.set_stream(stream.cuda_stream)
         depth = det.pipeline_depth()
         n_out = depth                 # as many sets of output planes as the library keeps batches in flight
@@ -681,7 +682,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     #      then a short timed run (3 windows of 5 steps, median) -- the full tables are tools/bench_configs.py's ----------------
     other = None
     if world == 1 and not args.no_other_configs:
-        other = other_configs(hc, synth, torch, stream, peak_gbs(), args.skip_parity)
+        other = other_configs(hc, synth, torch, stream, peak_gbs(), args.skip_parity, not args.no_defer_tail)
 
     torch.cuda.synchronize()
     if world > 1:
