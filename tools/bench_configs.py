@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
 """Throughput of the BASELINE.json configs other than the headline one (configs[2..4]); the headline config is
-bench.py's.  Device-resident inputs, CUDA events on the launching stream, steady state (buffers alternate).
+bench.py's.  Device-resident inputs, CUDA events on the launching stream, steady state (hv_pipeline_depth() sets of output
+planes in rotation).
 Every case is checked against the oracle on one frame before it is timed (measurement infrastructure like bench.py: the
 oracle is the checker here, never the thing measured).  Writes a markdown table.
 
-usage: bench_configs.py [out.md] [--quick]
+usage: bench_configs.py [out.md] [--quick] [--only=<substring of a row name>]...
+environment: BENCH_SETS (6) sets of output planes in rotation; BENCH_DEFER=1 creates every context with HV_FLAG_DEFER_TAIL
+(the rows that name the flag always do)
 """
 import json
 import os

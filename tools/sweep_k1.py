@@ -1,6 +1,8 @@
 """Headline batch (25 x 1280x1024), steady state as in bench.py (8 rotating input batches, 2 output sets): step time with the
 K1/CCL overlap, and K1 alone (events around every launch).  Environment switches (HV_K1_*) are read by the library once per
-process, so run one process per variant:  HV_K1_LOOKAHEAD=2 python tools/sweep_k1.py"""
+process, so run one process per variant:  HV_K1_LOOKAHEAD=2 python tools/sweep_k1.py
+SWEEP_N/H/W (batch shape), SWEEP_POOL, SWEEP_OUTS, SWEEP_COMPRESS, SWEEP_MORPH=k, SWEEP_GAUSS=k,sigma, SWEEP_DEFER=1
+(HV_FLAG_DEFER_TAIL); HEIMDALL_CUDA_LIB=<path> runs another build of the library (A/B inside one gpurun call)."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, 'heimdall-vision_b200'); sys.path.insert(0, '.')
 import heimdall_core as hc, synth
