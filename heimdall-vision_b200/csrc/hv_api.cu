@@ -44,7 +44,7 @@ hv::Tunables read_tunables() {
     t.k1_tail_lookahead = env_int("HV_K1_TAIL_LOOKAHEAD", t.k1_tail_lookahead, 1, 8);
     t.k1_tail_rounds = env_int("HV_K1_TAIL_ROUNDS", t.k1_tail_rounds, 0, 1 << 20);
     t.k1_prefetch = env_int("HV_K1_PREFETCH", t.k1_prefetch, 0, 1 << 20);
-    t.k1_claim_ahead = env_int("HV_K1_CLAIM_AHEAD", t.k1_claim_ahead, 0, 1);
+    t.k1_claim_ahead = env_int("HV_K1_CLAIM_AHEAD", t.k1_claim_ahead, -1, 1);
     t.k1_wait_hint_ns = env_int("HV_K1_WAIT_HINT_NS", t.k1_wait_hint_ns, 0, 2000000000);
     t.morph_tiles_per_sm = env_int("HV_MORPH_TILES_PER_SM", t.morph_tiles_per_sm, 1, 8);
     t.phase_frame = env_int("HV_PHASE_FRAME", 0, 0, 1 << 20);

@@ -131,7 +131,7 @@ struct Tunables {
     int k1_tail_lookahead = 1;    // HV_K1_TAIL_LOOKAHEAD
     int k1_tail_rounds = 0;       // HV_K1_TAIL_ROUNDS
     int k1_prefetch = 0;          // HV_K1_PREFETCH: L2 tensor prefetch distance in tiles (0 = off)
-    int k1_claim_ahead = 0;       // HV_K1_CLAIM_AHEAD
+    int k1_claim_ahead = -1;      // HV_K1_CLAIM_AHEAD: 0 / 1, -1 = when K1 runs at reduced residency (see launch_preprocess_tma)
     int k1_wait_hint_ns = 10000000;  // HV_K1_WAIT_HINT_NS
     int ccl_small_max_tiles = 32768;  // HV_CCL_SMALL_MAX_TILES: batches with more 128x32 tiles use the big per-frame CCL build
     int morph_tiles_per_sm = 2;   // HV_MORPH_TILES_PER_SM
