@@ -700,7 +700,11 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
     // (only for small batches: the chain needs the tiles kernel resident as a whole, two CTAs per SM, which pays when launch
     // gaps and serialisation dominate -- 8000 tiles: 78 -> 66 us -- and costs when the kernels are long -- 256 x 5 MP: 2.0 ->
     // 2.6 ms)
-    const bool morph_chain = morph_fused_plan && !tun.no_morph_chain &&
+    // (HV_FLAG_DEFER_TAIL: long kernels behind K1 go onto the slot's own stream, see below; for the morphology tiles kernels
+    //  that also beats the counter chain on small batches -- headline batch, open+close k = 7 / 15: 69.3 / 83.1 -> 65.2 / 78.3 us)
+    const bool side_ok = may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && ctx->prof_mask == 0 && s.stream != st &&
+                         !tun.no_side_ccl;
+    const bool morph_chain = morph_fused_plan && !tun.no_morph_chain && !side_ok &&
                              (size_t)n * ((h + 31) / 32) * ((w + 127) / 128) <= 16384;
     bool ccl_small = fused && (!morph || morph_chain) && !gauss && !box_other && c == 1 && b.ccl_done && !tun.ccl_big;
     if (!ctx->ccl_small_ok) ccl_small = false;  // until the big build reports frames that fit the small one again
@@ -815,8 +819,6 @@ hv_status enqueue_pipeline(hv_ctx *ctx, Slot &s, cudaStream_t st, const uint8_t 
         ctx->tail_used = true;
         return cudaSuccess;
     };
-    const bool side_ok = may_defer && (ctx->cfg.flags & HV_FLAG_DEFER_TAIL) && ctx->prof_mask == 0 && s.stream != st &&
-                         !tun.no_side_ccl;
     if (morph) {
         ProfScope ps(ctx, HV_K_MORPH, st);
         if (side_ok && !morph_chain) HV_TRY_CUDA(ctx, to_side_stream());

@@ -935,6 +935,8 @@ def test_deferred_tail_long_kernels_on_side_streams(oracle):
     st = torch.cuda.current_stream().cuda_stream
     cases = [("morph7", [synth.bottle_frame(2048, 2448, 610 + i, contaminants=2 + i) for i in range(2)], 13,
               dict(morph_open_k=7, morph_close_k=7)),
+             ("morph7small", [synth.bottle_frame(512, 640, 650 + i, contaminants=1 + i) for i in range(2)], 3,
+              dict(morph_open_k=7, morph_close_k=7)),   # (small batch: the flag prefers the slot's stream to the counter chain)
              ("dense", [synth.high_contamination_frame(768, 1024, 5 + i) for i in range(2)], 4, {})]
     for name, distinct, n, mk in cases:
         h, w = distinct[0].shape
