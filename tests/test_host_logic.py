@@ -140,6 +140,70 @@ def test_gaussian_q8_kernels_sum_to_256():
             assert int(kk.sum()) == 256 and np.array_equal(kk, kk[::-1])
 
 
+def test_gaussian_packed_pass_model_equals_the_oracle():
+    """The arithmetic of K1's packed Gaussian taps (k_preprocess.cu, gauss_fast_blur), modelled in numpy on the interior of
+    an image: vertical pass first on the bytes (every lane stays below 2^16: a u16x2 lane never carries), horizontal pass as
+    sums of two-tap products with a 32-bit accumulator that starts at 32768 (IDP.2A), blur = acc >> 16 -- equal to the
+    oracle's rows-then-columns cv2.GaussianBlur restatement for every odd kernel size 3..15 whose taps fit a byte."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, (96, 128), dtype=np.uint8)
+    img[:8] = 255                                            # saturated region: the lanes' worst case
+    for k in range(3, 16, 2):
+        for sg in (0.0, 0.7, 2.5, 0.1):
+            taps = O.gaussian_kernel_q8(k, sg).astype(np.uint32)
+            if taps.max() > 255:
+                assert sg == 0.1                             # (the kernel sends these to the generic taps)
+                continue
+            r = k // 2
+            v = np.zeros(img.shape, np.uint32)
+            for t in range(k):                               # vertical: v[y] = sum_t taps[t] * img[y - r + t]
+                v[r:-r] += taps[t] * img[t:img.shape[0] - 2 * r + t].astype(np.uint32)
+            assert int(v.max()) <= 255 * 256 < 65536
+            acc = np.full(img.shape, 32768, np.uint32)
+            for m in range((k + 1) // 2):                    # horizontal, two taps per step (the odd tail pairs with a 0)
+                t0, t1 = 2 * m, 2 * m + 1
+                acc[:, r:-r] += taps[t0] * v[:, t0:img.shape[1] - 2 * r + t0]
+                if t1 < k:
+                    acc[:, r:-r] += taps[t1] * v[:, t1:img.shape[1] - 2 * r + t1]
+            got = (acc >> 16).astype(np.uint8)
+            ref = O.gaussian_blur(img, k, sg)
+            assert np.array_equal(got[r:-r, r:-r], ref[r:-r, r:-r]), (k, sg)
+
+
+def test_bench_reads_the_gpu_local_cpu_list(tmp_path, monkeypatch):
+    """bench.py binds the thread that allocates the pinned staging buffers to the GPU's NUMA node (sysfs local_cpulist);
+    without the sysfs entry, or when the list is the whole affinity mask, it leaves the affinity alone."""
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    class Props:
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0x1b, 0
+
+    fake = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: Props()))
+    before = os.sched_getaffinity(0)
+    assert bench.gpu_numa_affinity(fake, 0) is None or os.sched_getaffinity(0) <= before   # (no such PCI function here)
+    bench.numa_restore(None)
+    os.sched_setaffinity(0, before)
+    real_open = open
+    first = sorted(before)[0]
+
+    def fake_open(path, *a, **k):
+        if str(path).endswith("0000:1b:00.0/local_cpulist"):
+            import io
+            return io.StringIO(f"{first}-{first}\n")
+        return real_open(path, *a, **k)
+    monkeypatch.setattr("builtins.open", fake_open)
+    state = bench.gpu_numa_affinity(fake, 0)
+    if len(before) > 1:
+        assert state is not None and os.sched_getaffinity(0) == {first} and state["before"] == before
+    bench.numa_restore(state)
+    assert os.sched_getaffinity(0) == before
+
+
 def test_synthetic_frames_are_deterministic():
     import synth
     a = synth.bottle_frame(128, 160, 3)
