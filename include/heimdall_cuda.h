@@ -254,7 +254,10 @@ HV_API hv_status hv_detect_batch_device(hv_ctx *ctx, const uint8_t *d_frames, in
 HV_API hv_status hv_enqueue_device(hv_ctx *ctx, const uint8_t *d_frames, int32_t n, int32_t h, int32_t w, int32_t c,
                                    size_t row_stride, size_t frame_stride, const hv_params *params, uint8_t *d_mask,
                                    int32_t *d_labels, int64_t *ticket);
-/* HV_FLAG_DEFER_TAIL: puts the kernels held back (and their read-backs) onto the stream now.  A no-op otherwise. */
+/* HV_FLAG_DEFER_TAIL: puts the kernels held back (and their read-backs) onto the stream now and makes the stream wait for
+ * the kernels that went onto streams of the context's own: after it, the planes of every enqueued batch are complete in
+ * stream order (frames the per-frame kernel flagged are finished when their batch is fetched or retired, as without the
+ * flag).  A no-op otherwise. */
 HV_API hv_status hv_flush(hv_ctx *ctx);
 /* Results of a batch enqueued with hv_enqueue_device, by ticket: blocks until its read-back has arrived.
  * HV_ERR_BAD_TICKET once the batch's scratch set has been reused (more than hv_pipeline_depth() - 1 batches later). */
